@@ -1,0 +1,184 @@
+/*
+ * lgdwt_b200.h — C ABI of the B200-native LGDWT-GS hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every entry point names the
+ * reference interface it replaces (paths relative to /root/reference, prefixes as in SURVEY.md:
+ *   DGR/ = fs3dgs_benchmark/gaussian-splatting/submodules/diff-gaussian-rasterization/
+ *   KNN/ = fs3dgs_benchmark/gaussian-splatting/submodules/simple-knn/
+ *   LG/  = fs3dgs_benchmark/LGDWT-GS/ ).
+ *
+ * Conventions
+ *   - all pointers except `*_ctx`, `num_rendered` and `out_host_*` are DEVICE pointers on the current device;
+ *   - tensors are dense, row-major fp32 unless stated; indices / counters are 32-bit;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, what the reference uses);
+ *   - every function returns LG_OK (0) or an error code; lg_last_error() returns the message of the calling
+ *     thread's last failure.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef LGDWT_B200_H_INCLUDED
+#define LGDWT_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_ERR_INVALID_ARGUMENT 1
+#define LG_ERR_CUDA 2
+#define LG_ERR_ALLOC 3
+#define LG_ERR_UNSUPPORTED 4
+
+#define LG_ABI_VERSION 1
+
+/* Caller-owned resizable buffer: replaces std::function<char*(size_t)> (DGR/cuda_rasterizer/rasterizer.h:33-35,
+ * DGR/rasterize_points.cu:27-33).  Must return a device pointer to >= bytes bytes (128-byte aligned), or NULL. */
+typedef char* (*lg_alloc_fn)(void* ctx, size_t bytes);
+
+int lg_abi_version(void);
+const char* lg_last_error(void);
+
+/* Sizes of the three opaque state buffers (layout private to the library).  Replaces
+ * CudaRasterizer::required<GeometryState|ImageState|BinningState> (DGR/cuda_rasterizer/rasterizer_impl.h:64-71). */
+size_t lg_geometry_state_bytes(int P, int channels);
+size_t lg_image_state_bytes(int width, int height);
+size_t lg_binning_state_bytes(int num_rendered, int width, int height);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:31-59,
+ * rasterizer_impl.cu:198-341) as bound by RasterizeGaussiansCUDA (DGR/rasterize_points.cu:35-124).
+ *   channels: 3 = the reference NUM_CHANNELS (DGR/cuda_rasterizer/config.h:15); 1..4 supported here.
+ *             SH evaluation needs channels == 3; other counts need colors_precomp (rasterizer_impl.cu:244-247).
+ *   shs (P,M,3) or NULL; colors_precomp (P,channels) or NULL; scales (P,3)+rotations (P,4) or cov3D_precomp (P,6).
+ *   out_color (channels,H,W); out_invdepth (1,H,W) or NULL; radii (P) int32 or NULL.
+ *   *num_rendered receives the number of (Gaussian, tile) instances (the reference's return value).  */
+int lg_rasterize_forward(
+    lg_alloc_fn geometry_alloc, void* geometry_ctx,
+    lg_alloc_fn binning_alloc, void* binning_ctx,
+    lg_alloc_fn image_alloc, void* image_ctx,
+    int P, int D, int M, int channels,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_invdepth,
+    int antialiasing,
+    int* radii,
+    int debug,
+    void* stream,
+    int* num_rendered);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (DGR/cuda_rasterizer/rasterizer.h:61-97,
+ * rasterizer_impl.cu:345-450) as bound by RasterizeGaussiansBackwardCUDA (DGR/rasterize_points.cu:126-223).
+ * All dL_* outputs are fully written by the call (zero for invisible Gaussians); the caller does NOT need to
+ * zero them first (the reference requires torch::zeros, rasterize_points.cu:163-172).
+ *   dL_dpix (channels,H,W); dL_dinvdepth_pix (1,H,W) or NULL.
+ *   dL_dmean2D (P,3) [xy in NDC-scaled units, z = 0]; dL_dconic (P,4) [a,b,unused,c as in the reference];
+ *   dL_dopacity (P); dL_dcolor (P,channels); dL_dinvdepth (P) or NULL; dL_dmean3D (P,3); dL_dcov3D (P,6);
+ *   dL_dsh (P,M,3) or NULL; dL_dscale (P,3); dL_drot (P,4).  */
+int lg_rasterize_backward(
+    int P, int D, int M, int R, int channels,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geometry_state,
+    char* binning_state,
+    char* image_state,
+    const float* dL_dpix,
+    const float* dL_dinvdepth_pix,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dinvdepth,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    int antialiasing,
+    int debug,
+    void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (DGR/cuda_rasterizer/rasterizer.h:24-29,
+ * rasterizer_impl.cu:54-66,141-153; torch glue DGR/rasterize_points.cu:225-244).  present: (P) uint8/bool. */
+int lg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, void* stream);
+
+/* Test/inspection access to the opaque state (what a `ref_probe` reads out of the reference buffers through
+ * GeometryState/ImageState/BinningState::fromChunk, DGR/cuda_rasterizer/rasterizer_impl.cu:155-194).
+ * Each call copies one named array into a caller-provided DEVICE buffer of the documented size:
+ *   "depths" f32[P]  "means2D" f32[2P]  "cov3D" f32[6P]  "conic_opacity" f32[4P]  "rgb" f32[channels*P]
+ *   "clamped" u8[3P]  "tiles_touched" u32[P]  "point_offsets" u32[P]
+ *   "final_T" f32[W*H]  "n_contrib" u32[W*H]  "ranges" u32[2*T]
+ *   "point_list" u32[R]  "point_list_keys" u64[R]                                                       */
+int lg_state_read(const char* name, int P, int channels, int width, int height, int R,
+                  const char* geometry_state, const char* binning_state, const char* image_state,
+                  void* dst, size_t dst_bytes, void* stream);
+
+/* Replaces SimpleKNN::knn (KNN/simple_knn.cu:186-222) as bound by distCUDA2 (KNN/spatial.cu:16-26):
+ * mean squared distance to the 3 nearest neighbours.  points (P,3); mean_dists (P).
+ * workspace: device scratch of >= lg_knn_workspace_bytes(P) bytes (the reference cudaMallocs internally). */
+size_t lg_knn_workspace_bytes(int P);
+int lg_knn_mean_dist2(int P, const float* points, float* mean_dists, char* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Fused Haar-DWT loss.  Replaces the PyTorch op chain LG/train.py:131-180 built from
+ * get_dwt_subbands (LG/utils/loss_utils.py:106-153), l1_loss (:40-41), compute_elf_map (:336-366) and
+ * compute_patch_dwt_loss (:368-442) on one (1,C,H,W) render/GT pair.
+ *   band_weights[8]: LL1,LH1,HL1,HH1,LL2,LH2,HL2,HH2 (LG/arguments/__init__.py:103-114).
+ *   patch_size / percentile / patch_w_lh / patch_w_hl: LG/arguments/__init__.py:116-121; patch_size <= 0
+ *   disables the patch term.
+ *   out_losses (device, 12 floats): [0] weighted global DWT loss, [1] patch loss, [2..9] the eight unweighted
+ *   band L1 means, [10] number of selected patches, [11] ELF threshold.
+ *   patch_mask (device, u8[ceil-free floor(H/ps)*floor(W/ps)]) receives the ELF selection (1 = selected).
+ *   workspace: device scratch of >= lg_dwt_workspace_bytes(C,H,W,patch_size) bytes.
+ * The backward writes dL/dpred (C,H,W) for loss = g_dwt * out[0] + g_patch * out[1], using the mask and
+ * selection count produced by the forward call on the same workspace.                                     */
+size_t lg_dwt_workspace_bytes(int C, int H, int W, int patch_size);
+int lg_dwt_loss_forward(const float* pred, const float* gt, int C, int H, int W,
+                        const float* band_weights_host, int patch_size, double percentile,
+                        float patch_w_lh, float patch_w_hl,
+                        float* out_losses, uint8_t* patch_mask,
+                        char* workspace, size_t workspace_bytes, void* stream);
+int lg_dwt_loss_backward(const float* pred, const float* gt, int C, int H, int W,
+                         const float* band_weights_host, int patch_size,
+                         float patch_w_lh, float patch_w_hl,
+                         const float* g_dwt_dev, const float* g_patch_dev,
+                         const uint8_t* patch_mask, const float* out_losses,
+                         float* dL_dpred, void* stream);
+
+/* Single-level Haar analysis (the pytorch_wavelets.DWTForward(J=1,'symmetric','db1') call sites at
+ * LG/utils/loss_utils.py:140-148).  x (N*C,H,W) -> ll (N*C,H2,W2), yh (N*C,3,H2,W2) with H2=(H+1)/2.
+ * and its adjoint (for autograd through the compat module).                                              */
+int lg_haar_dwt2_forward(const float* x, int planes, int H, int W, float* ll, float* yh, void* stream);
+int lg_haar_dwt2_backward(const float* g_ll, const float* g_yh, int planes, int H, int W, float* g_x, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGDWT_B200_H_INCLUDED */

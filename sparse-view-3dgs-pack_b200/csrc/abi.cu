@@ -1,0 +1,284 @@
+// abi.cu — the extern "C" boundary declared in include/lgdwt_b200.h: argument validation, opaque-state layout,
+// stage orchestration (the job of CudaRasterizer::Rasterizer::forward/backward,
+// DGR/cuda_rasterizer/rasterizer_impl.cu:198-450) and error reporting.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace lg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return LG_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- opaque state layouts
+GeometryState GeometryState::from_chunk(char*& chunk, size_t P, int channels) {
+    GeometryState g;
+    const size_t blocks = (P + 255) / 256;
+    carve(chunk, g.depths, P);
+    carve(chunk, g.clamped, P * 3);
+    carve(chunk, g.internal_radii, P);
+    carve(chunk, g.means2D, P);
+    carve(chunk, g.cov3D, P * 6);
+    carve(chunk, g.conic_opacity, P);
+    carve(chunk, g.rgb, P * (size_t)channels);
+    carve(chunk, g.tiles_touched, P);
+    carve(chunk, g.point_offsets, P);
+    carve(chunk, g.scan_state, blocks + 1);
+    carve(chunk, g.counters, 8);
+    carve(chunk, g.grad_scratch, P * 12);
+    return g;
+}
+size_t geometry_state_bytes(size_t P, int channels) {
+    char* p = nullptr;
+    GeometryState::from_chunk(p, P, channels);
+    return (size_t)p + 128;
+}
+
+ImageState ImageState::from_chunk(char*& chunk, size_t W, size_t H) {
+    ImageState s;
+    const size_t T = (size_t)num_tiles_x((int)W) * num_tiles_y((int)H);
+    carve(chunk, s.accum_alpha, W * H);
+    carve(chunk, s.n_contrib, W * H);
+    carve(chunk, s.ranges, T);
+    return s;
+}
+size_t image_state_bytes(size_t W, size_t H) {
+    char* p = nullptr;
+    ImageState::from_chunk(p, W, H);
+    return (size_t)p + 128;
+}
+
+BinningState BinningState::from_chunk(char*& chunk, size_t R) {
+    BinningState b;
+    carve(chunk, b.point_list, R);
+    carve(chunk, b.point_list_unsorted, R);
+    carve(chunk, b.point_list_keys, R);
+    carve(chunk, b.point_list_keys_unsorted, R);
+    b.sort_temp_bytes = radix_sort_temp_bytes(R, 8);
+    carve(chunk, b.sort_temp, b.sort_temp_bytes);
+    return b;
+}
+size_t binning_state_bytes(size_t R) {
+    char* p = nullptr;
+    BinningState::from_chunk(p, R);
+    return (size_t)p + 128;
+}
+
+static thread_local uint32_t* g_pinned_word = nullptr;  // pinned staging for the num_rendered read-back
+
+}  // namespace lg
+
+using namespace lg;
+
+extern "C" {
+
+int lg_abi_version(void) { return LG_ABI_VERSION; }
+const char* lg_last_error(void) { return lg::g_err; }
+
+size_t lg_geometry_state_bytes(int P, int channels) { return geometry_state_bytes((size_t)P, channels); }
+size_t lg_image_state_bytes(int width, int height) { return image_state_bytes((size_t)width, (size_t)height); }
+size_t lg_binning_state_bytes(int num_rendered, int width, int height) {
+    (void)width; (void)height;
+    return binning_state_bytes((size_t)num_rendered);
+}
+
+int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_alloc_fn binning_alloc, void* binning_ctx,
+                         lg_alloc_fn image_alloc, void* image_ctx, int P, int D, int M, int channels,
+                         const float* background, int width, int height, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* opacities, const float* scales,
+                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                         float tan_fovy, int prefiltered, float* out_color, float* out_invdepth, int antialiasing,
+                         int* radii, int debug, void* stream_v, int* num_rendered) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (num_rendered) *num_rendered = 0;
+    if (P < 0 || width <= 0 || height <= 0 || !geometry_alloc || !binning_alloc || !image_alloc || !num_rendered) {
+        set_error("lg_rasterize_forward: invalid sizes or missing allocator");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (channels < 1 || channels > LG_MAX_CHANNELS) {
+        set_error("lg_rasterize_forward: channels must be in [1,%d], got %d", LG_MAX_CHANNELS, channels);
+        return LG_ERR_UNSUPPORTED;
+    }
+    if (channels != 3 && colors_precomp == nullptr) {
+        // same message as the reference (rasterizer_impl.cu:244-247)
+        set_error("For non-RGB, provide precomputed Gaussian colors!");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (!background || !out_color || !viewmatrix || !projmatrix || !cam_pos) {
+        set_error("lg_rasterize_forward: null camera/background/output pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return LG_OK;  // reference: outputs keep their fill values (rasterize_points.cu:87-123)
+    if (!means3D || !opacities || (!shs && !colors_precomp) || (!cov3D_precomp && (!scales || !rotations))) {
+        set_error("lg_rasterize_forward: missing Gaussian parameter array");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (colors_precomp == nullptr && (M <= 0 || (D + 1) * (D + 1) > M)) {
+        set_error("lg_rasterize_forward: SH degree %d needs %d coefficients, tensor has %d", D, (D + 1) * (D + 1), M);
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+
+    char* gchunk = geometry_alloc(geometry_ctx, geometry_state_bytes((size_t)P, channels));
+    char* ichunk = image_alloc(image_ctx, image_state_bytes((size_t)width, (size_t)height));
+    if (!gchunk || !ichunk) {
+        set_error("lg_rasterize_forward: state allocation callback returned NULL");
+        return LG_ERR_ALLOC;
+    }
+    GeometryState g = GeometryState::from_chunk(gchunk, (size_t)P, channels);
+    ImageState img = ImageState::from_chunk(ichunk, (size_t)width, (size_t)height);
+    if (radii == nullptr) radii = g.internal_radii;
+
+    ForwardArgs f;
+    f.P = P; f.D = D; f.M = M; f.C = channels; f.background = background; f.W = width; f.H = height;
+    f.means3D = means3D; f.shs = shs; f.colors_precomp = colors_precomp; f.opacities = opacities; f.scales = scales;
+    f.scale_modifier = scale_modifier; f.rotations = rotations; f.cov3D_precomp = cov3D_precomp;
+    f.viewmatrix = viewmatrix; f.projmatrix = projmatrix; f.cam_pos = cam_pos; f.tan_fovx = tan_fovx;
+    f.tan_fovy = tan_fovy;
+    f.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:224-225
+    f.focal_x = width / (2.0f * tan_fovx);
+    f.prefiltered = prefiltered != 0; f.antialiasing = antialiasing != 0; f.debug = debug != 0;
+
+    int rc = launch_preprocess(f, g, radii, stream);
+    if (rc != LG_OK) return rc;
+
+    // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288)
+    if (!g_pinned_word) LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
+    LG_CUDA(cudaMemcpyAsync(g_pinned_word, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LG_CUDA(cudaStreamSynchronize(stream));
+    const int R = (int)*g_pinned_word;
+    *num_rendered = R;
+
+    char* bchunk = binning_alloc(binning_ctx, binning_state_bytes((size_t)R));
+    if (!bchunk) {
+        set_error("lg_rasterize_forward: binning allocation callback returned NULL");
+        return LG_ERR_ALLOC;
+    }
+    BinningState b = BinningState::from_chunk(bchunk, (size_t)R);
+    rc = launch_binning(P, R, width, height, g, radii, b, img, f.debug, stream);
+    if (rc != LG_OK) return rc;
+
+    const float* features = colors_precomp ? colors_precomp : g.rgb;
+    return launch_blend_forward(channels, width, height, g, b, img, features, background, out_color, out_invdepth,
+                                f.debug, stream);
+}
+
+int lg_rasterize_backward(int P, int D, int M, int R, int channels, const float* background, int width, int height,
+                          const float* means3D, const float* shs, const float* colors_precomp,
+                          const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                          const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geometry_state,
+                          char* binning_state, char* image_state, const float* dL_dpix,
+                          const float* dL_dinvdepth_pix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                          float* dL_dcolor, float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                          float* dL_dscale, float* dL_drot, int antialiasing, int debug, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (P < 0 || R < 0 || width <= 0 || height <= 0 || channels < 1 || channels > LG_MAX_CHANNELS) {
+        set_error("lg_rasterize_backward: invalid sizes");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return LG_OK;
+    if (!geometry_state || !binning_state || !image_state || !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor ||
+        !dL_dmean3D || !dL_dcov3D || !means3D || !opacities || !background || !viewmatrix || !projmatrix || !campos) {
+        set_error("lg_rasterize_backward: missing required pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if ((!cov3D_precomp && (!scales || !rotations || !dL_dscale || !dL_drot)) || (shs && !dL_dsh)) {
+        set_error("lg_rasterize_backward: missing parameter / gradient array for the active input path");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    char* gp = geometry_state;
+    char* bp = binning_state;
+    char* ip = image_state;
+    GeometryState g = GeometryState::from_chunk(gp, (size_t)P, channels);
+    BinningState b = BinningState::from_chunk(bp, (size_t)R);
+    ImageState img = ImageState::from_chunk(ip, (size_t)width, (size_t)height);
+    if (radii == nullptr) radii = g.internal_radii;
+    const float* features = colors_precomp ? colors_precomp : g.rgb;
+
+    int rc = launch_blend_backward(P, channels, width, height, g, b, img, features, background, dL_dpix,
+                                   dL_dinvdepth_pix, g.grad_scratch, debug != 0, stream);
+    if (rc != LG_OK) return rc;
+
+    BackwardArgs a;
+    a.P = P; a.D = D; a.M = M; a.C = channels; a.W = width; a.H = height; a.means3D = means3D; a.shs = shs;
+    a.colors_precomp = colors_precomp; a.opacities = opacities; a.scales = cov3D_precomp ? nullptr : scales;
+    a.scale_modifier = scale_modifier; a.rotations = cov3D_precomp ? nullptr : rotations;
+    a.cov3D_precomp = cov3D_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.campos = campos;
+    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.focal_y = height / (2.0f * tan_fovy);
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.antialiasing = antialiasing != 0; a.has_invdepth = dL_dinvdepth_pix != nullptr;
+    a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+    a.dL_dinvdepth = dL_dinvdepth; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
+    a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+    return launch_preprocess_backward(a, g, radii, debug != 0, stream);
+}
+
+int lg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                    void* stream_v) {
+    (void)projmatrix;  // the reference computes p_proj and never uses it (auxiliary.h:163, nvcc warning #177)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("lg_mark_visible: invalid arguments");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return LG_OK;
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_v);
+}
+
+int lg_state_read(const char* name, int P, int channels, int width, int height, int R, const char* geometry_state,
+                  const char* binning_state, const char* image_state, void* dst, size_t dst_bytes, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const size_t N = (size_t)width * height, T = (size_t)num_tiles_x(width) * num_tiles_y(height);
+    if (geometry_state) {
+        char* p = const_cast<char*>(geometry_state);
+        GeometryState g = GeometryState::from_chunk(p, (size_t)P, channels);
+        if (!strcmp(name, "depths")) { src = g.depths; bytes = 4 * (size_t)P; }
+        else if (!strcmp(name, "means2D")) { src = g.means2D; bytes = 8 * (size_t)P; }
+        else if (!strcmp(name, "cov3D")) { src = g.cov3D; bytes = 24 * (size_t)P; }
+        else if (!strcmp(name, "conic_opacity")) { src = g.conic_opacity; bytes = 16 * (size_t)P; }
+        else if (!strcmp(name, "rgb")) { src = g.rgb; bytes = 4 * (size_t)channels * P; }
+        else if (!strcmp(name, "clamped")) { src = g.clamped; bytes = 3 * (size_t)P; }
+        else if (!strcmp(name, "tiles_touched")) { src = g.tiles_touched; bytes = 4 * (size_t)P; }
+        else if (!strcmp(name, "point_offsets")) { src = g.point_offsets; bytes = 4 * (size_t)P; }
+        else if (!strcmp(name, "grad_record")) { src = g.grad_scratch; bytes = 48 * (size_t)P; }
+    }
+    if (!src && image_state) {
+        char* p = const_cast<char*>(image_state);
+        ImageState s = ImageState::from_chunk(p, (size_t)width, (size_t)height);
+        if (!strcmp(name, "final_T")) { src = s.accum_alpha; bytes = 4 * N; }
+        else if (!strcmp(name, "n_contrib")) { src = s.n_contrib; bytes = 4 * N; }
+        else if (!strcmp(name, "ranges")) { src = s.ranges; bytes = 8 * T; }
+    }
+    if (!src && binning_state) {
+        char* p = const_cast<char*>(binning_state);
+        BinningState b = BinningState::from_chunk(p, (size_t)R);
+        if (!strcmp(name, "point_list")) { src = b.point_list; bytes = 4 * (size_t)R; }
+        else if (!strcmp(name, "point_list_keys")) { src = b.point_list_keys; bytes = 8 * (size_t)R; }
+    }
+    if (!src) {
+        set_error("lg_state_read: unknown array '%s' (or its state buffer was not given)", name);
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (dst_bytes < bytes) {
+        set_error("lg_state_read: '%s' needs %zu bytes, destination has %zu", name, bytes, dst_bytes);
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (bytes) LG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
+    return LG_OK;
+}
+
+}  // extern "C"

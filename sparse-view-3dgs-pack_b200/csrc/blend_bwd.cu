@@ -1,0 +1,193 @@
+// blend_bwd.cu — per-tile back-to-front replay of the alpha blend (backward).  Replaces renderCUDA<C> in
+// DGR/cuda_rasterizer/backward.cu:452-638.
+//
+// The reference issues 9-10 global atomicAdds per (pixel, Gaussian) hit.  Here the 32 pixels of a warp (an 8x4
+// patch) reduce their 7+C partial gradients with a halving butterfly (12 shuffles for 10 values instead of 50),
+// after which 7+C *different lanes* each own one total and issue ONE coalesced red.global.add per warp into a
+// packed 12-float per-Gaussian record.  Warps in which no pixel hits the Gaussian skip everything after a ballot,
+// and list entries behind the last contributor of every pixel of the tile are never even staged.
+#include "common.cuh"
+
+namespace lg {
+
+#define BWD_BATCH 256
+#define LG_REC 12  // floats per packed gradient record: mean2D.xy, conic.xyw, opacity, invdepth, colour[C], pad
+
+// Sum N per-lane values over the 32 lanes of a warp.  On return lane L holds in `out` the warp total of value
+// `idx` (idx < N valid); lanes whose slot is padding get valid=false.
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, float& out, int& idx, bool& valid) {
+    int n = N;        // padded slot count at this stage (compile-time after unrolling)
+    int cnt = N;      // true slot count of this lane's group
+    int base = 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+        if (n > 1) {
+            const int h = (n + 1) / 2;
+#pragma unroll
+            for (int k = 0; k < h; k++) {
+                const float lo = v[k];
+                const float hi = (k + h < n) ? v[k + h] : 0.0f;
+                const float send = upper ? lo : hi;
+                const float keep = upper ? hi : lo;
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+            if (upper) { base += h; cnt -= h; } else { cnt = min(cnt, h); }
+            n = h;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+    out = v[0];
+    idx = base;
+    valid = cnt >= 1;
+}
+
+template <int C, bool INVD>
+__global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
+    const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec) {
+    constexpr int NV = 7 + C;
+    __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ float2 s_xy[BWD_BATCH];
+    __shared__ float4 s_co[BWD_BATCH];
+    __shared__ float s_feat[BWD_BATCH * (C + 1)];
+    __shared__ uint32_t s_max;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
+    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
+    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+    const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.0f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    const uint32_t warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0 && warp_max) atomicMax(&s_max, warp_max);
+    __syncthreads();
+    const uint32_t n_eff = s_max;  // entries [0, n_eff) of this tile's list can contribute to some pixel
+    if (n_eff == 0) return;
+
+    float dL_dpixel[C];
+    float accum_rec[C], last_color[C];
+    float bg_dot_dpixel = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        dL_dpixel[c] = inside ? dL_dpixels[(size_t)c * H * W + pix_id] : 0.0f;
+        accum_rec[c] = 0.0f;
+        last_color[c] = 0.0f;
+        bg_dot_dpixel += bg_color[c] * dL_dpixel[c];
+    }
+    float dL_invd = 0.0f, accum_invd_rec = 0.0f, last_invd = 0.0f;
+    if (INVD) dL_invd = inside ? dL_dinvdepth_pix[pix_id] : 0.0f;
+    float last_alpha = 0.0f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    const int rounds = (int)((n_eff + BWD_BATCH - 1) / BWD_BATCH);
+    for (int i = 0; i < rounds; i++) {
+        __syncthreads();
+        const uint32_t progress = (uint32_t)i * BWD_BATCH + tid;
+        if (progress < n_eff) {
+            const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
+            s_id[tid] = id;
+            s_xy[tid] = means2D[id];
+            s_co[tid] = conic_opacity[id];
+#pragma unroll
+            for (int c = 0; c < C; c++) s_feat[tid * (C + 1) + c] = colors[(size_t)id * C + c];
+            if (INVD) s_feat[tid * (C + 1) + C] = 1.0f / depths[id];
+        }
+        __syncthreads();
+        const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - (uint32_t)i * BWD_BATCH);
+        for (int j = 0; j < batch; j++) {
+            const uint32_t rel = n_eff - 1u - ((uint32_t)i * BWD_BATCH + (uint32_t)j);  // 0-based position in the list
+            if (rel >= warp_max) continue;  // behind every pixel's last contributor in this warp (warp-uniform)
+            const float2 xy = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
+            const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
+            const float power = F_SUB(F_MUL(q, -0.5f), F_MUL(dy, F_MUL(dx, co.y)));
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, F_MUL(co.w, G));
+            const bool hit = rel < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
+
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; k++) v[k] = 0.0f;
+            if (hit) {
+                T = T / (1.0f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.0f;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const float col = s_feat[j * (C + 1) + c];
+                    accum_rec[c] = last_alpha * last_color[c] + (1.0f - last_alpha) * accum_rec[c];
+                    last_color[c] = col;
+                    dL_dalpha += (col - accum_rec[c]) * dL_dpixel[c];
+                    v[7 + c] = dchannel_dcolor * dL_dpixel[c];
+                }
+                if (INVD) {
+                    const float invd = s_feat[j * (C + 1) + C];
+                    accum_invd_rec = last_alpha * last_invd + (1.0f - last_alpha) * accum_invd_rec;
+                    last_invd = invd;
+                    dL_dalpha += (invd - accum_invd_rec) * dL_invd;
+                    v[6] = dchannel_dcolor * dL_invd;
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
+                const float dL_dG = co.w * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                const float dG_ddely = -gdy * co.z - gdx * co.y;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+            }
+            float total;
+            int slot;
+            bool ok;
+            warp_multi_reduce<NV>(v, lane, total, slot, ok);
+            if (ok && (INVD || slot != 6)) atomicAdd(grad_rec + (size_t)s_id[j] * LG_REC + slot, total);
+        }
+    }
+}
+
+int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, const BinningState& b,
+                          const ImageState& img, const float* features, const float* background,
+                          const float* dL_dpix, const float* dL_dinvdepth_pix, float* grad_scratch, bool debug,
+                          cudaStream_t stream) {
+    LG_CUDA(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * LG_REC * (size_t)P, stream));
+    const dim3 grid(num_tiles_x(W), num_tiles_y(H), 1), block(LG_TILE_PIX, 1, 1);
+#define LG_LAUNCH_BWD(CH, INVD)                                                                                    \
+    blend_backward_kernel<CH, INVD><<<grid, block, 0, stream>>>(                                                     \
+        img.ranges, b.point_list, W, H, (int)grid.x, background, g.means2D, g.conic_opacity, features, g.depths,     \
+        img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch)
+    const bool invd = dL_dinvdepth_pix != nullptr;
+    switch (C) {
+        case 1: if (invd) LG_LAUNCH_BWD(1, true); else LG_LAUNCH_BWD(1, false); break;
+        case 2: if (invd) LG_LAUNCH_BWD(2, true); else LG_LAUNCH_BWD(2, false); break;
+        case 3: if (invd) LG_LAUNCH_BWD(3, true); else LG_LAUNCH_BWD(3, false); break;
+        case 4: if (invd) LG_LAUNCH_BWD(4, true); else LG_LAUNCH_BWD(4, false); break;
+        default: set_error("blend backward: unsupported channel count %d", C); return LG_ERR_UNSUPPORTED;
+    }
+#undef LG_LAUNCH_BWD
+    LG_LAUNCH_CHECK(debug, stream);
+    return LG_OK;
+}
+
+}  // namespace lg

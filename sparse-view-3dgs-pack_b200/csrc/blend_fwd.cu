@@ -1,0 +1,126 @@
+// blend_fwd.cu — per-tile front-to-back alpha blending (forward).  Replaces renderCUDA<NUM_CHANNELS>
+// (DGR/cuda_rasterizer/forward.cu:274-397), generalised to C = 1..4 channels.
+//
+// Bit-exact contract: the power / alpha / test_T chain decides n_contrib and final_T, so it is evaluated with the
+// exact operation order of the reference's sm_100a build and the same libdevice expf (this file
+// must never be compiled with --use_fast_math).  Only the thread->pixel mapping and the data staging differ:
+//  - a warp covers an 8x4 pixel patch (better hit coherence than the reference's 16x2 rows);
+//  - colours and 1/depth are staged in shared memory with the geometry, so a hit never touches global memory
+//    (the reference gathers features[] / depths[] per hit, forward.cu:372,375).
+#include "common.cuh"
+
+namespace lg {
+
+#define BLEND_BATCH 256
+
+template <int C>
+struct FeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
+
+template <int C>
+__global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
+    const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth) {
+    constexpr int FS = FeatStride<C>::value;
+    __shared__ float2 s_xy[BLEND_BATCH];
+    __shared__ float4 s_co[BLEND_BATCH];
+    __shared__ __align__(16) float s_feat[BLEND_BATCH * FS];  // C colours then 1/depth
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
+    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
+    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+
+    const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
+    const int rounds = (int)((range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH);
+    int to_do = (int)(range.y - range.x);
+
+    bool done = !inside;
+    float T = 1.0f;
+    uint32_t contributor = 0, last_contributor = 0;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] = 0.0f;
+    float acc_invd = 0.0f;
+
+    for (int i = 0; i < rounds; i++, to_do -= BLEND_BATCH) {
+        if (__syncthreads_count(done) == LG_TILE_PIX) break;
+        const uint32_t progress = (uint32_t)i * BLEND_BATCH + tid;
+        if (range.x + progress < range.y) {
+            const uint32_t id = point_list[range.x + progress];
+            s_xy[tid] = means2D[id];
+            s_co[tid] = conic_opacity[id];
+#pragma unroll
+            for (int c = 0; c < C; c++) s_feat[tid * FS + c] = features[(size_t)id * C + c];
+            s_feat[tid * FS + C] = F_RCP(depths[id]);
+        }
+        __syncthreads();
+        const int batch = min(BLEND_BATCH, to_do);
+        for (int j = 0; !done && j < batch; j++) {
+            contributor++;
+            const float2 xy = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
+            // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
+            const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
+            const float power = F_SUB(F_MUL(q, -0.5f), F_MUL(dy, F_MUL(dx, co.y)));
+            if (power > 0.0f) continue;
+            const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+            if (test_T < 0.0001f) {
+                done = true;
+                continue;
+            }
+            if constexpr (FS == 4) {
+                const float4 f = *reinterpret_cast<const float4*>(&s_feat[j * 4]);
+                const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
+                acc_invd = F_FMA(T, F_MUL(alpha, fv[C]), acc_invd);
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(&s_feat[j * 8]);
+                const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
+                acc_invd = F_FMA(T, F_MUL(alpha, s_feat[j * 8 + C]), acc_invd);
+            }
+            T = test_T;
+            last_contributor = contributor;
+        }
+    }
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+#pragma unroll
+        for (int c = 0; c < C; c++) out_color[(size_t)c * H * W + pix_id] = F_FMA(T, bg_color[c], acc[c]);
+        if (out_invdepth) out_invdepth[pix_id] = acc_invd;
+    }
+}
+
+int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
+                         const float* features, const float* background, float* out_color, float* out_invdepth,
+                         bool debug, cudaStream_t stream) {
+    const dim3 grid(num_tiles_x(W), num_tiles_y(H), 1), block(LG_TILE_PIX, 1, 1);
+#define LG_LAUNCH_FWD(CH)                                                                                          \
+    blend_forward_kernel<CH><<<grid, block, 0, stream>>>(img.ranges, b.point_list, W, H, (int)grid.x, g.means2D,     \
+                                                         features, g.conic_opacity, g.depths, img.accum_alpha,       \
+                                                         img.n_contrib, background, out_color, out_invdepth)
+    switch (C) {
+        case 1: LG_LAUNCH_FWD(1); break;
+        case 2: LG_LAUNCH_FWD(2); break;
+        case 3: LG_LAUNCH_FWD(3); break;
+        case 4: LG_LAUNCH_FWD(4); break;
+        default: set_error("blend forward: unsupported channel count %d", C); return LG_ERR_UNSUPPORTED;
+    }
+#undef LG_LAUNCH_FWD
+    LG_LAUNCH_CHECK(debug, stream);
+    return LG_OK;
+}
+
+}  // namespace lg

@@ -1,0 +1,199 @@
+// common.cuh — shared declarations for the B200-native LGDWT-GS hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include "../../include/lgdwt_b200.h"
+
+#define LG_TILE_X 16
+#define LG_TILE_Y 16
+#define LG_TILE_PIX (LG_TILE_X * LG_TILE_Y)
+#define LG_MAX_CHANNELS 4
+#define LG_NUM_SMS 148
+
+namespace lg {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define LG_CUDA(call)                                                            \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess) return lg::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// After a kernel launch: always catch launch-configuration errors; with debug also sync and check
+// (the reference's CHECK_CUDA(debug) behaviour, DGR/cuda_rasterizer/auxiliary.h:178-185).
+#define LG_LAUNCH_CHECK(debug, stream)                                           \
+    do {                                                                         \
+        LG_CUDA(cudaGetLastError());                                             \
+        if (debug) LG_CUDA(cudaStreamSynchronize(stream));                       \
+    } while (0)
+
+// ---------------------------------------------------------------- opaque state layouts
+template <typename T>
+static inline void carve(char*& chunk, T*& ptr, size_t count, size_t alignment = 128) {
+    size_t offset = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(alignment - 1);
+    ptr = reinterpret_cast<T*>(offset);
+    chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+// Per-Gaussian state (P-sized).  Same information as the reference GeometryState
+// (DGR/cuda_rasterizer/rasterizer_impl.h:32-46) in a layout of our own.
+struct GeometryState {
+    float* depths;            // P
+    uint8_t* clamped;         // 3P (SH clamp flags)
+    int* internal_radii;      // P
+    float2* means2D;          // P
+    float* cov3D;             // 6P
+    float4* conic_opacity;    // P
+    float* rgb;               // channels * P
+    uint32_t* tiles_touched;  // P
+    uint32_t* point_offsets;  // P (inclusive scan of tiles_touched)
+    unsigned long long* scan_state;  // one descriptor per 256-Gaussian block (decoupled look-back)
+    uint32_t* counters;       // [0] ticket, [1] num_rendered, [2..] spare
+    float* grad_scratch;      // backward only: 12 floats / Gaussian packed 2-D gradient record
+    static GeometryState from_chunk(char*& chunk, size_t P, int channels);
+};
+size_t geometry_state_bytes(size_t P, int channels);
+
+struct ImageState {
+    float* accum_alpha;   // W*H final transmittance
+    uint32_t* n_contrib;  // W*H
+    uint2* ranges;        // T
+    static ImageState from_chunk(char*& chunk, size_t W, size_t H);
+};
+size_t image_state_bytes(size_t W, size_t H);
+
+struct BinningState {
+    uint32_t* point_list;            // R sorted Gaussian ids
+    uint32_t* point_list_unsorted;   // R
+    uint64_t* point_list_keys;       // R sorted keys
+    uint64_t* point_list_keys_unsorted;  // R
+    char* sort_temp;                 // radix-sort scratch
+    size_t sort_temp_bytes;
+    static BinningState from_chunk(char*& chunk, size_t R);
+};
+size_t binning_state_bytes(size_t R);
+
+static inline int num_tiles_x(int W) { return (W + LG_TILE_X - 1) / LG_TILE_X; }
+static inline int num_tiles_y(int H) { return (H + LG_TILE_Y - 1) / LG_TILE_Y; }
+
+// ---------------------------------------------------------------- stage entry points (host side)
+struct ForwardArgs {
+    int P, D, M, C;
+    const float* background;
+    int W, H;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;
+    bool prefiltered;
+    bool antialiasing;
+    bool debug;
+};
+
+int launch_preprocess(const ForwardArgs& a, GeometryState& g, int* radii, cudaStream_t stream);
+int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
+                   ImageState& img, bool debug, cudaStream_t stream);
+int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
+                         const float* features, const float* background, float* out_color, float* out_invdepth,
+                         bool debug, cudaStream_t stream);
+int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, const BinningState& b,
+                          const ImageState& img, const float* features, const float* background,
+                          const float* dL_dpix, const float* dL_dinvdepth_pix, float* grad_scratch, bool debug,
+                          cudaStream_t stream);
+
+struct BackwardArgs {
+    int P, D, M, C;
+    int W, H;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;
+    bool antialiasing;
+    bool has_invdepth;
+    float* dL_dmean2D;
+    float* dL_dconic;
+    float* dL_dopacity;
+    float* dL_dcolor;
+    float* dL_dinvdepth;
+    float* dL_dmean3D;
+    float* dL_dcov3D;
+    float* dL_dsh;
+    float* dL_dscale;
+    float* dL_drot;
+};
+int launch_preprocess_backward(const BackwardArgs& a, const GeometryState& g, const int* radii, bool debug,
+                               cudaStream_t stream);
+
+// radix sort (radix_sort.cu).  Input in (keys_a, vals_a); both buffer pairs are clobbered; the sorted result lands
+// in (keys_b, vals_b) when the number of 8-bit passes is odd, else in (keys_a, vals_a) (*result_in_b says which).
+size_t radix_sort_temp_bytes(size_t n, int key_bytes);
+int radix_sort_num_passes(int begin_bit, int end_bit);
+int radix_sort_pairs_u64(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                         int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
+                         bool* result_in_b);
+int radix_sort_pairs_u32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                         int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
+                         bool* result_in_b);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
+
+}  // namespace lg
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+// Explicitly rounded fp32 ops: never re-contracted by nvcc, so the bit-exact contract (read off the
+// reference's sm_100a PTX) survives any restructuring of the surrounding code.
+#define F_MUL(a, b) __fmul_rn((a), (b))
+#define F_ADD(a, b) __fadd_rn((a), (b))
+#define F_SUB(a, b) __fsub_rn((a), (b))
+#define F_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define F_DIV(a, b) __fdiv_rn((a), (b))
+#define F_RCP(a) __frcp_rn((a))
+#define F_SQRT(a) __fsqrt_rn((a))
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// getRect (DGR/cuda_rasterizer/auxiliary.h:45-55) with BLOCK_X = BLOCK_Y = 16: the divisions by 16 are exact
+// multiplies by 0.0625 and `p + r + 15` is evaluated as ((p + r) + 16) - 1 (reference PTX).
+__device__ __forceinline__ void lg_get_rect(float px, float py, int radius, int grid_x, int grid_y, uint32_t& x0,
+                                            uint32_t& y0, uint32_t& x1, uint32_t& y1) {
+    const float r = (float)radius;
+    x0 = min((uint32_t)grid_x, (uint32_t)max(0, __float2int_rz(F_MUL(F_SUB(px, r), 0.0625f))));
+    y0 = min((uint32_t)grid_y, (uint32_t)max(0, __float2int_rz(F_MUL(F_SUB(py, r), 0.0625f))));
+    x1 = min((uint32_t)grid_x,
+             (uint32_t)max(0, __float2int_rz(F_MUL(F_ADD(F_ADD(F_ADD(px, r), 16.0f), -1.0f), 0.0625f))));
+    y1 = min((uint32_t)grid_y,
+             (uint32_t)max(0, __float2int_rz(F_MUL(F_ADD(F_ADD(F_ADD(py, r), 16.0f), -1.0f), 0.0625f))));
+}
+
+// 128-bit read-only streaming load
+__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+#endif

@@ -1,0 +1,301 @@
+// radix_sort.cu — stable LSD radix sort of (key, u32 value) pairs, onesweep style: one up-front histogram of
+// every digit place, then ONE read + ONE write of the pairs per 8-bit digit, with the per-tile digit offsets
+// resolved by a decoupled look-back chain instead of a separate scan pass.
+// Replaces cub::DeviceRadixSort::SortPairs at DGR/cuda_rasterizer/rasterizer_impl.cu:306-311 (u64 tile|depth keys)
+// and KNN/simple_knn.cu:211-214 (u32 Morton codes).
+#include "common.cuh"
+
+namespace lg {
+
+constexpr int RS_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;  // == RS_RADIX: thread d owns digit d in the scan / look-back steps
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_IPT = 16;       // items per thread
+constexpr int RS_TILE = RS_THREADS * RS_IPT;
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr uint32_t LB_PARTIAL = 1u << 30;
+constexpr uint32_t LB_INCLUSIVE = 2u << 30;
+constexpr uint32_t LB_FLAGS = 3u << 30;
+constexpr uint32_t LB_VALUE = ~LB_FLAGS;
+
+// ------------------------------------------------------------------ up-front histogram of all digit places
+template <typename K>
+__global__ void __launch_bounds__(256) rs_histogram_kernel(const K* __restrict__ keys, uint32_t n, int begin_bit,
+                                                           int end_bit, int passes, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_RADIX];
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const K key = keys[i];
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; p++) {
+            if (p < passes) {
+                const int shift = begin_bit + p * RS_BITS;
+                const int nb = min(RS_BITS, end_bit - shift);
+                const uint32_t d = (uint32_t)(key >> shift) & ((1u << nb) - 1u);
+                atomicAdd(&s_hist[p * RS_RADIX + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// exclusive scan of each 256-bin histogram in place; one block per digit place
+__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_warp[RS_WARPS];
+    uint32_t* h = hist + blockIdx.x * RS_RADIX;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t v = h[threadIdx.x];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (unsigned w = 0; w < warp; w++) base += s_warp[w];
+    h[threadIdx.x] = base + incl - v;
+}
+
+// ------------------------------------------------------------------ one digit pass
+template <typename K>
+struct RsSmem {
+    uint32_t warp_hist[RS_WARPS][RS_RADIX];
+    uint32_t tile_excl[RS_RADIX];
+    uint32_t digit_off[RS_RADIX];
+    uint32_t warp_sums[RS_WARPS];
+    uint32_t tile_id;
+    uint32_t vals[RS_TILE];
+    K keys[RS_TILE];
+};
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+                                                                 const uint32_t* __restrict__ vals_in,
+                                                                 uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                                 uint32_t digit_mask,
+                                                                 const uint32_t* __restrict__ global_offsets,
+                                                                 volatile uint32_t* lookback, uint32_t* ticket) {
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    RsSmem<K>& s = *reinterpret_cast<RsSmem<K>*>(rs_smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) s.warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile_id;
+    const uint32_t tile_base = tile * RS_TILE;
+    const uint32_t warp_base = tile_base + warp * (32 * RS_IPT);
+
+    // warp-striped load: item i of this lane is element warp_base + i*32 + lane (order = (warp, i, lane))
+    K key[RS_IPT];
+    uint32_t val[RS_IPT];
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        if (g < n) {
+            key[i] = keys_in[g];
+            val[i] = vals_in[g];
+        } else {
+            key[i] = (K)0;
+            val[i] = 0;
+        }
+    }
+
+    // rank items inside the warp by digit, in order, with match_any groups (stable)
+    uint32_t rank[RS_IPT];
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        const bool valid = g < n;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
+        const unsigned grp = __match_any_sync(0xffffffffu, valid ? d : (RS_RADIX + lane));
+        const unsigned before = grp & lt_mask;
+        uint32_t pre = 0;
+        if (valid) pre = s.warp_hist[warp][d];
+        __syncwarp();
+        if (valid && before == 0) s.warp_hist[warp][d] = pre + __popc(grp);
+        __syncwarp();
+        rank[i] = pre + __popc(before);
+    }
+    __syncthreads();
+
+    // thread d: exclusive scan of digit d over warps -> tile count
+    uint32_t tile_count = 0;
+    {
+        const uint32_t d = tid;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            const uint32_t c = s.warp_hist[w][d];
+            s.warp_hist[w][d] = tile_count;
+            tile_count += c;
+        }
+    }
+    // publish this tile's digit count as early as possible
+    if (tile == 0) lookback[tid] = tile_count | LB_INCLUSIVE;
+    else lookback[(size_t)tile * RS_RADIX + tid] = tile_count | LB_PARTIAL;
+
+    // exclusive scan of tile_count over digits (in-tile bucket starts)
+    uint32_t incl = tile_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) s.warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) wbase += (w < (int)warp) ? s.warp_sums[w] : 0u;
+    const uint32_t excl_in_tile = wbase + incl - tile_count;
+    s.tile_excl[tid] = excl_in_tile;
+
+    // decoupled look-back for digit `tid`
+    uint32_t prev = 0;
+    if (tile > 0) {
+        for (int j = (int)tile - 1; j >= 0; j--) {
+            uint32_t v;
+            do { v = lookback[(size_t)j * RS_RADIX + tid]; } while ((v & LB_FLAGS) == 0u);
+            prev += v & LB_VALUE;
+            if (v & LB_INCLUSIVE) break;
+        }
+        lookback[(size_t)tile * RS_RADIX + tid] = ((prev + tile_count) & LB_VALUE) | LB_INCLUSIVE;
+    }
+    s.digit_off[tid] = global_offsets[tid] + prev - excl_in_tile;
+    __syncthreads();
+
+    // scatter into shared memory in tile-sorted order
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        if (g < n) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
+            const uint32_t q = s.tile_excl[d] + s.warp_hist[warp][d] + rank[i];
+            s.keys[q] = key[i];
+            s.vals[q] = val[i];
+        }
+    }
+    __syncthreads();
+
+    // coalesced write-out: consecutive threads hold consecutive slots of a digit run
+    const uint32_t tile_n = min((uint32_t)RS_TILE, n - tile_base);
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        const uint32_t q = i * RS_THREADS + tid;
+        if (q < tile_n) {
+            const K k = s.keys[q];
+            const uint32_t d = (uint32_t)(k >> shift) & digit_mask;
+            const uint32_t dst = s.digit_off[d] + q;
+            keys_out[dst] = k;
+            vals_out[dst] = s.vals[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host driver
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t radix_sort_temp_bytes(size_t n, int key_bytes) {
+    (void)key_bytes;
+    const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    size_t b = 0;
+    b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * RS_RADIX, 128);          // histograms / global offsets
+    b += align_up(sizeof(uint32_t) * 32, 128);                                // tickets (one per pass)
+    b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * tiles * RS_RADIX, 128);  // look-back descriptors
+    return b + 128;
+}
+
+int radix_sort_num_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + RS_BITS - 1) / RS_BITS; }
+
+// Sorts n pairs on key bits [begin_bit, end_bit).  Input in (keys_a, vals_a); buffers are ping-ponged and BOTH are
+// clobbered.  The sorted result lands in (keys_b, vals_b) when the pass count is odd, else in (keys_a, vals_a);
+// *result_in_b tells which.
+template <typename K>
+static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n, int begin_bit,
+                                 int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
+                                 bool* result_in_b) {
+    const int passes = radix_sort_num_passes(begin_bit, end_bit);
+    *result_in_b = (passes & 1) != 0;
+    if (n == 0 || passes == 0) {
+        *result_in_b = false;
+        return LG_OK;
+    }
+    if (passes > RS_MAX_PASSES) {
+        set_error("radix sort: %d passes requested, max %d", passes, RS_MAX_PASSES);
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (n >= (size_t)LB_VALUE) {
+        set_error("radix sort: n=%zu exceeds 2^30-1", n);
+        return LG_ERR_UNSUPPORTED;
+    }
+    if (temp_bytes < radix_sort_temp_bytes(n, sizeof(K))) {
+        set_error("radix sort: temp buffer too small");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    char* p = temp;
+    uint32_t* hist;
+    uint32_t* tickets;
+    uint32_t* lookback;
+    carve(p, hist, RS_MAX_PASSES * RS_RADIX);
+    carve(p, tickets, 32);
+    carve(p, lookback, RS_MAX_PASSES * tiles * RS_RADIX);
+    const size_t zero_bytes = (size_t)((char*)(lookback + (size_t)passes * tiles * RS_RADIX) - (char*)hist);
+    LG_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, stream));
+
+    const int hist_blocks = (int)min((size_t)LG_NUM_SMS * 8, (n + 255) / 256);
+    rs_histogram_kernel<K><<<hist_blocks, 256, 0, stream>>>(keys_a, (uint32_t)n, begin_bit, end_bit, passes, hist);
+    LG_LAUNCH_CHECK(debug, stream);
+    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, stream>>>(hist);
+    LG_LAUNCH_CHECK(debug, stream);
+
+    static bool attr_set = false;
+    const size_t smem = sizeof(RsSmem<K>);
+    if (!attr_set || true) {
+        LG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    K* src_k = keys_a;
+    K* dst_k = keys_b;
+    uint32_t* src_v = vals_a;
+    uint32_t* dst_v = vals_b;
+    for (int pass = 0; pass < passes; pass++) {
+        const int shift = begin_bit + pass * RS_BITS;
+        const int nb = min(RS_BITS, end_bit - shift);
+        rs_onesweep_kernel<K><<<(unsigned)tiles, RS_THREADS, smem, stream>>>(
+            src_k, dst_k, src_v, dst_v, (uint32_t)n, shift, (1u << nb) - 1u, hist + pass * RS_RADIX,
+            lookback + (size_t)pass * tiles * RS_RADIX, tickets + pass);
+        LG_LAUNCH_CHECK(debug, stream);
+        K* tk = src_k; src_k = dst_k; dst_k = tk;
+        uint32_t* tv = src_v; src_v = dst_v; dst_v = tv;
+    }
+    return LG_OK;
+}
+
+int radix_sort_pairs_u64(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                         int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
+                         bool* result_in_b) {
+    return radix_sort_pairs_impl<unsigned long long>(reinterpret_cast<unsigned long long*>(keys_a),
+                                                     reinterpret_cast<unsigned long long*>(keys_b), vals_a, vals_b, n,
+                                                     begin_bit, end_bit, temp, temp_bytes, debug, stream, result_in_b);
+}
+
+int radix_sort_pairs_u32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                         int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
+                         bool* result_in_b) {
+    return radix_sort_pairs_impl<uint32_t>(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                           debug, stream, result_in_b);
+}
+
+}  // namespace lg

@@ -1,0 +1,184 @@
+"""Drop-in `diff_gaussian_rasterization` operator surface backed by the B200-native C-ABI library.
+
+Mirrors the reference package DGR/dgr_3dgs/__init__.py (GaussianRasterizationSettings :143-156,
+GaussianRasterizer :158-207, _RasterizeGaussians :44-141): same names, argument order, return values
+(color, radii, invdepth), gradient contract and error behaviour, so LG/gaussian_renderer/__init__.py,
+MS/gaussian_renderer/__init__.py, train.py, train_nir.py and render.py run unchanged.
+
+Extensions (not in the reference): colors_precomp may carry 1..4 channels (RGB+NIR in one pass); kernels run on
+the current torch stream instead of the legacy default stream; gradient buffers are not pre-zeroed by the caller.
+`SparseGaussianAdam` is intentionally NOT exported: its presence would switch the callers to the `separate_sh`
+calling convention the bundled reference surface does not have.
+"""
+import ctypes
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from lgdwt_b200 import _lib
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool
+
+
+def _f32c(t):
+    """contiguous fp32 view of an optional tensor (the reference applies .contiguous() at the boundary,
+    DGR/rasterize_points.cu:101-120)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            # same check and exception type as AT_ERROR in DGR/rasterize_points.cu:58-60
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise RuntimeError("diff_gaussian_rasterization (B200-native): tensors must live on a CUDA device; "
+                               "there is no CPU path")
+        device = means3D.device
+        P = means3D.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+
+        means3D_c = _f32c(means3D)
+        sh_c, colors_c = _f32c(sh), _f32c(colors_precomp)
+        opac_c, scales_c, rots_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
+        bg_c, view_c, proj_c, campos_c = _f32c(rs.bg), _f32c(rs.viewmatrix), _f32c(rs.projmatrix), _f32c(rs.campos)
+        channels = 3 if colors_c is None else int(colors_c.size(-1))
+        M = 0 if sh_c is None else int(sh_c.size(1))
+
+        color = torch.zeros((channels, H, W), dtype=torch.float32, device=device)
+        invdepth = torch.zeros((1, H, W), dtype=torch.float32, device=device)
+        radii = torch.zeros((P,), dtype=torch.int32, device=device)
+        geom, binning, img = (_lib.ResizableBuffer(device) for _ in range(3))
+        num_rendered = ctypes.c_int(0)
+        with torch.cuda.device(device):
+            rc = _lib.lib.lg_rasterize_forward(
+                geom.callback, None, binning.callback, None, img.callback, None,
+                P, int(rs.sh_degree), M, channels,
+                _lib.ptr(bg_c), W, H,
+                _lib.ptr(means3D_c), _lib.ptr(sh_c), _lib.ptr(colors_c), _lib.ptr(opac_c), _lib.ptr(scales_c),
+                float(rs.scale_modifier), _lib.ptr(rots_c), _lib.ptr(cov_c),
+                _lib.ptr(view_c), _lib.ptr(proj_c), _lib.ptr(campos_c),
+                float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)),
+                _lib.ptr(color), _lib.ptr(invdepth), int(bool(rs.antialiasing)), _lib.ptr(radii),
+                int(bool(rs.debug)), _lib.stream_ptr(device), ctypes.byref(num_rendered))
+        _lib.check(rc, RuntimeError)
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered.value
+        ctx.channels = channels
+        ctx.M = M
+        ctx.cam = (bg_c, view_c, proj_c, campos_c)
+        ctx.had = (sh is not None and sh.numel() > 0, colors_precomp is not None and colors_precomp.numel() > 0,
+                   scales is not None and scales.numel() > 0, cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0)
+        empty = torch.empty(0, device=device)
+        ctx.save_for_backward(*(t if t is not None else empty for t in
+                                (colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, opac_c)),
+                              geom.tensor, binning.tensor, img.tensor)
+        ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)
+        return color, radii, invdepth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, grad_out_depth):
+        rs = ctx.raster_settings
+        (colors_c, means3D_c, scales_c, rots_c, cov_c, radii, sh_c, opac_c, geom, binning, img) = ctx.saved_tensors
+        bg_c, view_c, proj_c, campos_c = ctx.cam
+        device = means3D_c.device
+        P = means3D_c.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+        C, M = ctx.channels, ctx.M
+        has_sh, has_colors, has_scales, has_cov = ctx.had
+
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((C, H, W), dtype=torch.float32, device=device)
+        grad_out_color = _f32c(grad_out_color)
+        grad_out_depth = _f32c(grad_out_depth)  # None => the inverse-depth branch is skipped entirely
+
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        dL_dmeans3D, dL_dmeans2D = new(P, 3), new(P, 3)
+        dL_dcolors, dL_dopacity, dL_dcov3D = new(P, C), new(P, 1), new(P, 6)
+        dL_dsh = new(P, M, 3) if has_sh else None
+        dL_dscales = new(P, 3) if has_scales else None
+        dL_drotations = new(P, 4) if has_scales else None
+        if P > 0:
+            with torch.cuda.device(device):
+                rc = _lib.lib.lg_rasterize_backward(
+                    P, int(rs.sh_degree), M, ctx.num_rendered, C,
+                    _lib.ptr(bg_c), W, H,
+                    _lib.ptr(means3D_c), _lib.ptr(sh_c), _lib.ptr(colors_c), _lib.ptr(opac_c), _lib.ptr(scales_c),
+                    float(rs.scale_modifier), _lib.ptr(rots_c), _lib.ptr(cov_c),
+                    _lib.ptr(view_c), _lib.ptr(proj_c), _lib.ptr(campos_c),
+                    float(rs.tanfovx), float(rs.tanfovy),
+                    _lib.ptr(radii), _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img),
+                    _lib.ptr(grad_out_color), _lib.ptr(grad_out_depth),
+                    _lib.ptr(dL_dmeans2D), None, _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors), None,
+                    _lib.ptr(dL_dmeans3D), _lib.ptr(dL_dcov3D), _lib.ptr(dL_dsh), _lib.ptr(dL_dscales),
+                    _lib.ptr(dL_drotations), int(bool(rs.antialiasing)), int(bool(rs.debug)),
+                    _lib.stream_ptr(device))
+            _lib.check(rc, RuntimeError)
+        # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors if has_colors else None, dL_dopacity, dL_dscales,
+                dL_drotations, dL_dcov3D if has_cov else None, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """bool (P,) mask of Gaussians in front of the near plane (DGR/dgr_3dgs/__init__.py:163-172)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions)
+            P = positions.size(0)
+            visible = torch.zeros((P,), dtype=torch.bool, device=positions.device)
+            if P > 0:
+                with torch.cuda.device(positions.device):
+                    rc = _lib.lib.lg_mark_visible(P, _lib.ptr(pos), _lib.ptr(_f32c(rs.viewmatrix)),
+                                                  _lib.ptr(_f32c(rs.projmatrix)), visible.data_ptr(),
+                                                  _lib.stream_ptr(positions.device))
+                _lib.check(rc, RuntimeError)
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        # same validation, exception type and messages as DGR/dgr_3dgs/__init__.py:178-182
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)

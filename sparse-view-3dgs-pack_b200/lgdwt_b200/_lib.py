@@ -1,0 +1,111 @@
+"""ctypes binding of lib/liblgdwt_b200.so (the C ABI declared in include/lgdwt_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, importing / calling raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "liblgdwt_b200.so")
+
+LG_OK = 0
+LG_ERR_INVALID_ARGUMENT = 1
+LG_ERR_CUDA = 2
+LG_ERR_ALLOC = 3
+LG_ERR_UNSUPPORTED = 4
+
+ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+_c_float_p = ctypes.c_void_p  # raw device pointers travel as integers
+_P = ctypes.c_void_p
+
+
+class LgdwtError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "liblgdwt_b200.so not found at %s — build it with `python sparse-view-3dgs-pack_b200/build.py` "
+            "(there is no CPU or PyTorch fallback for this operator)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.lg_abi_version.restype = ctypes.c_int
+    lib.lg_last_error.restype = ctypes.c_char_p
+    for name in ("lg_geometry_state_bytes", "lg_image_state_bytes", "lg_binning_state_bytes", "lg_knn_workspace_bytes",
+                 "lg_dwt_workspace_bytes"):
+        getattr(lib, name).restype = ctypes.c_size_t
+    lib.lg_geometry_state_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.lg_image_state_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.lg_binning_state_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.lg_knn_workspace_bytes.argtypes = [ctypes.c_int]
+    lib.lg_dwt_workspace_bytes.argtypes = [ctypes.c_int] * 4
+
+    i, f = ctypes.c_int, ctypes.c_float
+    lib.lg_rasterize_forward.restype = i
+    lib.lg_rasterize_forward.argtypes = (
+        [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f, i,
+                                                                                      _P, _P, i, _P, i, _P,
+                                                                                      ctypes.POINTER(i)])
+    lib.lg_rasterize_backward.restype = i
+    lib.lg_rasterize_backward.argtypes = (
+        [i, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f] + [_P] * 16 + [i, i, _P])
+    lib.lg_mark_visible.restype = i
+    lib.lg_mark_visible.argtypes = [i, _P, _P, _P, _P, _P]
+    lib.lg_state_read.restype = i
+    lib.lg_state_read.argtypes = [ctypes.c_char_p, i, i, i, i, i, _P, _P, _P, _P, ctypes.c_size_t, _P]
+    lib.lg_knn_mean_dist2.restype = i
+    lib.lg_knn_mean_dist2.argtypes = [i, _P, _P, _P, ctypes.c_size_t, _P]
+    lib.lg_dwt_loss_forward.restype = i
+    lib.lg_dwt_loss_forward.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, ctypes.c_double, f, f, _P, _P, _P,
+                                        ctypes.c_size_t, _P]
+    lib.lg_dwt_loss_backward.restype = i
+    lib.lg_dwt_loss_backward.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, f, f, _P, _P, _P, _P, _P, _P]
+    lib.lg_haar_dwt2_forward.restype = i
+    lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
+    lib.lg_haar_dwt2_backward.restype = i
+    lib.lg_haar_dwt2_backward.argtypes = [_P, _P, i, i, i, _P, _P]
+    if lib.lg_abi_version() != 1:
+        raise ImportError("liblgdwt_b200.so has ABI version %d, expected 1" % lib.lg_abi_version())
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, exc=LgdwtError):
+    if rc != LG_OK:
+        msg = lib.lg_last_error().decode("utf-8", "replace")
+        raise exc(msg)
+
+
+def ptr(t):
+    """Device pointer of a tensor, or NULL for None / empty tensors (the reference passes torch.Tensor([]) for
+    absent optional inputs and its C++ side sees a null data pointer, DGR/dgr_3dgs/__init__.py:184-194)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class ResizableBuffer:
+    """A torch.uint8 CUDA tensor the library can grow through an lg_alloc_fn callback — the counterpart of the
+    reference's resizeFunctional lambdas (DGR/rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.callback = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # surfaced as LG_ERR_ALLOC by the library
+            return 0
