@@ -37,6 +37,7 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, 
             n = h;
         } else {
             v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+            if (upper) cnt = 0;  // both partners now hold the same total: the lower lane owns it
         }
     }
     out = v[0];
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
             const float4 co = s_co[j];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
-            const float power = F_SUB(F_MUL(q, -0.5f), F_MUL(dy, F_MUL(dx, co.y)));
+            const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
             const float G = expf(power);
             const float alpha = fminf(0.99f, F_MUL(co.w, G));
             const bool hit = rel < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
-            const float power = F_SUB(F_MUL(q, -0.5f), F_MUL(dy, F_MUL(dx, co.y)));
+            const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
             if (power > 0.0f) continue;
             const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
             if (alpha < 1.0f / 255.0f) continue;

@@ -4,8 +4,10 @@
 // (DGR/cuda_rasterizer/forward.cu:151-269, rasterizer_impl.cu:280).
 //
 // Numerical contract: every quantity that decides radii / tile rectangles / depth bits is evaluated with
-// explicitly rounded intrinsics in exactly the operation order nvcc 12.9 emits for the reference on sm_100a
-// (DESIGN.md "bit-exact contract").  Comments "ref: fNNN" name the PTX register of that build.
+// explicitly rounded intrinsics in exactly the operation order of the reference's sm_100a SASS (nvcc 12.9 -O3):
+// the NVVM front end contracts some a*b+c into fma.rn in the PTX and ptxas then fuses further mul/add pairs, so the
+// SASS, not the source or the PTX, is the contract (DESIGN.md "bit-exact contract").  Comments "fNNN" / "Rnn" name
+// the PTX / SASS registers of that build.
 #include "common.cuh"
 
 namespace lg {
@@ -67,23 +69,22 @@ __device__ __forceinline__ float ndc2pix(float v, int S) {
 __device__ __forceinline__ void compute_cov3d(float sx0, float sy0, float sz0, float mod, float qr, float qx, float qy,
                                               float qz, float* cov) {
     const float sx = F_MUL(mod, sx0), sy = F_MUL(mod, sy0), sz = F_MUL(mod, sz0);
-    const float yy = F_MUL(qy, qy);                 // f112
-    const float zz = F_MUL(qz, qz);                 // f113
-    const float yy_zz = F_ADD(yy, zz);              // f114
-    const float xy = F_MUL(qx, qy);                 // f115
-    const float rz = F_MUL(qr, qz);                 // f116
-    const float xy_m_rz = F_SUB(xy, rz);            // f117
-    const float xz = F_MUL(qx, qz);                 // f118
-    const float ry = F_MUL(qr, qy);                 // f119
-    const float xz_p_ry = F_ADD(ry, xz);            // f120
-    const float xy_p_rz = F_ADD(xy, rz);            // f121
-    const float xx_zz = F_FMA(qx, qx, zz);          // f122
-    const float yz = F_MUL(qy, qz);                 // f123
-    const float rx = F_MUL(qr, qx);                 // f124
-    const float yz_m_rx = F_SUB(yz, rx);            // f125
-    const float xz_m_ry = F_SUB(xz, ry);            // f126
-    const float yz_p_rx = F_ADD(rx, yz);            // f127
-    const float xx_yy = F_FMA(qx, qx, yy);          // f128
+    // Two-product sums are single FFMAs in the reference SASS (ptxas fuses the PTX mul+add pairs), squares that are
+    // reused stay separate multiplies.  "Rnn" = SASS register of the reference build.
+    const float xz = F_MUL(qx, qz);                 // R21
+    const float rx = F_MUL(qr, qx);                 // R29
+    const float xz_p_ry = F_FMA(qr, qy, xz);        // R10
+    const float xz_m_ry = F_FMA(-qr, qy, xz);       // R21'
+    const float yz_m_rx = F_FMA(qy, qz, -rx);       // R11
+    const float yy = F_MUL(qy, qy);                 // R20
+    const float rz = F_MUL(qr, qz);                 // R12
+    const float yz_p_rx = F_FMA(qy, qz, rx);        // R29'
+    const float zz = F_MUL(qz, qz);                 // R15
+    const float xx_yy = F_FMA(qx, qx, yy);          // R30
+    const float xy_m_rz = F_FMA(qx, qy, -rz);       // R8
+    const float xy_p_rz = F_FMA(qx, qy, rz);        // R14
+    const float yy_zz = F_ADD(yy, zz);              // R20'
+    const float xx_zz = F_FMA(qx, qx, zz);          // R13
     const float R22 = F_SUB(1.0f, F_ADD(xx_yy, xx_yy));     // f131
     const float R21 = F_ADD(yz_p_rx, yz_p_rx);              // f132
     const float R20 = F_ADD(xz_m_ry, xz_m_ry);              // f133
@@ -204,10 +205,10 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
 
             // low-pass dilation + optional anti-aliasing compensation (forward.cu:215-231)
             const float xy2 = F_MUL(cov_xy, cov_xy);                               // f268
-            const float det_cov = F_SUB(F_MUL(cov_xx, cov_yy), xy2);               // f26
+            const float det_cov = F_FMA(cov_xx, cov_yy, -xy2);                     // SASS: one FFMA
             const float cxx = F_ADD(cov_xx, 0.3f);                                 // f27
             const float cyy = F_ADD(cov_yy, 0.3f);                                 // f28
-            const float det = F_SUB(F_MUL(cxx, cyy), xy2);                         // f29
+            const float det = F_FMA(cxx, cyy, -xy2);                               // SASS: one FFMA
             float h_scaling = 1.0f;
             if (a.antialiasing) h_scaling = F_SQRT(fmaxf(F_DIV(det_cov, det), 0.000025f));
             if (!(det == 0.0f)) {
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                 const float con_z = F_MUL(cxx, det_inv);
                 // screen-space extent (forward.cu:237-240)
                 const float mid = F_MUL(F_ADD(cxx, cyy), 0.5f);
-                const float disc = F_SQRT(fmaxf(F_SUB(F_MUL(mid, mid), det), 0.1f));
+                const float disc = F_SQRT(fmaxf(F_FMA(mid, mid, -det), 0.1f));  // SASS: one FFMA
                 const float lam = fmaxf(F_ADD(mid, disc), F_SUB(mid, disc));
                 const float radius_f = ceilf(F_MUL(F_SQRT(lam), 3.0f));
                 const float pix_x = ndc2pix(proj_x, a.W);
@@ -242,9 +243,9 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                             const float k1x = F_MUL(x, 0.4886025119029199f);
 #pragma unroll
                             for (int c = 0; c < 3; c++) {
-                                float v = F_SUB(r[c], F_MUL(k1y, __ldg(sh + 3 + c)));
+                                float v = F_FMA(-k1y, __ldg(sh + 3 + c), r[c]);
                                 v = F_FMA(k1z, __ldg(sh + 6 + c), v);
-                                r[c] = F_SUB(v, F_MUL(k1x, __ldg(sh + 9 + c)));
+                                r[c] = F_FMA(-k1x, __ldg(sh + 9 + c), v);
                             }
                             if (a.D > 1) {
                                 const float xx = F_MUL(x, x), yy = F_MUL(y, y), zz = F_MUL(z, z);
@@ -265,16 +266,14 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                                     r[c] = F_FMA(k8, __ldg(sh + 24 + c), v);
                                 }
                                 if (a.D > 2) {
-                                    const float xx3 = F_MUL(xx, 3.0f);
-                                    const float yy3 = F_MUL(yy, 3.0f);
-                                    const float zz4_xx_yy = F_SUB(F_SUB(F_MUL(zz, 4.0f), xx), yy);
-                                    const float k9 = F_MUL(F_MUL(y, -0.5900435899266435f), F_SUB(xx3, yy));
+                                    const float zz4_xx_yy = F_SUB(F_FMA(zz, 4.0f, -xx), yy);
+                                    const float k9 = F_MUL(F_MUL(y, -0.5900435899266435f), F_FMA(xx, 3.0f, -yy));
                                     const float k10 = F_MUL(z, F_MUL(xy, 2.890611442640554f));
                                     const float k11 = F_MUL(F_MUL(y, -0.4570457994644658f), zz4_xx_yy);
-                                    const float k12 = F_MUL(F_MUL(z, 0.3731763325901154f), F_SUB(F_SUB(zz2, xx3), yy3));
+                                    const float k12 = F_MUL(F_MUL(z, 0.3731763325901154f), F_FMA(yy, -3.0f, F_FMA(xx, -3.0f, zz2)));
                                     const float k13 = F_MUL(F_MUL(x, -0.4570457994644658f), zz4_xx_yy);
                                     const float k14 = F_MUL(F_MUL(z, 1.445305721320277f), xx_yy);
-                                    const float k15 = F_MUL(F_MUL(x, -0.5900435899266435f), F_SUB(xx, yy3));
+                                    const float k15 = F_MUL(F_MUL(x, -0.5900435899266435f), F_FMA(yy, -3.0f, xx));
 #pragma unroll
                                     for (int c = 0; c < 3; c++) {
                                         float v = F_FMA(k9, __ldg(sh + 27 + c), r[c]);

@@ -1,0 +1,236 @@
+"""Shared test plumbing: run this repo's operator and (when oracle/_ref/libref_dgr.so was prebuilt) the unmodified
+reference CUDA rasterizer on the same tensors, and read both sides' internal state for bit-exact comparison."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_dgr.so")
+
+STATE_DTYPES = {
+    "depths": (torch.float32, lambda P, C, N, T, R: P),
+    "means2D": (torch.float32, lambda P, C, N, T, R: 2 * P),
+    "cov3D": (torch.float32, lambda P, C, N, T, R: 6 * P),
+    "conic_opacity": (torch.float32, lambda P, C, N, T, R: 4 * P),
+    "rgb": (torch.float32, lambda P, C, N, T, R: C * P),
+    "clamped": (torch.uint8, lambda P, C, N, T, R: 3 * P),
+    "tiles_touched": (torch.int32, lambda P, C, N, T, R: P),
+    "point_offsets": (torch.int32, lambda P, C, N, T, R: P),
+    "final_T": (torch.float32, lambda P, C, N, T, R: N),
+    "n_contrib": (torch.int32, lambda P, C, N, T, R: N),
+    "ranges": (torch.int32, lambda P, C, N, T, R: 2 * T),
+    "point_list": (torch.int32, lambda P, C, N, T, R: R),
+    "point_list_keys": (torch.int64, lambda P, C, N, T, R: R),
+}
+
+
+def scene_to_torch(scene, device="cuda"):
+    return {k: torch.from_numpy(np.ascontiguousarray(getattr(scene, k))).to(device)
+            for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+
+
+def cam_to_torch(cam, device="cuda"):
+    return {"viewmatrix": torch.from_numpy(cam.viewmatrix).to(device),
+            "projmatrix": torch.from_numpy(cam.projmatrix).to(device),
+            "campos": torch.from_numpy(cam.campos).to(device)}
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+class _Buf:
+    def __init__(self, fn_type, device):
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.device = device
+        self.cb = fn_type(self._alloc)
+
+    def _alloc(self, _ctx, n):
+        self.tensor = torch.empty(int(n), dtype=torch.uint8, device=self.device)
+        return self.tensor.data_ptr()
+
+
+def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
+             scale_modifier=1.0, debug=False, want_state=True, with_invdepth=True):
+    """Low-level call through the C ABI (no autograd).  Returns dict of outputs, state tensors and raw buffers."""
+    from lgdwt_b200 import _lib
+    dev = t["means3D"].device
+    P = t["means3D"].shape[0]
+    H, W = cam.image_height, cam.image_width
+    C = 3 if colors_precomp is None else colors_precomp.shape[-1]
+    color = torch.zeros((C, H, W), device=dev)
+    invd = torch.zeros((1, H, W), device=dev)
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    geom, binning, img = (_lib.ResizableBuffer(dev) for _ in range(3))
+    R = ctypes.c_int(0)
+    shs = None if colors_precomp is not None else t["shs"]
+    M = 0 if shs is None else shs.shape[1]
+    scales = None if cov3D_precomp is not None else t["scales"]
+    rots = None if cov3D_precomp is not None else t["rotations"]
+    rc = _lib.lib.lg_rasterize_forward(
+        geom.callback, None, binning.callback, None, img.callback, None, P, sh_degree, M, C, _ptr(bg), W, H,
+        _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier,
+        _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]),
+        cam.tanfovx, cam.tanfovy, 0, _ptr(color), _ptr(invd) if with_invdepth else None, int(antialiasing),
+        _ptr(radii), int(debug), _lib.stream_ptr(dev), ctypes.byref(R))
+    _lib.check(rc)
+    out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,
+           "binning": binning.tensor, "img": img.tensor, "C": C, "M": M}
+    if want_state:
+        N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+        for name, (dt, nfn) in STATE_DTYPES.items():
+            if name == "rgb" and colors_precomp is not None:
+                continue
+            n = nfn(P, C, N, T, R.value)
+            dst = torch.zeros(max(n, 1), dtype=dt, device=dev)
+            rc = _lib.lib.lg_state_read(name.encode(), P, C, W, H, R.value, _ptr(geom.tensor), _ptr(binning.tensor),
+                                        _ptr(img.tensor), dst.data_ptr(), dst.numel() * dst.element_size(),
+                                        _lib.stream_ptr(dev))
+            _lib.check(rc)
+            out[name] = dst[:n]
+    torch.cuda.synchronize()
+    return out
+
+
+def backward_ours(t, c, cam, bg, fwd, dL_dpix, dL_dinvd=None, sh_degree=3, colors_precomp=None, cov3D_precomp=None,
+                  antialiasing=False, scale_modifier=1.0, debug=False):
+    from lgdwt_b200 import _lib
+    dev = t["means3D"].device
+    P = t["means3D"].shape[0]
+    H, W = cam.image_height, cam.image_width
+    C, M = fwd["C"], fwd["M"]
+    shs = None if colors_precomp is not None else t["shs"]
+    scales = None if cov3D_precomp is not None else t["scales"]
+    rots = None if cov3D_precomp is not None else t["rotations"]
+    new = lambda *s: torch.full(s, float("nan"), device=dev)  # NaN-filled: every element must be written
+    g = {"dL_dmean2D": new(P, 3), "dL_dconic": new(P, 4), "dL_dopacity": new(P, 1), "dL_dcolor": new(P, C),
+         "dL_dinvdepth": new(P, 1), "dL_dmean3D": new(P, 3), "dL_dcov3D": new(P, 6),
+         "dL_dsh": new(P, M, 3) if shs is not None else None, "dL_dscale": new(P, 3) if scales is not None else None,
+         "dL_drot": new(P, 4) if scales is not None else None}
+    rc = _lib.lib.lg_rasterize_backward(
+        P, sh_degree, M, fwd["num_rendered"], C, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp),
+        _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]),
+        _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]),
+        _ptr(fwd["binning"]), _ptr(fwd["img"]), _ptr(dL_dpix), _ptr(dL_dinvd), _ptr(g["dL_dmean2D"]),
+        _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolor"]),
+        _ptr(g["dL_dinvdepth"]) if dL_dinvd is not None else None, _ptr(g["dL_dmean3D"]), _ptr(g["dL_dcov3D"]),
+        _ptr(g["dL_dsh"]), _ptr(g["dL_dscale"]), _ptr(g["dL_drot"]), int(antialiasing), int(debug),
+        _lib.stream_ptr(dev))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    if dL_dinvd is None:
+        g["dL_dinvdepth"] = None
+    return g
+
+
+# ----------------------------------------------------------------------------- reference (oracle/_ref) side
+_REF = None
+REF_ALLOC = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+def load_ref():
+    """ctypes handle of the prebuilt reference shim, or None when oracle/_ref was not built (no /root/reference)."""
+    global _REF
+    if _REF is None and os.path.exists(REF_LIB):
+        lib = ctypes.CDLL(REF_LIB)
+        lib.ref_last_error.restype = ctypes.c_char_p
+        i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+        lib.ref_rasterize_forward.restype = i
+        lib.ref_rasterize_forward.argtypes = ([REF_ALLOC, p] * 3 + [i, i, i, p, i, i] + [p] * 5 + [f] + [p] * 5 +
+                                              [f, f, i, p, p, i, p, i, ctypes.POINTER(i)])
+        lib.ref_rasterize_backward.restype = i
+        lib.ref_rasterize_backward.argtypes = ([i, i, i, i, p, i, i] + [p] * 5 + [f] + [p] * 5 + [f, f] + [p] * 16 +
+                                               [i, i])
+        lib.ref_state_read.restype = i
+        lib.ref_state_read.argtypes = [ctypes.c_char_p, i, i, i, i, p, p, p, p, ctypes.c_size_t]
+        lib.ref_mark_visible.restype = i
+        lib.ref_mark_visible.argtypes = [i, p, p, p, p]
+        lib.ref_knn_mean_dist2.restype = i
+        lib.ref_knn_mean_dist2.argtypes = [i, p, p]
+        _REF = lib
+    return _REF
+
+
+def _ref_check(lib, rc):
+    if rc != 0:
+        raise RuntimeError("reference shim: " + lib.ref_last_error().decode())
+
+
+def run_ref(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
+            scale_modifier=1.0, debug=False, want_state=True):
+    lib = load_ref()
+    dev = t["means3D"].device
+    P = t["means3D"].shape[0]
+    H, W = cam.image_height, cam.image_width
+    color = torch.zeros((3, H, W), device=dev)
+    invd = torch.zeros((1, H, W), device=dev)
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    geom, binning, img = (_Buf(REF_ALLOC, dev) for _ in range(3))
+    R = ctypes.c_int(0)
+    shs = None if colors_precomp is not None else t["shs"]
+    M = 0 if shs is None else shs.shape[1]
+    scales = None if cov3D_precomp is not None else t["scales"]
+    rots = None if cov3D_precomp is not None else t["rotations"]
+    torch.cuda.synchronize()
+    rc = lib.ref_rasterize_forward(
+        geom.cb, None, binning.cb, None, img.cb, None, P, sh_degree, M, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs),
+        _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp),
+        _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, 0, _ptr(color),
+        _ptr(invd), int(antialiasing), _ptr(radii), int(debug), ctypes.byref(R))
+    _ref_check(lib, rc)
+    torch.cuda.synchronize()
+    out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,
+           "binning": binning.tensor, "img": img.tensor, "C": 3, "M": M}
+    if want_state:
+        N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+        for name, (dt, nfn) in STATE_DTYPES.items():
+            if name == "rgb" and colors_precomp is not None:
+                continue
+            n = nfn(P, 3, N, T, R.value)
+            dst = torch.zeros(max(n, 1), dtype=dt, device=dev)
+            rc = lib.ref_state_read(name.encode(), P, W, H, R.value, _ptr(geom.tensor), _ptr(binning.tensor),
+                                    _ptr(img.tensor), dst.data_ptr(), dst.numel() * dst.element_size())
+            _ref_check(lib, rc)
+            out[name] = dst[:n]
+    torch.cuda.synchronize()
+    return out
+
+
+def backward_ref(t, c, cam, bg, fwd, dL_dpix, dL_dinvd=None, sh_degree=3, colors_precomp=None, cov3D_precomp=None,
+                 antialiasing=False, scale_modifier=1.0, debug=False):
+    lib = load_ref()
+    dev = t["means3D"].device
+    P = t["means3D"].shape[0]
+    H, W = cam.image_height, cam.image_width
+    M = fwd["M"]
+    shs = None if colors_precomp is not None else t["shs"]
+    scales = None if cov3D_precomp is not None else t["scales"]
+    rots = None if cov3D_precomp is not None else t["rotations"]
+    z = lambda *s: torch.zeros(s, device=dev)  # the reference requires zero-initialised gradient buffers
+    g = {"dL_dmean2D": z(P, 3), "dL_dconic": z(P, 4), "dL_dopacity": z(P, 1), "dL_dcolor": z(P, 3),
+         "dL_dinvdepth": z(P, 1), "dL_dmean3D": z(P, 3), "dL_dcov3D": z(P, 6), "dL_dsh": z(P, max(M, 1), 3),
+         "dL_dscale": z(P, 3), "dL_drot": z(P, 4)}
+    torch.cuda.synchronize()
+    rc = lib.ref_rasterize_backward(
+        P, sh_degree, M, fwd["num_rendered"], _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp),
+        _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]),
+        _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]),
+        _ptr(fwd["binning"]), _ptr(fwd["img"]), _ptr(dL_dpix), _ptr(dL_dinvd), _ptr(g["dL_dmean2D"]),
+        _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolor"]),
+        _ptr(g["dL_dinvdepth"]) if dL_dinvd is not None else None, _ptr(g["dL_dmean3D"]), _ptr(g["dL_dcov3D"]),
+        _ptr(g["dL_dsh"]), _ptr(g["dL_dscale"]), _ptr(g["dL_drot"]), int(antialiasing), int(debug))
+    _ref_check(lib, rc)
+    torch.cuda.synchronize()
+    if shs is None:
+        g["dL_dsh"] = None
+    if dL_dinvd is None:
+        g["dL_dinvdepth"] = None
+    return g
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|_inf, eps): the per-tensor relative error of SURVEY §8c."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
