@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native LGDWT-GS hot path.
+
+Metric (BASELINE.json): rasterize forward+backward per view at 1 M Gaussians, 800x800, SH degree 3, reported as
+whole-job views/s (ms/view = ms_per_step at N = 1); at N > 1 every rank renders its own view of the step (weak
+scaling by camera view) and the per-Gaussian parameter gradients (59 floats = 236 B each) are summed with ONE NCCL
+all-reduce inside the timed step — the path's only exchange step.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's own CUDA rasterizer (oracle/_ref), same metric
+
+One JSON line on rank 0.  `value`: operator fwd+bwd with all inputs resident in HBM.  `e2e`: the same step through
+the public torch operator with the step's inputs (camera matrices + ground-truth image) copied from pinned host
+memory, an L1 loss against that image, backward, and a device->host read of the loss.  `roofline`: the dominant
+kernel against its bound, timed live with CUDA events on the launching stream; `stages`: every stage likewise.
+`cpu_baseline`: the CPU oracle (a port: the reference has no CPU rasterizer) timed on this box's cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "sparse-view-3dgs-pack_b200"))
+sys.path.insert(0, ROOT)
+
+P_GAUSSIANS = 1_000_000
+WIDTH = HEIGHT = 800
+SH_DEGREE = 3
+N_CAMERAS = 8
+FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: not in MEASURED_PEAKS.json
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(device):
+    from lgdwt_b200 import scenes
+    sc = scenes.trained_like_scene(P_GAUSSIANS, seed=1)
+    cams = [scenes.metric_camera(WIDTH, HEIGHT)] + scenes.orbit_cameras(N_CAMERAS - 1, WIDTH, HEIGHT, phase=0.4)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    params = {k: t(getattr(sc, k)).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    return sc, cams, params
+
+
+def cam_dict(cam, device):
+    from lgdwt_b200.dp import camera_to_device
+    return camera_to_device(cam, device)
+
+
+class Stepper:
+    """One benchmark step for either implementation; identical work outside the operator."""
+
+    def __init__(self, impl, params, device, world):
+        self.impl, self.p, self.device, self.world = impl, params, device, world
+        self.bg = torch.zeros(3, device=device)
+        P = params["means3D"].shape[0]
+        self.bucket = torch.zeros(59 * P, device=device) if world > 1 else None
+        gen = torch.Generator(device=device).manual_seed(1234)
+        self.dL = torch.randn((3, HEIGHT, WIDTH), device=device, generator=gen)
+        self.means2D = torch.zeros((P, 3), device=device, requires_grad=True)
+        if impl == "ours":
+            from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+            self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
+        else:
+            from oracle import ref_cuda
+            self.ref = ref_cuda
+
+    def render(self, cam):
+        p = self.p
+        if self.impl == "ours":
+            rs = self.RS(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], self.bg, 1.0, cam["viewmatrix"],
+                         cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, False)
+            return self.R(rs)(means3D=p["means3D"], means2D=self.means2D, shs=p["shs"], opacities=p["opacities"],
+                              scales=p["scales"], rotations=p["rotations"])
+        return self.ref.RefRasterize.apply(p["means3D"], self.means2D, p["shs"], p["opacities"], p["scales"],
+                                           p["rotations"], cam, self.bg, SH_DEGREE)
+
+    def zero_grads(self):
+        for t in list(self.p.values()) + [self.means2D]:
+            t.grad = None
+
+    def exchange(self):
+        """the path's only collective: sum the 236 B/Gaussian gradient bucket over ranks"""
+        if self.world <= 1:
+            return
+        off = 0
+        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+            g = self.p[k].grad.reshape(-1)
+            self.bucket[off:off + g.numel()].copy_(g)
+            off += g.numel()
+        dist.all_reduce(self.bucket)
+
+    def step_resident(self, cam):
+        self.zero_grads()
+        color, radii, invd = self.render(cam)
+        color.backward(self.dL)
+        self.exchange()
+
+    def step_e2e(self, host_cam, host_gt, dev_gt):
+        """inputs of the step come from pinned host memory; the loss value goes back to the host"""
+        self.zero_grads()
+        cam = dict(host_cam)
+        for k in ("viewmatrix", "projmatrix", "campos"):
+            cam[k] = host_cam[k].to(self.device, non_blocking=True)
+        dev_gt.copy_(host_gt, non_blocking=True)
+        color, radii, invd = self.render(cam)
+        loss = (color - dev_gt).abs().mean()
+        loss.backward()
+        self.exchange()
+        return float(loss.item())
+
+
+def timed_loop(fn, steps, world, device):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def cpu_baseline(sc, cam):
+    """CPU oracle (port of the reference algorithm) on ONE view of the same workload, all host threads for the
+    parallel stages.  Bounded sample: forward + backward of a single view."""
+    from oracle import oracle
+    kw = oracle.scene_kwargs(sc, cam, np.zeros(3, np.float32))
+    rng = np.random.default_rng(0)
+    dL = rng.standard_normal((3, HEIGHT, WIDTH)).astype(np.float32)
+    t0 = time.perf_counter()
+    f = oracle.rasterize_forward(**kw)
+    t1 = time.perf_counter()
+    oracle.rasterize_backward(f, dL_dpix=dL, **kw)
+    t2 = time.perf_counter()
+    return {"value": 1.0 / (t2 - t0), "unit": "views/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": "1 view fwd+bwd of the same 1M-Gaussian 800x800 scene (fwd %.2f s, bwd %.2f s; blend backward "
+                      "is single-threaded)" % (t1 - t0, t2 - t1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # rank 0 alone runs the reference arm
+    if args.impl == "reference":
+        world = 1
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback", "impl": args.impl}))
+        return 1
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from oracle import ref_cuda
+    impl = "ours"
+    ref_kind = None
+    if args.impl == "reference":
+        if ref_cuda.load_ref() is not None:
+            impl, ref_kind = "reference_cuda", "reference"
+        else:
+            return reference_cpu_port(args, K, W)
+
+    sc, cams, params = make_workload(device)
+    cam_devs = [cam_dict(c, device) for c in cams]
+    stepper = Stepper("ours" if impl == "ours" else "ref", params, device, world)
+    pick = lambda i: cam_devs[(i * world + rank) % len(cam_devs)]
+
+    from lgdwt_b200 import _lib
+    # ---- value: inputs resident in HBM
+    for i in range(W):
+        stepper.step_resident(pick(i))
+    launches0 = _lib.lib.lg_launch_count()
+    if impl == "ours":
+        _lib.stage_timing(min(K, 256))
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device)
+    clocks = sampler.stop()
+    launches = _lib.lib.lg_launch_count() - launches0
+    ms_step = ms_total / K
+    value = world * K / (ms_total / 1e3)
+
+    # ---- per-stage times recorded during that same timed region
+    stages, roofline = None, None
+    if impl == "ours":
+        rows = [_lib.read_stage_times(s) for s in range(min(K, 256))]
+        _lib.stage_timing(0)
+        mean_ms = {k: float(np.mean([r[k] for r in rows if r[k] >= 0])) for k in _lib.STAGES}
+        from diff_gaussian_rasterization import _RasterizeGaussians
+        # work terms of the metric camera (step 0's view on rank 0)
+        stepper.step_resident(cam_devs[0])
+        lc = _RasterizeGaussians.last_call
+        counts = torch.zeros(2, dtype=torch.int64, device=device)
+        _lib.check(_lib.lib.lg_blend_work_count(lc["P"], lc["channels"], lc["W"], lc["H"], lc["num_rendered"],
+                                                lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
+                                                counts.data_ptr(), _lib.stream_ptr(device)))
+        n_contrib = torch.zeros(WIDTH * HEIGHT, dtype=torch.int32, device=device)
+        _lib.check(_lib.lib.lg_state_read(b"n_contrib", lc["P"], lc["channels"], lc["W"], lc["H"], lc["num_rendered"],
+                                          lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
+                                          n_contrib.data_ptr(), n_contrib.numel() * 4, _lib.stream_ptr(device)))
+        radii = torch.zeros(lc["P"], dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        n_eval, n_hit = int(counts[0]), int(counts[1])
+        n_trav = int(n_contrib.long().sum())
+        R = lc["num_rendered"]
+        P = lc["P"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        T = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+        alg = {  # algorithmic work per launch, SURVEY.md §8(d)
+            "preprocess": ("hbm", P * (44 + 12 * 16) + 8 * P + 67 * P),
+            "binning": ("hbm", 20 * P + 12 * R + 24 * R + 8 * R + 8 * T),
+            "blend_forward": ("fp32_simt", 15 * n_eval + 15 * n_hit),
+            "blend_backward": ("fp32_simt", 15 * n_trav + 80 * n_hit),
+            "preprocess_backward": ("hbm", 560 * P),
+        }
+        stages = {}
+        for k in _lib.STAGES:
+            bound, work = alg[k]
+            ach = work / (mean_ms[k] * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            peak = hbm_peak if bound == "hbm" else FP32_SIMT_PEAK_TFLOPS
+            stages[k] = {"ms": round(mean_ms[k], 4), "bound": bound, "achieved": round(ach, 2),
+                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "peak": round(peak, 2),
+                         "frac": round(ach / peak, 4)}
+        dom = max(_lib.STAGES, key=lambda k: mean_ms[k])
+        roofline = dict(stages[dom])
+        roofline.update({"kernel": dom, "traffic": None, "share_of_step": round(mean_ms[dom] / ms_step, 3),
+                         "peak_source": hbm_src if roofline["bound"] == "hbm" else
+                         "nominal FP32 SIMT peak 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak in "
+                         "MEASURED_PEAKS.json)",
+                         "work_terms": {"num_rendered": R, "n_eval_fwd": n_eval, "n_trav": n_trav, "n_hit": n_hit}})
+
+    # ---- e2e: host inputs every step + loss read-back
+    host_cams = []
+    for c in cams:
+        d = cam_dict(c, "cpu")
+        for k in ("viewmatrix", "projmatrix", "campos"):
+            d[k] = d[k].pin_memory()
+        host_cams.append(d)
+    rng = np.random.default_rng(7)
+    host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory() for _ in range(2)]
+    dev_gt = torch.empty((3, HEIGHT, WIDTH), device=device)
+    e2e_fn = lambda i: stepper.step_e2e(host_cams[(i * world + rank) % len(host_cams)], host_gts[i % 2], dev_gt)
+    for i in range(W):
+        e2e_fn(i)
+    ms_e2e = timed_loop(e2e_fn, K, world, device)
+    e2e_value = world * K / (ms_e2e / 1e3)
+    h2d = 3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4
+    e2e = {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_step": round(ms_e2e / K, 4),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4}
+
+    line = {
+        "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)", "value": round(value, 3),
+        "unit": "views/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, one view "
+                               "per rank per step, rasterize forward+backward" +
+                               (" + NCCL all-reduce of the 236 B/Gaussian gradient bucket" if world > 1 else ""),
+                   "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
+                   "cameras": N_CAMERAS, "parallelism": "view-parallel dp%d" % world,
+                   "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 43 MB of sort keys per step)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if impl == "ours":
+        line["roofline"], line["stages"] = roofline, stages
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sc, cams[0])
+    else:
+        line["impl"] = "reference"
+        line["gpu_launches"] = None
+        line["reference_kind"] = ("reference CUDA rasterizer compiled for sm_100a from its own sources "
+                                  "(oracle/_ref/libref_dgr.so) behind a line-for-line mirror of its torch glue")
+        line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": ref_kind,
+                                "sample": "the reference has no CPU implementation of this path; this arm times its "
+                                          "own CUDA implementation on the same GPU (cores = 0 host threads)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_cpu_port(args, K, W):
+    """fallback when oracle/_ref was not prebuilt: the CPU oracle port, bounded sample"""
+    from lgdwt_b200 import scenes
+    sc = scenes.trained_like_scene(P_GAUSSIANS, seed=1)
+    cb = cpu_baseline(sc, scenes.metric_camera(WIDTH, HEIGHT))
+    line = {"impl": "reference", "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)",
+            "value": round(cb["value"], 5), "unit": "views/s", "n_gpus": 1, "steps": 1, "warmup": 0,
+            "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "cpu_baseline": cb,
+            "config": {"workload": "CPU oracle port, one view of the 1M-Gaussian 800x800 SH3 scene"},
+            "e2e": {"value": round(cb["value"], 5), "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

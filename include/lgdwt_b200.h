@@ -140,6 +140,23 @@ int lg_state_read(const char* name, int P, int channels, int width, int height, 
                   const char* geometry_state, const char* binning_state, const char* image_state,
                   void* dst, size_t dst_bytes, void* stream);
 
+/* Instrumentation (no counterpart in the reference, whose only timing is two torch.cuda.Events around an
+ * iteration, LG/train.py:65-66,97,220): number of kernels this library has launched in this process, and optional
+ * per-stage CUDA-event timing on the launching stream.  lg_stage_timing_enable(slots) arms a ring of `slots`
+ * (<= 256, 0 disables) event sets; every lg_rasterize_forward call advances to the next slot and the following
+ * lg_rasterize_backward records into the same one, so a run can be timed step by step without a host sync in the
+ * loop.  Stage order of lg_stage_timing_read (milliseconds, -1 when the stage did not run in that slot):
+ * preprocess, binning, blend_forward, blend_backward, preprocess_backward. */
+/* counts_dev (device, 2 x u64): [0] tile-list entries evaluated over all pixels before early termination,
+ * [1] (pixel, Gaussian) pairs that pass all blend tests — the work terms of the blend roofline. */
+int lg_blend_work_count(int P, int channels, int width, int height, int R, const char* geometry_state,
+                        const char* binning_state, const char* image_state, unsigned long long* counts_dev,
+                        void* stream);
+#define LG_NUM_STAGES 5
+unsigned long long lg_launch_count(void);
+int lg_stage_timing_enable(int slots);
+int lg_stage_timing_read(int slot, float* ms_out, int n);
+
 /* Replaces SimpleKNN::knn (KNN/simple_knn.cu:186-222) as bound by distCUDA2 (KNN/spatial.cu:16-26):
  * mean squared distance to the 3 nearest neighbours.  points (P,3); mean_dists (P).
  * workspace: device scratch of >= lg_knn_workspace_bytes(P) bytes (the reference cudaMallocs internally). */

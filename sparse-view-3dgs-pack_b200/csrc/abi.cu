@@ -77,6 +77,30 @@ size_t binning_state_bytes(size_t R) {
 
 static thread_local uint32_t* g_pinned_word = nullptr;  // pinned staging for the num_rendered read-back
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+// Per-stage CUDA-event timing with a ring of slots, so a benchmark can time every step of a run without a host
+// sync inside the loop: each forward call advances to the next slot, the matching backward records into it.
+#define LG_TIMING_SLOTS 256
+static int g_timing_slots = 0;
+static int g_slot = -1;
+static cudaEvent_t g_ev[LG_TIMING_SLOTS][ST_COUNT][2];
+static bool g_ev_used[LG_TIMING_SLOTS][ST_COUNT];
+void stage_begin(int stage, cudaStream_t stream) {
+    if (g_timing_slots <= 0) return;
+    if (stage == ST_PREPROCESS) {
+        g_slot = (g_slot + 1) % g_timing_slots;
+        for (int s = 0; s < ST_COUNT; s++) g_ev_used[g_slot][s] = false;
+    }
+    if (g_slot >= 0) cudaEventRecord(g_ev[g_slot][stage][0], stream);
+}
+void stage_end(int stage, cudaStream_t stream) {
+    if (g_timing_slots <= 0 || g_slot < 0) return;
+    cudaEventRecord(g_ev[g_slot][stage][1], stream);
+    g_ev_used[g_slot][stage] = true;
+}
+
 }  // namespace lg
 
 using namespace lg;
@@ -150,8 +174,10 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
     f.focal_x = width / (2.0f * tan_fovx);
     f.prefiltered = prefiltered != 0; f.antialiasing = antialiasing != 0; f.debug = debug != 0;
 
+    stage_begin(ST_PREPROCESS, stream);
     int rc = launch_preprocess(f, g, radii, stream);
     if (rc != LG_OK) return rc;
+    stage_end(ST_PREPROCESS, stream);
 
     // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288)
     if (!g_pinned_word) LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
@@ -166,12 +192,17 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
         return LG_ERR_ALLOC;
     }
     BinningState b = BinningState::from_chunk(bchunk, (size_t)R);
+    stage_begin(ST_BINNING, stream);
     rc = launch_binning(P, R, width, height, g, radii, b, img, f.debug, stream);
     if (rc != LG_OK) return rc;
+    stage_end(ST_BINNING, stream);
 
     const float* features = colors_precomp ? colors_precomp : g.rgb;
-    return launch_blend_forward(channels, width, height, g, b, img, features, background, out_color, out_invdepth,
-                                f.debug, stream);
+    stage_begin(ST_BLEND_FWD, stream);
+    rc = launch_blend_forward(channels, width, height, g, b, img, features, background, out_color, out_invdepth,
+                              f.debug, stream);
+    stage_end(ST_BLEND_FWD, stream);
+    return rc;
 }
 
 int lg_rasterize_backward(int P, int D, int M, int R, int channels, const float* background, int width, int height,
@@ -207,9 +238,11 @@ int lg_rasterize_backward(int P, int D, int M, int R, int channels, const float*
     if (radii == nullptr) radii = g.internal_radii;
     const float* features = colors_precomp ? colors_precomp : g.rgb;
 
+    stage_begin(ST_BLEND_BWD, stream);
     int rc = launch_blend_backward(P, channels, width, height, g, b, img, features, background, dL_dpix,
                                    dL_dinvdepth_pix, g.grad_scratch, debug != 0, stream);
     if (rc != LG_OK) return rc;
+    stage_end(ST_BLEND_BWD, stream);
 
     BackwardArgs a;
     a.P = P; a.D = D; a.M = M; a.C = channels; a.W = width; a.H = height; a.means3D = means3D; a.shs = shs;
@@ -223,7 +256,60 @@ int lg_rasterize_backward(int P, int D, int M, int R, int channels, const float*
     a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
     a.dL_dinvdepth = dL_dinvdepth; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
     a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
-    return launch_preprocess_backward(a, g, radii, debug != 0, stream);
+    stage_begin(ST_PREGRAD, stream);
+    rc = launch_preprocess_backward(a, g, radii, debug != 0, stream);
+    stage_end(ST_PREGRAD, stream);
+    return rc;
+}
+
+int lg_blend_work_count(int P, int channels, int width, int height, int R, const char* geometry_state,
+                        const char* binning_state, const char* image_state, unsigned long long* counts_dev,
+                        void* stream_v) {
+    if (!geometry_state || !binning_state || !image_state || !counts_dev || P <= 0) {
+        set_error("lg_blend_work_count: invalid arguments");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    char* gp = const_cast<char*>(geometry_state);
+    char* bp = const_cast<char*>(binning_state);
+    char* ip = const_cast<char*>(image_state);
+    GeometryState g = GeometryState::from_chunk(gp, (size_t)P, channels);
+    BinningState b = BinningState::from_chunk(bp, (size_t)R);
+    ImageState img = ImageState::from_chunk(ip, (size_t)width, (size_t)height);
+    return launch_blend_count(width, height, g, b, img, counts_dev, (cudaStream_t)stream_v);
+}
+
+unsigned long long lg_launch_count(void) { return __atomic_load_n(&lg::g_launches, __ATOMIC_RELAXED); }
+
+int lg_stage_timing_enable(int slots) {
+    if (slots > LG_TIMING_SLOTS) slots = LG_TIMING_SLOTS;
+    if (slots < 0) slots = 0;
+    for (int i = 0; i < lg::g_timing_slots; i++)
+        for (int s = 0; s < ST_COUNT; s++)
+            for (int k = 0; k < 2; k++) cudaEventDestroy(lg::g_ev[i][s][k]);
+    lg::g_timing_slots = 0;
+    lg::g_slot = -1;
+    for (int i = 0; i < slots; i++)
+        for (int s = 0; s < ST_COUNT; s++) {
+            for (int k = 0; k < 2; k++) LG_CUDA(cudaEventCreate(&lg::g_ev[i][s][k]));
+            lg::g_ev_used[i][s] = false;
+        }
+    lg::g_timing_slots = slots;
+    return LG_OK;
+}
+
+int lg_stage_timing_read(int slot, float* ms_out, int n) {
+    if (slot < 0 || slot >= lg::g_timing_slots || !ms_out || n < ST_COUNT) {
+        set_error("lg_stage_timing_read: bad slot %d (enabled slots %d) or output too small (need %d floats)", slot,
+                  lg::g_timing_slots, (int)ST_COUNT);
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    for (int s = 0; s < ST_COUNT; s++) {
+        ms_out[s] = -1.0f;
+        if (!lg::g_ev_used[slot][s]) continue;
+        LG_CUDA(cudaEventSynchronize(lg::g_ev[slot][s][1]));
+        LG_CUDA(cudaEventElapsedTime(&ms_out[s], lg::g_ev[slot][s][0], lg::g_ev[slot][s][1]));
+    }
+    return LG_OK;
 }
 
 int lg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,

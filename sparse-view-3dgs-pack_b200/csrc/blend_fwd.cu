@@ -103,6 +103,61 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
     }
 }
 
+// Instrumentation: replays the blend decisions and counts, over all pixels, the list entries evaluated before early
+// termination (N_eval) and the (pixel, Gaussian) pairs that pass all three tests (N_hit) — the work terms of the
+// blend roofline.  Not part of the rendering path.
+__global__ void __launch_bounds__(LG_TILE_PIX) blend_count_kernel(const uint2* __restrict__ ranges,
+                                                                  const uint32_t* __restrict__ point_list, int W, int H,
+                                                                  int grid_x, const float2* __restrict__ means2D,
+                                                                  const float4* __restrict__ conic_opacity,
+                                                                  unsigned long long* __restrict__ counts) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t pix_x = blockIdx.x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t pix_y = blockIdx.y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
+    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+    const uint2 range = ranges[blockIdx.y * (uint32_t)grid_x + blockIdx.x];
+    unsigned long long n_eval = 0, n_hit = 0;
+    if (inside) {
+        float T = 1.0f;
+        for (uint32_t e = range.x; e < range.y; e++) {
+            n_eval++;
+            const uint32_t id = point_list[e];
+            const float2 xy = means2D[id];
+            const float4 co = conic_opacity[id];
+            const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
+            const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
+            const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));
+            if (power > 0.0f) continue;
+            const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+            if (test_T < 0.0001f) break;
+            T = test_T;
+            n_hit++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+        n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&counts[0], n_eval);
+        atomicAdd(&counts[1], n_hit);
+    }
+}
+
+int launch_blend_count(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
+                       unsigned long long* counts, cudaStream_t stream) {
+    LG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), stream));
+    const dim3 grid(num_tiles_x(W), num_tiles_y(H), 1);
+    blend_count_kernel<<<grid, LG_TILE_PIX, 0, stream>>>(img.ranges, b.point_list, W, H, (int)grid.x, g.means2D,
+                                                         g.conic_opacity, counts);
+    LG_LAUNCH_CHECK(false, stream);
+    return LG_OK;
+}
+
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream) {

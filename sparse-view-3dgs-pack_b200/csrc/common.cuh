@@ -16,6 +16,11 @@ namespace lg {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
+void count_launch();
+// optional per-stage CUDA-event timing (lg_stage_timing_enable); no-ops when disabled
+enum Stage { ST_PREPROCESS = 0, ST_BINNING, ST_BLEND_FWD, ST_BLEND_BWD, ST_PREGRAD, ST_COUNT };
+void stage_begin(int stage, cudaStream_t stream);
+void stage_end(int stage, cudaStream_t stream);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define LG_CUDA(call)                                                            \
@@ -28,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // (the reference's CHECK_CUDA(debug) behaviour, DGR/cuda_rasterizer/auxiliary.h:178-185).
 #define LG_LAUNCH_CHECK(debug, stream)                                           \
     do {                                                                         \
+        lg::count_launch();                                                      \
         LG_CUDA(cudaGetLastError());                                             \
         if (debug) LG_CUDA(cudaStreamSynchronize(stream));                       \
     } while (0)
@@ -110,6 +116,8 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream);
+int launch_blend_count(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
+                       unsigned long long* counts, cudaStream_t stream);
 int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, const BinningState& b,
                           const ImageState& img, const float* features, const float* background,
                           const float* dL_dpix, const float* dL_dinvdepth_pix, float* grad_scratch, bool debug,

@@ -54,6 +54,8 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 
 
 class _RasterizeGaussians(torch.autograd.Function):
+    last_call = None
+
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings):
@@ -93,6 +95,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 int(bool(rs.debug)), _lib.stream_ptr(device), ctypes.byref(num_rendered))
         _lib.check(rc, RuntimeError)
 
+        # inspection hook for benchmarks / tests (work counters, state read-back); not used by the operator itself
+        _RasterizeGaussians.last_call = dict(num_rendered=num_rendered.value, P=P, channels=channels, W=W, H=H,
+                                             geom=geom.tensor, binning=binning.tensor, img=img.tensor)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered.value
         ctx.channels = channels

@@ -68,6 +68,13 @@ def _load():
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i
     lib.lg_haar_dwt2_backward.argtypes = [_P, _P, i, i, i, _P, _P]
+    lib.lg_blend_work_count.restype = i
+    lib.lg_blend_work_count.argtypes = [i, i, i, i, i, _P, _P, _P, _P, _P]
+    lib.lg_launch_count.restype = ctypes.c_ulonglong
+    lib.lg_stage_timing_enable.restype = i
+    lib.lg_stage_timing_enable.argtypes = [i]
+    lib.lg_stage_timing_read.restype = i
+    lib.lg_stage_timing_read.argtypes = [i, ctypes.POINTER(f), i]
     if lib.lg_abi_version() != 1:
         raise ImportError("liblgdwt_b200.so has ABI version %d, expected 1" % lib.lg_abi_version())
     return lib
@@ -92,6 +99,21 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+STAGES = ("preprocess", "binning", "blend_forward", "blend_backward", "preprocess_backward")
+
+
+def stage_timing(slots):
+    """arm (slots > 0) or disarm (0) the per-stage CUDA-event ring"""
+    check(lib.lg_stage_timing_enable(int(slots)))
+
+
+def read_stage_times(slot):
+    """dict stage -> milliseconds recorded in ring slot `slot` (-1 = stage did not run)"""
+    buf = (ctypes.c_float * len(STAGES))()
+    check(lib.lg_stage_timing_read(int(slot), buf, len(STAGES)))
+    return {name: float(buf[k]) for k, name in enumerate(STAGES)}
 
 
 class ResizableBuffer:

@@ -1,0 +1,56 @@
+"""Seeded inputs shared by the golden-vector generators and the tests that consume the fixtures."""
+import numpy as np
+
+
+def dwt_case_inputs(name, C, H, W):
+    rng = np.random.default_rng(sum(map(ord, name)))
+    gt = rng.random((C, H, W)).astype(np.float32)
+    pred = np.clip(gt + 0.05 * rng.standard_normal((C, H, W)), 0, 1).astype(np.float32)
+    return pred, gt
+
+
+RASTER_CASES = {
+    # name: (P, seed, spacing_scale, W, H, antialiasing, mode)
+    "g_sh": (800, 11, 0.11, 120, 72, False, "sh"),
+    "g_sh_aa": (800, 12, 0.09, 104, 88, True, "sh"),
+    "g_precomp": (600, 13, 0.12, 96, 64, False, "precomp"),
+}
+
+
+def raster_case(name):
+    """(scene, camera, bg, extras) for a golden rasterizer case; extras holds colors_precomp / cov3D_precomp and the
+    upstream gradients."""
+    import math
+    from lgdwt_b200 import scenes
+    P, seed, spacing, W, H, aa, mode = RASTER_CASES[name]
+    rng = np.random.default_rng(seed)
+    base = scenes.blender_init_scene(P, seed=seed, spacing_scale=spacing)
+    # anisotropic scales + random rotations so that no gradient is analytically zero
+    scales = (base.scales * np.exp(rng.normal(0, 0.4, (P, 3)))).astype(np.float32)
+    q = rng.standard_normal((P, 4))
+    rots = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    opac = (1.0 / (1.0 + np.exp(-rng.normal(0.0, 1.5, (P, 1))))).astype(np.float32)
+    sc = scenes.Scene(base.means3D, scales, rots, opac, base.shs, 3)
+    cam = scenes.look_at_camera(W, H, 0.6911, 0.6911 * H / W, (0.4, -0.3, -4.03))
+    bg = np.array([0.1, 0.4, 0.7], np.float32)
+    ex = {"aa": aa, "mode": mode,
+          "dL_dpix": rng.standard_normal((3, H, W)).astype(np.float32),
+          "dL_dinvd": rng.standard_normal((1, H, W)).astype(np.float32)}
+    if mode == "precomp":
+        ex["colors_precomp"] = rng.random((P, 3)).astype(np.float32)
+        r, x, y, z = rots[:, 0], rots[:, 1], rots[:, 2], rots[:, 3]
+        Rm = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                       2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                       2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+        Lm = Rm * scales[:, None, :]
+        Sg = Lm @ Lm.transpose(0, 2, 1)
+        ex["cov3D_precomp"] = np.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]],
+                                       1).astype(np.float32)
+    return sc, cam, bg, ex
+
+
+def knn_points(P=6000, seed=5):
+    rng = np.random.default_rng(seed)
+    pts = rng.normal(0, 1.0, (P, 3)).astype(np.float32)
+    pts[: P // 50] = pts[P // 50: 2 * (P // 50)]  # exact duplicates -> zero distances, like COLMAP clouds have
+    return pts

@@ -7,7 +7,6 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_dgr.so")
 
 STATE_DTYPES = {
     "depths": (torch.float32, lambda P, C, N, T, R: P),
@@ -125,109 +124,7 @@ def backward_ours(t, c, cam, bg, fwd, dL_dpix, dL_dinvd=None, sh_degree=3, color
     return g
 
 
-# ----------------------------------------------------------------------------- reference (oracle/_ref) side
-_REF = None
-REF_ALLOC = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
-
-
-def load_ref():
-    """ctypes handle of the prebuilt reference shim, or None when oracle/_ref was not built (no /root/reference)."""
-    global _REF
-    if _REF is None and os.path.exists(REF_LIB):
-        lib = ctypes.CDLL(REF_LIB)
-        lib.ref_last_error.restype = ctypes.c_char_p
-        i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
-        lib.ref_rasterize_forward.restype = i
-        lib.ref_rasterize_forward.argtypes = ([REF_ALLOC, p] * 3 + [i, i, i, p, i, i] + [p] * 5 + [f] + [p] * 5 +
-                                              [f, f, i, p, p, i, p, i, ctypes.POINTER(i)])
-        lib.ref_rasterize_backward.restype = i
-        lib.ref_rasterize_backward.argtypes = ([i, i, i, i, p, i, i] + [p] * 5 + [f] + [p] * 5 + [f, f] + [p] * 16 +
-                                               [i, i])
-        lib.ref_state_read.restype = i
-        lib.ref_state_read.argtypes = [ctypes.c_char_p, i, i, i, i, p, p, p, p, ctypes.c_size_t]
-        lib.ref_mark_visible.restype = i
-        lib.ref_mark_visible.argtypes = [i, p, p, p, p]
-        lib.ref_knn_mean_dist2.restype = i
-        lib.ref_knn_mean_dist2.argtypes = [i, p, p]
-        _REF = lib
-    return _REF
-
-
-def _ref_check(lib, rc):
-    if rc != 0:
-        raise RuntimeError("reference shim: " + lib.ref_last_error().decode())
-
-
-def run_ref(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
-            scale_modifier=1.0, debug=False, want_state=True):
-    lib = load_ref()
-    dev = t["means3D"].device
-    P = t["means3D"].shape[0]
-    H, W = cam.image_height, cam.image_width
-    color = torch.zeros((3, H, W), device=dev)
-    invd = torch.zeros((1, H, W), device=dev)
-    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = (_Buf(REF_ALLOC, dev) for _ in range(3))
-    R = ctypes.c_int(0)
-    shs = None if colors_precomp is not None else t["shs"]
-    M = 0 if shs is None else shs.shape[1]
-    scales = None if cov3D_precomp is not None else t["scales"]
-    rots = None if cov3D_precomp is not None else t["rotations"]
-    torch.cuda.synchronize()
-    rc = lib.ref_rasterize_forward(
-        geom.cb, None, binning.cb, None, img.cb, None, P, sh_degree, M, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs),
-        _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp),
-        _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, 0, _ptr(color),
-        _ptr(invd), int(antialiasing), _ptr(radii), int(debug), ctypes.byref(R))
-    _ref_check(lib, rc)
-    torch.cuda.synchronize()
-    out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,
-           "binning": binning.tensor, "img": img.tensor, "C": 3, "M": M}
-    if want_state:
-        N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
-        for name, (dt, nfn) in STATE_DTYPES.items():
-            if name == "rgb" and colors_precomp is not None:
-                continue
-            n = nfn(P, 3, N, T, R.value)
-            dst = torch.zeros(max(n, 1), dtype=dt, device=dev)
-            rc = lib.ref_state_read(name.encode(), P, W, H, R.value, _ptr(geom.tensor), _ptr(binning.tensor),
-                                    _ptr(img.tensor), dst.data_ptr(), dst.numel() * dst.element_size())
-            _ref_check(lib, rc)
-            out[name] = dst[:n]
-    torch.cuda.synchronize()
-    return out
-
-
-def backward_ref(t, c, cam, bg, fwd, dL_dpix, dL_dinvd=None, sh_degree=3, colors_precomp=None, cov3D_precomp=None,
-                 antialiasing=False, scale_modifier=1.0, debug=False):
-    lib = load_ref()
-    dev = t["means3D"].device
-    P = t["means3D"].shape[0]
-    H, W = cam.image_height, cam.image_width
-    M = fwd["M"]
-    shs = None if colors_precomp is not None else t["shs"]
-    scales = None if cov3D_precomp is not None else t["scales"]
-    rots = None if cov3D_precomp is not None else t["rotations"]
-    z = lambda *s: torch.zeros(s, device=dev)  # the reference requires zero-initialised gradient buffers
-    g = {"dL_dmean2D": z(P, 3), "dL_dconic": z(P, 4), "dL_dopacity": z(P, 1), "dL_dcolor": z(P, 3),
-         "dL_dinvdepth": z(P, 1), "dL_dmean3D": z(P, 3), "dL_dcov3D": z(P, 6), "dL_dsh": z(P, max(M, 1), 3),
-         "dL_dscale": z(P, 3), "dL_drot": z(P, 4)}
-    torch.cuda.synchronize()
-    rc = lib.ref_rasterize_backward(
-        P, sh_degree, M, fwd["num_rendered"], _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp),
-        _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]),
-        _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]),
-        _ptr(fwd["binning"]), _ptr(fwd["img"]), _ptr(dL_dpix), _ptr(dL_dinvd), _ptr(g["dL_dmean2D"]),
-        _ptr(g["dL_dconic"]), _ptr(g["dL_dopacity"]), _ptr(g["dL_dcolor"]),
-        _ptr(g["dL_dinvdepth"]) if dL_dinvd is not None else None, _ptr(g["dL_dmean3D"]), _ptr(g["dL_dcov3D"]),
-        _ptr(g["dL_dsh"]), _ptr(g["dL_dscale"]), _ptr(g["dL_drot"]), int(antialiasing), int(debug))
-    _ref_check(lib, rc)
-    torch.cuda.synchronize()
-    if shs is None:
-        g["dL_dsh"] = None
-    if dL_dinvd is None:
-        g["dL_dinvdepth"] = None
-    return g
+from oracle.ref_cuda import REF_LIB, backward_ref, load_ref, run_ref  # noqa: E402,F401  (reference side)
 
 
 def rel_err(a, b):
