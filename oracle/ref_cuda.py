@@ -36,14 +36,21 @@ def _ptr(t):
 
 
 class _Buf:
-    def __init__(self, fn_type, device):
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.device = device
-        self.cb = fn_type(self._alloc)
+    """resizable uint8 buffer + ctypes callback (closure over a list: no reference cycle, see lgdwt_b200/_lib.py)"""
 
-    def _alloc(self, _ctx, n):
-        self.tensor = torch.empty(int(n), dtype=torch.uint8, device=self.device)
-        return self.tensor.data_ptr()
+    def __init__(self, fn_type, device):
+        holder = [torch.empty(0, dtype=torch.uint8, device=device)]
+
+        def _alloc(_ctx, n, _holder=holder, _device=device):
+            _holder[0] = torch.empty(int(n), dtype=torch.uint8, device=_device)
+            return _holder[0].data_ptr()
+
+        self._holder = holder
+        self.cb = fn_type(_alloc)
+
+    @property
+    def tensor(self):
+        return self._holder[0]
 
 
 _REF = None

@@ -33,14 +33,18 @@ struct DwtWorkspace {
 struct HaarBands { float ll, lh, hl, hh; };
 
 // one 2x2 analysis step in the operation order of pytorch_wavelets' AFB2D: filter along W, then along H
+// Explicitly rounded (never FMA-contracted) so that s*a - s*b is exactly 0 when a == b — at the symmetric-extension
+// boundary and on flat regions the high bands must vanish exactly, otherwise sign() of a rounding residual leaks a
+// spurious +-1 into the gradient — and so that every band equals the fp32 strided-convolution result bit for bit.
 __device__ __forceinline__ HaarBands haar2x2(float x00, float x01, float x10, float x11) {
-    const float lo_t = DWT_S * x00 + DWT_S * x01, hi_t = DWT_S * x00 - DWT_S * x01;
-    const float lo_b = DWT_S * x10 + DWT_S * x11, hi_b = DWT_S * x10 - DWT_S * x11;
+    const float a0 = F_MUL(DWT_S, x00), a1 = F_MUL(DWT_S, x01), b0 = F_MUL(DWT_S, x10), b1 = F_MUL(DWT_S, x11);
+    const float lo_t = F_MUL(DWT_S, F_ADD(a0, a1)), hi_t = F_MUL(DWT_S, F_SUB(a0, a1));
+    const float lo_b = F_MUL(DWT_S, F_ADD(b0, b1)), hi_b = F_MUL(DWT_S, F_SUB(b0, b1));
     HaarBands b;
-    b.ll = DWT_S * lo_t + DWT_S * lo_b;
-    b.lh = DWT_S * lo_t - DWT_S * lo_b;
-    b.hl = DWT_S * hi_t + DWT_S * hi_b;
-    b.hh = DWT_S * hi_t - DWT_S * hi_b;
+    b.ll = F_ADD(lo_t, lo_b);
+    b.lh = F_SUB(lo_t, lo_b);
+    b.hl = F_ADD(hi_t, hi_b);
+    b.hh = F_SUB(hi_t, hi_b);
     return b;
 }
 

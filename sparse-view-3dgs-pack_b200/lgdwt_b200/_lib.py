@@ -118,16 +118,25 @@ def read_stage_times(slot):
 
 class ResizableBuffer:
     """A torch.uint8 CUDA tensor the library can grow through an lg_alloc_fn callback — the counterpart of the
-    reference's resizeFunctional lambdas (DGR/rasterize_points.cu:27-33)."""
+    reference's resizeFunctional lambdas (DGR/rasterize_points.cu:27-33).
+
+    The ctypes callback closes over a plain list, not over `self`: a bound-method callback would form a reference
+    cycle (buffer -> callback -> buffer) and the hundreds of megabytes of state would then only be released by the
+    cyclic garbage collector instead of by reference counting."""
 
     def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.callback = ALLOC_FN(self._alloc)
+        holder = [torch.empty(0, dtype=torch.uint8, device=device)]
 
-    def _alloc(self, _ctx, nbytes):
-        try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
-        except Exception:  # surfaced as LG_ERR_ALLOC by the library
-            return 0
+        def _alloc(_ctx, nbytes, _holder=holder, _device=device):
+            try:
+                _holder[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=_device)
+                return _holder[0].data_ptr()
+            except Exception:  # surfaced as LG_ERR_ALLOC by the library
+                return 0
+
+        self._holder = holder
+        self.callback = ALLOC_FN(_alloc)
+
+    @property
+    def tensor(self):
+        return self._holder[0]

@@ -255,7 +255,14 @@ def test_fused_dwt_loss_full_size_config1():
     assert abs(float(dwt) - float(d64)) <= 2e-6 * float(d64)
     assert abs(float(patch) - float(p64)) <= 2e-6 * float(p64)
     assert int(details[10]) == int(mask.sum()) == 9
-    assert np.abs(p.grad.cpu().numpy() - po.grad.numpy()).max() <= 1e-6
+    # image gradient: identical to the fp32 oracle (same roundings => same signs) ...
+    p32 = torch.from_numpy(pred).requires_grad_(True)
+    d32, q32, _, _ = dwt_oracle.lgdwt_losses(p32, torch.from_numpy(gt))
+    (d32 + 0.1 * q32).backward()
+    assert np.abs(p.grad.cpu().numpy() - p32.grad.numpy()).max() <= 1e-6 * 1e-3
+    # ... and equal to the fp64 oracle except where an fp32 sub-band difference rounds across zero (sign flip)
+    d = np.abs(p.grad.cpu().numpy() - po.grad.numpy())
+    assert (d > 1e-9).mean() <= 1e-4 and d.max() <= 4.2e-6
 
 
 def test_pytorch_wavelets_compat_module():
