@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec) {
     constexpr int NV = 7 + C;
     __shared__ uint32_t s_id[BWD_BATCH];
-    __shared__ float2 s_xy[BWD_BATCH];
+    __shared__ float4 s_xy[BWD_BATCH];  // mean.x, mean.y, cut-off radius^2, unused
     __shared__ float4 s_co[BWD_BATCH];
     __shared__ float s_feat[BWD_BATCH * (C + 1)];
     __shared__ uint32_t s_max;
@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+    const float patch_x0 = (float)(tile_x * LG_TILE_X + (warp & 1u) * 8u), patch_x1 = patch_x0 + 7.0f;
+    const float patch_y0 = (float)(tile_y * LG_TILE_Y + (warp >> 1) * 4u), patch_y1 = patch_y0 + 3.0f;
     const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
 
     const float T_final = inside ? final_Ts[pix_id] : 0.0f;
@@ -102,8 +104,10 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
         if (progress < n_eff) {
             const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
             s_id[tid] = id;
-            s_xy[tid] = means2D[id];
-            s_co[tid] = conic_opacity[id];
+            const float2 m = means2D[id];
+            const float4 cq = conic_opacity[id];
+            s_xy[tid] = make_float4(m.x, m.y, lg_cutoff_radius2(cq), 0.0f);
+            s_co[tid] = cq;
 #pragma unroll
             for (int c = 0; c < C; c++) s_feat[tid * (C + 1) + c] = colors[(size_t)id * C + c];
             if (INVD) s_feat[tid * (C + 1) + C] = 1.0f / depths[id];
@@ -113,7 +117,12 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
         for (int j = 0; j < batch; j++) {
             const uint32_t rel = n_eff - 1u - ((uint32_t)i * BWD_BATCH + (uint32_t)j);  // 0-based position in the list
             if (rel >= warp_max) continue;  // behind every pixel's last contributor in this warp (warp-uniform)
-            const float2 xy = s_xy[j];
+            const float4 xy = s_xy[j];
+            {   // whole-warp reject, identical to the forward's (a skipped entry has alpha < 1/255 on every pixel)
+                const float ex = xy.x - fminf(fmaxf(xy.x, patch_x0), patch_x1);
+                const float ey = xy.y - fminf(fmaxf(xy.y, patch_y0), patch_y1);
+                if (ex * ex + ey * ey > xy.z) continue;
+            }
             const float4 co = s_co[j];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));

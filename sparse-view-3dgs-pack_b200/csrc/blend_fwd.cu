@@ -5,6 +5,9 @@
 // exact operation order of the reference's sm_100a build and the same libdevice expf (this file
 // must never be compiled with --use_fast_math).  Only the thread->pixel mapping and the data staging differ:
 //  - a warp covers an 8x4 pixel patch (better hit coherence than the reference's 16x2 rows);
+//  - while a batch is staged, every entry gets an 8-bit mask of the patches it can reach at all (conservative
+//    alpha >= 1/255 radius); each warp compacts its own order-preserving list with ballots and only evaluates those
+//    entries — a skipped entry would have failed the reference's alpha test on all 32 pixels, so results are unchanged;
 //  - colours and 1/depth are staged in shared memory with the geometry, so a hit never touches global memory
 //    (the reference gathers features[] / depths[] per hit, forward.cu:372,375).
 #include "common.cuh"
@@ -26,6 +29,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
     __shared__ float2 s_xy[BLEND_BATCH];
     __shared__ float4 s_co[BLEND_BATCH];
     __shared__ __align__(16) float s_feat[BLEND_BATCH * FS];  // C colours then 1/depth
+    __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
+    __shared__ uint8_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -34,6 +39,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+    const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
 
     const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
     const int rounds = (int)((range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH);
@@ -41,7 +47,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
 
     bool done = !inside;
     float T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
     float acc[C];
 #pragma unroll
     for (int c = 0; c < C; c++) acc[c] = 0.0f;
@@ -49,19 +55,28 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
 
     for (int i = 0; i < rounds; i++, to_do -= BLEND_BATCH) {
         if (__syncthreads_count(done) == LG_TILE_PIX) break;
+        // ---- stage one batch of the tile's depth-sorted list, with the per-patch reach mask of every entry
         const uint32_t progress = (uint32_t)i * BLEND_BATCH + tid;
+        unsigned mask = 0;
         if (range.x + progress < range.y) {
             const uint32_t id = point_list[range.x + progress];
-            s_xy[tid] = means2D[id];
-            s_co[tid] = conic_opacity[id];
+            const float2 m = means2D[id];
+            const float4 co = conic_opacity[id];
+            mask = lg_patch_mask(m.x, m.y, lg_cutoff_radius2(co), tile_x0, tile_y0);
+            s_xy[tid] = m;
+            s_co[tid] = co;
 #pragma unroll
             for (int c = 0; c < C; c++) s_feat[tid * FS + c] = features[(size_t)id * C + c];
             s_feat[tid * FS + C] = F_RCP(depths[id]);
         }
+        s_mask[tid] = (uint8_t)mask;
         __syncthreads();
         const int batch = min(BLEND_BATCH, to_do);
-        for (int j = 0; !done && j < batch; j++) {
-            contributor++;
+        // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)
+        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, batch, batch);
+        const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
+        for (int k = 0; !done && k < cnt; k++) {
+            const int j = s_list[warp][k];
             const float2 xy = s_xy[j];
             const float4 co = s_co[j];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
@@ -90,7 +105,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
                 acc_invd = F_FMA(T, F_MUL(alpha, s_feat[j * 8 + C]), acc_invd);
             }
             T = test_T;
-            last_contributor = contributor;
+            last_contributor = batch_base + (uint32_t)j + 1u;  // 1-based position in the tile list (forward.cu:345,381)
         }
     }
 

@@ -202,6 +202,62 @@ __device__ __forceinline__ void lg_get_rect(float px, float py, int radius, int 
              (uint32_t)max(0, __float2int_rz(F_MUL(F_ADD(F_ADD(F_ADD(py, r), 16.0f), -1.0f), 0.0625f))));
 }
 
+// Conservative per-Gaussian cut-off used by the blend kernels to let a whole warp (an 8x4 pixel patch) skip a list
+// entry: alpha = o * exp(power) >= 1/255 needs power >= -ln(255 o), and power(p) <= -0.5 * lambda_min(Q) * |p - mean|^2
+// (Q = conic).  Returns r2 such that |p - mean|^2 > r2  ==>  alpha < 1/255 with a 1 % margin in alpha — five orders of
+// magnitude above the fp32 rounding of `power`, so the skip can never change a decision the reference takes.
+__device__ __forceinline__ float lg_cutoff_radius2(float4 conic_opacity) {
+    const float a = conic_opacity.x, b = conic_opacity.y, c = conic_opacity.z, o = conic_opacity.w;
+    const float mid = 0.5f * (a + c);
+    const float lam_min = mid - sqrtf(fmaxf(0.25f * (a - c) * (a - c) + b * b, 0.0f));
+    const float k = 0.5f * lam_min * 0.999f;
+    if (!(k > 0.0f) || !(o > 0.0f)) return k > 0.0f ? -1.0f : 3.0e38f;  // o <= 0 never contributes; bad conic: never skip
+    const float L = __logf(255.0f * o) + 0.01f;
+    return L / k;  // negative when o < 1/255: every pixel is skipped
+}
+
+// 8-bit mask over the eight 8x4 pixel patches (= warps) of a 16x16 tile: bit (r*2 + k) is set when the patch whose
+// pixel centres span x in [tx0+8k, tx0+8k+7], y in [ty0+4r, ty0+4r+3] has a pixel within the cut-off radius of the
+// Gaussian mean.  A clear bit means alpha < 1/255 on every pixel of that patch (see lg_cutoff_radius2).
+__device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float r2cut, float tx0, float ty0) {
+    float ex2[2], ey2[4];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float x0 = tx0 + 8.0f * k;
+        const float e = mx - fminf(fmaxf(mx, x0), x0 + 7.0f);
+        ex2[k] = e * e;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float y0 = ty0 + 4.0f * r;
+        const float e = my - fminf(fmaxf(my, y0), y0 + 3.0f);
+        ey2[r] = e * e;
+    }
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) m |= (ex2[k] + ey2[r] <= r2cut) ? (1u << (r * 2 + k)) : 0u;
+    return m;
+}
+
+// Warp `w` turns the per-entry patch masks of a staged batch into its own compacted, order-preserving list of entry
+// slots (slots < `limit` only).  Returns the list length.  Only warp w reads list_w afterwards.
+__device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, uint8_t* list_w, unsigned w, unsigned lane,
+                                                     int batch, int limit) {
+    int cnt = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < batch; base += 32) {
+        const int slot = base + (int)lane;
+        const bool bit = slot < limit && ((s_mask[slot] >> w) & 1u);
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        if (bit) list_w[cnt + __popc(bal & lt)] = (uint8_t)slot;
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+    return cnt;
+}
+
 // 128-bit read-only streaming load
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 #endif
