@@ -45,6 +45,15 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, 
     valid = cnt >= 1;
 }
 
+template <int C>
+struct BwdFeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
+
+// Per-Gaussian record accumulated here (LG_REC floats, consumed by preprocess_backward_kernel):
+//   [0] sum w*dx   [1] sum w*dy   [2] sum w*dx^2   [3] sum w*dx*dy   [4] sum w*dy^2   [5] sum w
+//   [6] sum alpha*T*dL/dinvdepth_pix   [7..7+C) sum alpha*T*dL/dpix_c
+// with w = G * dL/dalpha and (dx, dy) = mean2D - pixel.  The reference's dL/dmean2D, dL/dconic and dL/dopacity
+// (backward.cu:598-632) are linear in these moments with per-Gaussian coefficients (conic, opacity), so the
+// coefficients are applied once per Gaussian in the per-Gaussian kernel instead of once per (pixel, Gaussian) hit.
 template <int C, bool INVD>
 __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
@@ -52,11 +61,15 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec) {
-    constexpr int NV = 7 + C;
+    constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
+    constexpr int VC = 6 + (INVD ? 1 : 0);      // first colour slot among the reduced values
+    constexpr int FS = BwdFeatStride<C>::value;
     __shared__ uint32_t s_id[BWD_BATCH];
-    __shared__ float4 s_xy[BWD_BATCH];  // mean.x, mean.y, cut-off radius^2, unused
+    __shared__ float2 s_xy[BWD_BATCH];
     __shared__ float4 s_co[BWD_BATCH];
-    __shared__ float s_feat[BWD_BATCH * (C + 1)];
+    __shared__ __align__(16) float s_feat[BWD_BATCH * FS];  // C colours then 1/depth
+    __shared__ uint8_t s_mask[BWD_BATCH];                    // per staged entry: which of the 8 patches it can touch
+    __shared__ uint8_t s_list[LG_TILE_PIX / 32][BWD_BATCH];  // per warp: compacted slots it must evaluate
     __shared__ uint32_t s_max;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -66,8 +79,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
-    const float patch_x0 = (float)(tile_x * LG_TILE_X + (warp & 1u) * 8u), patch_x1 = patch_x0 + 7.0f;
-    const float patch_y0 = (float)(tile_y * LG_TILE_Y + (warp >> 1) * 4u), patch_y1 = patch_y0 + 3.0f;
+    const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
     const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
 
     const float T_final = inside ? final_Ts[pix_id] : 0.0f;
@@ -92,37 +104,42 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
         last_color[c] = 0.0f;
         bg_dot_dpixel += bg_color[c] * dL_dpixel[c];
     }
+    const float bg_term = -T_final * bg_dot_dpixel;
     float dL_invd = 0.0f, accum_invd_rec = 0.0f, last_invd = 0.0f;
     if (INVD) dL_invd = inside ? dL_dinvdepth_pix[pix_id] : 0.0f;
     float last_alpha = 0.0f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
     const int rounds = (int)((n_eff + BWD_BATCH - 1) / BWD_BATCH);
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
-        const uint32_t progress = (uint32_t)i * BWD_BATCH + tid;
+        // ---- stage one batch, back to front, with the per-patch reach mask of every entry
+        const uint32_t batch_base = (uint32_t)i * BWD_BATCH;
+        const uint32_t progress = batch_base + tid;
+        unsigned mask = 0;
         if (progress < n_eff) {
             const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
             s_id[tid] = id;
             const float2 m = means2D[id];
             const float4 cq = conic_opacity[id];
-            s_xy[tid] = make_float4(m.x, m.y, lg_cutoff_radius2(cq), 0.0f);
+            mask = lg_patch_mask(m.x, m.y, lg_cutoff_radius2(cq), tile_x0, tile_y0);
+            s_xy[tid] = m;
             s_co[tid] = cq;
 #pragma unroll
-            for (int c = 0; c < C; c++) s_feat[tid * (C + 1) + c] = colors[(size_t)id * C + c];
-            if (INVD) s_feat[tid * (C + 1) + C] = 1.0f / depths[id];
+            for (int c = 0; c < C; c++) s_feat[tid * FS + c] = colors[(size_t)id * C + c];
+            if (INVD) s_feat[tid * FS + C] = 1.0f / depths[id];
         }
+        s_mask[tid] = (uint8_t)mask;
         __syncthreads();
-        const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - (uint32_t)i * BWD_BATCH);
-        for (int j = 0; j < batch; j++) {
-            const uint32_t rel = n_eff - 1u - ((uint32_t)i * BWD_BATCH + (uint32_t)j);  // 0-based position in the list
-            if (rel >= warp_max) continue;  // behind every pixel's last contributor in this warp (warp-uniform)
-            const float4 xy = s_xy[j];
-            {   // whole-warp reject, identical to the forward's (a skipped entry has alpha < 1/255 on every pixel)
-                const float ex = xy.x - fminf(fmaxf(xy.x, patch_x0), patch_x1);
-                const float ey = xy.y - fminf(fmaxf(xy.y, patch_y0), patch_y1);
-                if (ex * ex + ey * ey > xy.z) continue;
-            }
+        const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - batch_base);
+        // slots whose list position is behind this warp's last contributor are dropped with the unreachable ones:
+        // position rel = n_eff-1-(batch_base+j) < warp_max  <=>  j >= n_eff - warp_max - batch_base
+        const int first = (int)max((long long)n_eff - (long long)warp_max - (long long)batch_base, 0ll);
+        if (first >= batch) continue;
+        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, first, batch);
+        for (int k = 0; k < cnt; k++) {
+            const int j = s_list[warp][k];
+            const uint32_t rel = n_eff - 1u - (batch_base + (uint32_t)j);  // 0-based position in the tile's list
+            const float2 xy = s_xy[j];
             const float4 co = s_co[j];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
@@ -134,45 +151,46 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
 
             float v[NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++) v[k] = 0.0f;
+            for (int n = 0; n < NV; n++) v[n] = 0.0f;
             if (hit) {
-                T = T / (1.0f - alpha);
-                const float dchannel_dcolor = alpha * T;
+                const float rinv = __fdividef(1.0f, 1.0f - alpha);  // 1 - alpha in [0.01, 1]
+                T = T * rinv;
+                const float aT = alpha * T;
                 float dL_dalpha = 0.0f;
+                const float4 f4 = *reinterpret_cast<const float4*>(&s_feat[j * FS]);
+                const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const float col = s_feat[j * (C + 1) + c];
-                    accum_rec[c] = last_alpha * last_color[c] + (1.0f - last_alpha) * accum_rec[c];
+                    const float col = fv[c];
+                    accum_rec[c] = fmaf(last_alpha, last_color[c] - accum_rec[c], accum_rec[c]);
                     last_color[c] = col;
-                    dL_dalpha += (col - accum_rec[c]) * dL_dpixel[c];
-                    v[7 + c] = dchannel_dcolor * dL_dpixel[c];
+                    dL_dalpha = fmaf(col - accum_rec[c], dL_dpixel[c], dL_dalpha);
+                    v[VC + c] = aT * dL_dpixel[c];
                 }
                 if (INVD) {
-                    const float invd = s_feat[j * (C + 1) + C];
-                    accum_invd_rec = last_alpha * last_invd + (1.0f - last_alpha) * accum_invd_rec;
+                    const float invd = (FS == 4) ? fv[C < 4 ? C : 3] : s_feat[j * FS + C];
+                    accum_invd_rec = fmaf(last_alpha, last_invd - accum_invd_rec, accum_invd_rec);
                     last_invd = invd;
-                    dL_dalpha += (invd - accum_invd_rec) * dL_invd;
-                    v[6] = dchannel_dcolor * dL_invd;
+                    dL_dalpha = fmaf(invd - accum_invd_rec, dL_invd, dL_dalpha);
+                    v[6] = aT * dL_invd;
                 }
-                dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
-                const float dL_dG = co.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                const float dG_ddely = -gdy * co.z - gdx * co.y;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
+                dL_dalpha = fmaf(dL_dalpha, T, bg_term * rinv);
+                const float w = G * dL_dalpha;
+                const float wx = w * dx, wy = w * dy;
+                v[0] = wx;
+                v[1] = wy;
+                v[2] = wx * dx;
+                v[3] = wx * dy;
+                v[4] = wy * dy;
+                v[5] = w;
             }
             float total;
             int slot;
             bool ok;
             warp_multi_reduce<NV>(v, lane, total, slot, ok);
-            if (ok && (INVD || slot != 6)) atomicAdd(grad_rec + (size_t)s_id[j] * LG_REC + slot, total);
+            if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
+            if (ok) atomicAdd(grad_rec + (size_t)s_id[j] * LG_REC + slot, total);
         }
     }
 }

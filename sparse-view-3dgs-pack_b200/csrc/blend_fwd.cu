@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
         __syncthreads();
         const int batch = min(BLEND_BATCH, to_do);
         // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)
-        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, batch, batch);
+        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, 0, batch);
         const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
         for (int k = 0; !done && k < cnt; k++) {
             const int j = s_list[warp][k];

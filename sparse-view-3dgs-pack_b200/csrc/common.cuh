@@ -241,15 +241,15 @@ __device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float r2cu
     return m;
 }
 
-// Warp `w` turns the per-entry patch masks of a staged batch into its own compacted, order-preserving list of entry
-// slots (slots < `limit` only).  Returns the list length.  Only warp w reads list_w afterwards.
+// Warp `w` turns the per-entry patch masks of a staged batch into its own compacted, order-preserving list of the
+// entry slots in [lo, hi) that can reach its patch.  Returns the list length.  Only warp w reads list_w afterwards.
 __device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, uint8_t* list_w, unsigned w, unsigned lane,
-                                                     int batch, int limit) {
+                                                     int lo, int hi) {
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < batch; base += 32) {
+    for (int base = lo & ~31; base < hi; base += 32) {
         const int slot = base + (int)lane;
-        const bool bit = slot < limit && ((s_mask[slot] >> w) & 1u);
+        const bool bit = slot >= lo && slot < hi && ((s_mask[slot] >> w) & 1u);
         const unsigned bal = __ballot_sync(0xffffffffu, bit);
         if (bit) list_w[cnt + __popc(bal & lt)] = (uint8_t)slot;
         cnt += __popc(bal);

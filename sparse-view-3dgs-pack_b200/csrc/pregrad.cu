@@ -10,8 +10,9 @@ namespace lg {
 #define LG_REC 12
 
 struct PreGradArgs {
-    int P, D, M, C;
+    int P, D, M, C, W, H;
     const float* __restrict__ means3D;
+    const float4* __restrict__ conic_opacity;
     const int* __restrict__ radii;
     const float* __restrict__ shs;
     const uint8_t* __restrict__ clamped;
@@ -64,6 +65,20 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
         const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
         r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
         r[8] = r2.x; r[9] = r2.y; r[10] = r2.z; r[11] = r2.w;
+    }
+    // The blend backward accumulates the moments S = sum over hits of w*(dx, dy, dx^2, dx*dy, dy^2, 1) with
+    // w = G*dL/dalpha and d = mean2D - pixel; the reference's per-hit expressions (backward.cu:598-632) are linear
+    // in them: dL/dmean2D = -o*(a*Sx + b*Sy, c*Sy + b*Sx) * (W/2, H/2), dL/dconic = -o/2 * (Sxx, Sxy, Syy),
+    // dL/dopacity = S1.  Invisible Gaussians carry an all-zero record.
+    if (visible) {
+        const float4 co = a.conic_opacity[i];
+        const float sx = r[0], sy = r[1];
+        r[0] = -co.w * (co.x * sx + co.y * sy) * (0.5f * (float)a.W);
+        r[1] = -co.w * (co.z * sy + co.y * sx) * (0.5f * (float)a.H);
+        const float k = -0.5f * co.w;
+        r[2] *= k;
+        r[3] *= k;
+        r[4] *= k;
     }
     // pass-through outputs (blend-stage gradients)
     a.dL_dmean2D[3 * i + 0] = r[0];
@@ -347,7 +362,7 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
                                cudaStream_t stream) {
     PreGradArgs a;
     a.P = b.P; a.D = b.D; a.M = b.M; a.C = b.C;
-    a.means3D = b.means3D; a.radii = radii; a.shs = b.shs; a.clamped = g.clamped; a.opacities = b.opacities;
+    a.W = b.W; a.H = b.H; a.means3D = b.means3D; a.conic_opacity = g.conic_opacity; a.radii = radii; a.shs = b.shs; a.clamped = g.clamped; a.opacities = b.opacities;
     a.scales = b.scales; a.rotations = b.rotations; a.scale_modifier = b.scale_modifier;
     a.cov3Ds = b.cov3D_precomp ? b.cov3D_precomp : g.cov3D;
     a.view = b.viewmatrix; a.proj = b.projmatrix; a.campos = b.campos;
