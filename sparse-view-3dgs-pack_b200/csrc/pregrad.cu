@@ -45,18 +45,50 @@ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
                                  0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                  -0.5900435899266435f};
 
+// SH coefficients and their gradients are (P, M, 3) arrays: one Gaussian's 3M floats are contiguous, so a thread
+// walking its own Gaussian touches one 4-byte word per 32-byte sector per instruction.  Instead every warp moves the
+// contiguous 32 x 3M block of its 32 Gaussians with fully coalesced 128-byte accesses through a shared-memory tile
+// whose row stride (3M | 1) is odd, so the per-thread walks along a row are bank-conflict free.  The tile first holds
+// the coefficients (read by the owner thread), then the gradients (written by it), then the warp streams them out.
+// STAGED = false (3M > PG_MAX_ROW, or no SH path) keeps direct global accesses.
+#define PG_MAX_ROW 48
+
+template <bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a) {
+    extern __shared__ float s_tile_dyn[];
     __shared__ float s_cam[35];
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.view + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(a.campos + threadIdx.x - 32);
-    __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
+    const int M3 = a.M * 3;
+    const int row = M3 | 1;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32u;
+    float* s_wtile = s_tile_dyn + (size_t)warp * 32u * row;
+    int warp_floats = 0;
+    if (STAGED) {
+        const long long left = (long long)a.P - (long long)warp_first;
+        warp_floats = left <= 0 ? 0 : (int)(left < 32 ? left : 32) * M3;
+        const float* src = a.shs + warp_first * M3;
+        int g = (int)lane / M3, k = (int)lane % M3;
+        const int dg = 32 / M3, dk = 32 % M3;
+        for (int e = (int)lane; e < warp_floats; e += 32) {
+            s_wtile[g * row + k] = __ldg(src + e);
+            g += dg;
+            k += dk;
+            if (k >= M3) { k -= M3; g++; }
+        }
+    }
+    __syncthreads();
+    if (idx < a.P) {
     const float* V = s_cam;
     const float* PR = s_cam + 16;
     const size_t i = (size_t)idx;
     const int C = a.C;
+    // SH rows: the staged tile row is read (coefficients) and then overwritten (gradients) by this thread alone
+    const float* sh = STAGED ? s_wtile + lane * row : a.shs + i * M3;
+    float* out_sh = STAGED ? s_wtile + lane * row : a.dL_dsh + i * M3;
 
     const bool visible = a.radii[idx] > 0;
     float r[LG_REC];
@@ -206,17 +238,16 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
         }
     }
 
-    // ---------------- SH backward (backward.cu:23-142)
+    // ---------------- SH backward (backward.cu:23-142).  Every coefficient is read before its slot is written:
+    // in the staged variant `sh` and `out_sh` are the same shared-memory row.
     if (a.sh_path) {
-        float* out_sh = a.dL_dsh + i * a.M * 3;
         if (!visible) {
-            for (int k = 0; k < a.M * 3; k++) out_sh[k] = 0.f;
+            for (int k = 0; k < M3; k++) out_sh[k] = 0.f;
         } else {
             const float mx = a.means3D[3 * i + 0], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
             const float ox = mx - V[32], oy = my - V[33], oz = mz - V[34];
             const float ilen = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
             const float x = ox * ilen, y = oy * ilen, z = oz * ilen;
-            const float* sh = a.shs + i * a.M * 3;
             float g[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) g[c] = a.clamped[3 * i + c] ? 0.f : r[7 + c];
@@ -230,12 +261,13 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
                 written = 4;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
+                    const float s1 = sh[3 + c], s2 = sh[6 + c], s3 = sh[9 + c];
+                    dx[c] = -C1 * s3;
+                    dy[c] = -C1 * s1;
+                    dz[c] = C1 * s2;
                     out_sh[3 + c] = -C1 * y * g[c];
                     out_sh[6 + c] = C1 * z * g[c];
                     out_sh[9 + c] = -C1 * x * g[c];
-                    dx[c] = -C1 * sh[9 + c];
-                    dy[c] = -C1 * sh[3 + c];
-                    dz[c] = C1 * sh[6 + c];
                 }
                 if (deg > 1) {
                     written = 9;
@@ -244,15 +276,15 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
                                 b7 = c_SH_C2[3] * xz, b8 = c_SH_C2[4] * (xx - yy);
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
+                        const float s4 = sh[12 + c], s5 = sh[15 + c], s6 = sh[18 + c], s7 = sh[21 + c], s8 = sh[24 + c];
+                        dx[c] += c_SH_C2[0] * y * s4 + c_SH_C2[2] * 2.f * -x * s6 + c_SH_C2[3] * z * s7 + c_SH_C2[4] * 2.f * x * s8;
+                        dy[c] += c_SH_C2[0] * x * s4 + c_SH_C2[1] * z * s5 + c_SH_C2[2] * 2.f * -y * s6 + c_SH_C2[4] * 2.f * -y * s8;
+                        dz[c] += c_SH_C2[1] * y * s5 + c_SH_C2[2] * 2.f * 2.f * z * s6 + c_SH_C2[3] * x * s7;
                         out_sh[12 + c] = b4 * g[c];
                         out_sh[15 + c] = b5 * g[c];
                         out_sh[18 + c] = b6 * g[c];
                         out_sh[21 + c] = b7 * g[c];
                         out_sh[24 + c] = b8 * g[c];
-                        const float s4 = sh[12 + c], s5 = sh[15 + c], s6 = sh[18 + c], s7 = sh[21 + c], s8 = sh[24 + c];
-                        dx[c] += c_SH_C2[0] * y * s4 + c_SH_C2[2] * 2.f * -x * s6 + c_SH_C2[3] * z * s7 + c_SH_C2[4] * 2.f * x * s8;
-                        dy[c] += c_SH_C2[0] * x * s4 + c_SH_C2[1] * z * s5 + c_SH_C2[2] * 2.f * -y * s6 + c_SH_C2[4] * 2.f * -y * s8;
-                        dz[c] += c_SH_C2[1] * y * s5 + c_SH_C2[2] * 2.f * 2.f * z * s6 + c_SH_C2[3] * x * s7;
                     }
                     if (deg > 2) {
                         written = 16;
@@ -263,13 +295,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
                                     b15 = c_SH_C3[6] * x * (xx - 3.f * yy);
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            out_sh[27 + c] = b9 * g[c];
-                            out_sh[30 + c] = b10 * g[c];
-                            out_sh[33 + c] = b11 * g[c];
-                            out_sh[36 + c] = b12 * g[c];
-                            out_sh[39 + c] = b13 * g[c];
-                            out_sh[42 + c] = b14 * g[c];
-                            out_sh[45 + c] = b15 * g[c];
                             const float s9 = sh[27 + c], s10 = sh[30 + c], s11 = sh[33 + c], s12 = sh[36 + c],
                                         s13 = sh[39 + c], s14 = sh[42 + c], s15 = sh[45 + c];
                             dx[c] += c_SH_C3[0] * s9 * 3.f * 2.f * xy + c_SH_C3[1] * s10 * yz + c_SH_C3[2] * s11 * -2.f * xy +
@@ -282,11 +307,18 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
                             dz[c] += c_SH_C3[1] * s10 * xy + c_SH_C3[2] * s11 * 4.f * 2.f * yz +
                                      c_SH_C3[3] * s12 * 3.f * (2.f * zz - xx - yy) + c_SH_C3[4] * s13 * 4.f * 2.f * xz +
                                      c_SH_C3[5] * s14 * (xx - yy);
+                            out_sh[27 + c] = b9 * g[c];
+                            out_sh[30 + c] = b10 * g[c];
+                            out_sh[33 + c] = b11 * g[c];
+                            out_sh[36 + c] = b12 * g[c];
+                            out_sh[39 + c] = b13 * g[c];
+                            out_sh[42 + c] = b14 * g[c];
+                            out_sh[45 + c] = b15 * g[c];
                         }
                     }
                 }
             }
-            for (int k = written * 3; k < a.M * 3; k++) out_sh[k] = 0.f;  // coefficients above the active degree
+            for (int k = written * 3; k < M3; k++) out_sh[k] = 0.f;  // coefficients above the active degree
             const float ddir_x = dx[0] * g[0] + dx[1] * g[1] + dx[2] * g[2];
             const float ddir_y = dy[0] * g[0] + dy[1] * g[1] + dy[2] * g[2];
             const float ddir_z = dz[0] * g[0] + dz[1] * g[1] + dz[2] * g[2];
@@ -356,6 +388,20 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
     a.dL_dmean3D[3 * i + 2] = dmean[2];
 #pragma unroll
     for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * i + k] = dcov[k];
+    }  // idx < P
+
+    if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
+        __syncwarp();
+        float* dst = a.dL_dsh + warp_first * M3;
+        int g = (int)lane / M3, k = (int)lane % M3;
+        const int dg = 32 / M3, dk = 32 % M3;
+        for (int e = (int)lane; e < warp_floats; e += 32) {
+            dst[e] = s_wtile[g * row + k];
+            g += dg;
+            k += dk;
+            if (k >= M3) { k -= M3; g++; }
+        }
+    }
 }
 
 int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, const int* radii, bool debug,
@@ -374,7 +420,15 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
     a.dL_dmean2D = b.dL_dmean2D; a.dL_dconic = b.dL_dconic; a.dL_dopacity = b.dL_dopacity; a.dL_dcolor = b.dL_dcolor;
     a.dL_dinvdepth = b.dL_dinvdepth; a.dL_dmean3D = b.dL_dmean3D; a.dL_dcov3D = b.dL_dcov3D; a.dL_dsh = b.dL_dsh;
     a.dL_dscale = b.dL_dscale; a.dL_drot = b.dL_drot;
-    preprocess_backward_kernel<<<(b.P + 255) / 256, 256, 0, stream>>>(a);
+    const int M3 = 3 * b.M;
+    if (a.sh_path && M3 <= PG_MAX_ROW) {
+        const size_t smem = sizeof(float) * 256 * (size_t)(M3 | 1);
+        LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(float) * 256 * (PG_MAX_ROW | 1))));
+        preprocess_backward_kernel<true><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+    } else {
+        preprocess_backward_kernel<false><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
+    }
     LG_LAUNCH_CHECK(debug, stream);
     return LG_OK;
 }

@@ -13,6 +13,7 @@
 namespace lg {
 
 #define PRE_BLOCK 256
+#define PRE_MAX_ROW 48  // widest SH row (floats per Gaussian) staged through shared memory
 
 struct PreArgs {
     int P, D, M, C;
@@ -116,7 +117,9 @@ __device__ __forceinline__ void compute_cov3d(float sx0, float sy0, float sz0, f
     cov[5] = dot3_mid_first(M20, M20, M21, M21, M22, M22);   // f445
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
+    extern __shared__ float s_tile_dyn[];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_sums[PRE_BLOCK / 32];
     __shared__ uint32_t s_block_prefix;
@@ -134,10 +137,12 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
 
     uint32_t tiles = 0;
     int radius_out = 0;
+    bool need_sh = false;
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
     if (idx < a.P) {
-        const float px = __ldg(a.means3D + 3 * (size_t)idx + 0);
-        const float py = __ldg(a.means3D + 3 * (size_t)idx + 1);
-        const float pz = __ldg(a.means3D + 3 * (size_t)idx + 2);
+        px = __ldg(a.means3D + 3 * (size_t)idx + 0);
+        py = __ldg(a.means3D + 3 * (size_t)idx + 1);
+        pz = __ldg(a.means3D + 3 * (size_t)idx + 2);
         // in_frustum (auxiliary.h:151-176)
         const float depth = xform_row(px, py, pz, V[2], V[6], V[10], V[14]);  // f1
         if (!(depth > 0.2f)) {
@@ -228,73 +233,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                 lg_get_rect(pix_x, pix_y, radius, a.grid_x, a.grid_y, x0, y0, x1, y1);
                 const uint32_t n = (x1 - x0) * (y1 - y0);
                 if (n != 0) {
-                    // SH -> RGB (forward.cu:20-71); needs only 1e-5 image parity, same association order anyway
-                    if (a.colors_precomp == nullptr) {
-                        const float dx = F_SUB(px, V[32]), dy = F_SUB(py, V[33]), dz = F_SUB(pz, V[34]);
-                        const float len = F_SQRT(F_FMA(dz, dz, F_FMA(dx, dx, F_MUL(dy, dy))));
-                        const float x = F_DIV(dx, len), y = F_DIV(dy, len), z = F_DIV(dz, len);
-                        const float* sh = a.shs + (size_t)idx * a.M * 3;
-                        float r[3];
-#pragma unroll
-                        for (int c = 0; c < 3; c++) r[c] = F_MUL(__ldg(sh + c), 0.28209479177387814f);
-                        if (a.D > 0) {
-                            const float k1y = F_MUL(y, 0.4886025119029199f);
-                            const float k1z = F_MUL(z, 0.4886025119029199f);
-                            const float k1x = F_MUL(x, 0.4886025119029199f);
-#pragma unroll
-                            for (int c = 0; c < 3; c++) {
-                                float v = F_FMA(-k1y, __ldg(sh + 3 + c), r[c]);
-                                v = F_FMA(k1z, __ldg(sh + 6 + c), v);
-                                r[c] = F_FMA(-k1x, __ldg(sh + 9 + c), v);
-                            }
-                            if (a.D > 1) {
-                                const float xx = F_MUL(x, x), yy = F_MUL(y, y), zz = F_MUL(z, z);
-                                const float xy = F_MUL(x, y), yz = F_MUL(y, z), xz = F_MUL(x, z);
-                                const float zz2 = F_ADD(zz, zz);
-                                const float xx_yy = F_SUB(xx, yy);
-                                const float k4 = F_MUL(xy, 1.0925484305920792f);
-                                const float k5 = F_MUL(yz, -1.0925484305920792f);
-                                const float k6 = F_MUL(F_SUB(F_SUB(zz2, xx), yy), 0.31539156525252005f);
-                                const float k7 = F_MUL(xz, -1.0925484305920792f);
-                                const float k8 = F_MUL(xx_yy, 0.5462742152960396f);
-#pragma unroll
-                                for (int c = 0; c < 3; c++) {
-                                    float v = F_FMA(k4, __ldg(sh + 12 + c), r[c]);
-                                    v = F_FMA(k5, __ldg(sh + 15 + c), v);
-                                    v = F_FMA(k6, __ldg(sh + 18 + c), v);
-                                    v = F_FMA(k7, __ldg(sh + 21 + c), v);
-                                    r[c] = F_FMA(k8, __ldg(sh + 24 + c), v);
-                                }
-                                if (a.D > 2) {
-                                    const float zz4_xx_yy = F_SUB(F_FMA(zz, 4.0f, -xx), yy);
-                                    const float k9 = F_MUL(F_MUL(y, -0.5900435899266435f), F_FMA(xx, 3.0f, -yy));
-                                    const float k10 = F_MUL(z, F_MUL(xy, 2.890611442640554f));
-                                    const float k11 = F_MUL(F_MUL(y, -0.4570457994644658f), zz4_xx_yy);
-                                    const float k12 = F_MUL(F_MUL(z, 0.3731763325901154f), F_FMA(yy, -3.0f, F_FMA(xx, -3.0f, zz2)));
-                                    const float k13 = F_MUL(F_MUL(x, -0.4570457994644658f), zz4_xx_yy);
-                                    const float k14 = F_MUL(F_MUL(z, 1.445305721320277f), xx_yy);
-                                    const float k15 = F_MUL(F_MUL(x, -0.5900435899266435f), F_FMA(yy, -3.0f, xx));
-#pragma unroll
-                                    for (int c = 0; c < 3; c++) {
-                                        float v = F_FMA(k9, __ldg(sh + 27 + c), r[c]);
-                                        v = F_FMA(k10, __ldg(sh + 30 + c), v);
-                                        v = F_FMA(k11, __ldg(sh + 33 + c), v);
-                                        v = F_FMA(k12, __ldg(sh + 36 + c), v);
-                                        v = F_FMA(k13, __ldg(sh + 39 + c), v);
-                                        v = F_FMA(k14, __ldg(sh + 42 + c), v);
-                                        r[c] = F_FMA(k15, __ldg(sh + 45 + c), v);
-                                    }
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const float v = F_ADD(r[c], 0.5f);
-                            const bool neg = v < 0.0f;
-                            a.clamped[3 * (size_t)idx + c] = neg ? 1 : 0;
-                            a.rgb[3 * (size_t)idx + c] = neg ? 0.0f : v;
-                        }
-                    }
+                    need_sh = a.colors_precomp == nullptr;
                     a.depths[idx] = depth;
                     a.means2D[idx] = make_float2(pix_x, pix_y);
                     const float opacity = __ldg(a.opacities + idx);
@@ -306,6 +245,100 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         }
         a.radii[idx] = radius_out;
         a.tiles_touched[idx] = tiles;
+    }
+
+    // ---- SH -> RGB (forward.cu:20-71) for the Gaussians that survived culling; needs only 1e-5 image parity, the
+    // association order of the reference is kept anyway.  One Gaussian's 3M coefficients are contiguous, so the warp
+    // first moves the rows it needs into a shared-memory tile with coalesced 128-byte loads (row stride 3M | 1 is
+    // odd: the per-thread walk along a row is bank-conflict free); STAGED = false reads global memory directly.
+    {
+        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        const int M3 = a.M * 3;
+        const float* sh = a.shs + (size_t)idx * M3;
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need_sh);
+        if (STAGED && need_mask) {
+            const int row = M3 | 1;
+            float* s_wtile = s_tile_dyn + (size_t)warp * 32u * row;
+            const size_t warp_first = (size_t)tile * PRE_BLOCK + (size_t)warp * 32u;
+            const long long left = (long long)a.P - (long long)warp_first;
+            const int warp_floats = (int)(left < 32 ? left : 32) * M3;
+            const float* src = a.shs + warp_first * M3;
+            int g = (int)lane / M3, k = (int)lane % M3;
+            const int dg = 32 / M3, dk = 32 % M3;
+            for (int e = (int)lane; e < warp_floats; e += 32) {
+                if ((need_mask >> g) & 1u) s_wtile[g * row + k] = __ldg(src + e);
+                g += dg;
+                k += dk;
+                if (k >= M3) { k -= M3; g++; }
+            }
+            __syncwarp();
+            sh = s_wtile + lane * row;
+        }
+        if (need_sh) {
+            const float dx = F_SUB(px, V[32]), dy = F_SUB(py, V[33]), dz = F_SUB(pz, V[34]);
+            const float len = F_SQRT(F_FMA(dz, dz, F_FMA(dx, dx, F_MUL(dy, dy))));
+            const float x = F_DIV(dx, len), y = F_DIV(dy, len), z = F_DIV(dz, len);
+            float r[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) r[c] = F_MUL(sh[c], 0.28209479177387814f);
+            if (a.D > 0) {
+                const float k1y = F_MUL(y, 0.4886025119029199f);
+                const float k1z = F_MUL(z, 0.4886025119029199f);
+                const float k1x = F_MUL(x, 0.4886025119029199f);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float v = F_FMA(-k1y, sh[3 + c], r[c]);
+                    v = F_FMA(k1z, sh[6 + c], v);
+                    r[c] = F_FMA(-k1x, sh[9 + c], v);
+                }
+                if (a.D > 1) {
+                    const float xx = F_MUL(x, x), yy = F_MUL(y, y), zz = F_MUL(z, z);
+                    const float xy = F_MUL(x, y), yz = F_MUL(y, z), xz = F_MUL(x, z);
+                    const float zz2 = F_ADD(zz, zz);
+                    const float xx_yy = F_SUB(xx, yy);
+                    const float k4 = F_MUL(xy, 1.0925484305920792f);
+                    const float k5 = F_MUL(yz, -1.0925484305920792f);
+                    const float k6 = F_MUL(F_SUB(F_SUB(zz2, xx), yy), 0.31539156525252005f);
+                    const float k7 = F_MUL(xz, -1.0925484305920792f);
+                    const float k8 = F_MUL(xx_yy, 0.5462742152960396f);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float v = F_FMA(k4, sh[12 + c], r[c]);
+                        v = F_FMA(k5, sh[15 + c], v);
+                        v = F_FMA(k6, sh[18 + c], v);
+                        v = F_FMA(k7, sh[21 + c], v);
+                        r[c] = F_FMA(k8, sh[24 + c], v);
+                    }
+                    if (a.D > 2) {
+                        const float zz4_xx_yy = F_SUB(F_FMA(zz, 4.0f, -xx), yy);
+                        const float k9 = F_MUL(F_MUL(y, -0.5900435899266435f), F_FMA(xx, 3.0f, -yy));
+                        const float k10 = F_MUL(z, F_MUL(xy, 2.890611442640554f));
+                        const float k11 = F_MUL(F_MUL(y, -0.4570457994644658f), zz4_xx_yy);
+                        const float k12 = F_MUL(F_MUL(z, 0.3731763325901154f), F_FMA(yy, -3.0f, F_FMA(xx, -3.0f, zz2)));
+                        const float k13 = F_MUL(F_MUL(x, -0.4570457994644658f), zz4_xx_yy);
+                        const float k14 = F_MUL(F_MUL(z, 1.445305721320277f), xx_yy);
+                        const float k15 = F_MUL(F_MUL(x, -0.5900435899266435f), F_FMA(yy, -3.0f, xx));
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            float v = F_FMA(k9, sh[27 + c], r[c]);
+                            v = F_FMA(k10, sh[30 + c], v);
+                            v = F_FMA(k11, sh[33 + c], v);
+                            v = F_FMA(k12, sh[36 + c], v);
+                            v = F_FMA(k13, sh[39 + c], v);
+                            v = F_FMA(k14, sh[42 + c], v);
+                            r[c] = F_FMA(k15, sh[45 + c], v);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float v = F_ADD(r[c], 0.5f);
+                const bool neg = v < 0.0f;
+                a.clamped[3 * (size_t)idx + c] = neg ? 1 : 0;
+                a.rgb[3 * (size_t)idx + c] = neg ? 0.0f : v;
+            }
+        }
     }
 
     // ---- fused inclusive scan of tiles_touched: block scan + decoupled look-back across blocks
@@ -398,7 +431,15 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     const int blocks = (f.P + PRE_BLOCK - 1) / PRE_BLOCK;
     LG_CUDA(cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
     LG_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 8, stream));
-    preprocess_kernel<<<blocks, PRE_BLOCK, 0, stream>>>(a);
+    const int M3 = 3 * f.M;
+    if (f.colors_precomp == nullptr && M3 <= PRE_MAX_ROW) {
+        const size_t smem = sizeof(float) * PRE_BLOCK * (size_t)(M3 | 1);
+        LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(float) * PRE_BLOCK * (PRE_MAX_ROW | 1))));
+        preprocess_kernel<true><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+    } else {
+        preprocess_kernel<false><<<blocks, PRE_BLOCK, 0, stream>>>(a);
+    }
     LG_LAUNCH_CHECK(f.debug, stream);
     return LG_OK;
 }
