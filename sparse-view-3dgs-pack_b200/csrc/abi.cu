@@ -37,6 +37,13 @@ GeometryState GeometryState::from_chunk(char*& chunk, size_t P, int channels) {
     carve(chunk, g.scan_state, blocks + 1);
     carve(chunk, g.counters, 8);
     carve(chunk, g.grad_scratch, P * 12);
+    for (int k = 0; k < 2; k++) {
+        carve(chunk, g.depth_keys[k], P);
+        carve(chunk, g.depth_ids[k], P);
+    }
+    carve(chunk, g.emit_scan_state, blocks + 1);
+    g.sort_temp_bytes = radix_sort_temp_bytes(P, 4);
+    carve(chunk, g.sort_temp, g.sort_temp_bytes);
     return g;
 }
 size_t geometry_state_bytes(size_t P, int channels) {
@@ -63,9 +70,9 @@ BinningState BinningState::from_chunk(char*& chunk, size_t R) {
     BinningState b;
     carve(chunk, b.point_list, R);
     carve(chunk, b.point_list_unsorted, R);
-    carve(chunk, b.point_list_keys, R);
-    carve(chunk, b.point_list_keys_unsorted, R);
-    b.sort_temp_bytes = radix_sort_temp_bytes(R, 8);
+    carve(chunk, b.tile_keys, R);
+    carve(chunk, b.tile_keys_unsorted, R);
+    b.sort_temp_bytes = radix_sort_temp_bytes(R, 4);
     carve(chunk, b.sort_temp, b.sort_temp_bytes);
     return b;
 }
@@ -179,6 +186,12 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
     if (rc != LG_OK) return rc;
     stage_end(ST_PREPROCESS, stream);
 
+    // The depth ordering of the Gaussians needs nothing from the host, so it is queued before the read-back below and
+    // runs while the host waits for num_rendered.
+    stage_begin(ST_BINNING, stream);
+    rc = launch_depth_order(P, g, f.debug, stream);
+    if (rc != LG_OK) return rc;
+
     // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288)
     if (!g_pinned_word) LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
     LG_CUDA(cudaMemcpyAsync(g_pinned_word, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -192,7 +205,6 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
         return LG_ERR_ALLOC;
     }
     BinningState b = BinningState::from_chunk(bchunk, (size_t)R);
-    stage_begin(ST_BINNING, stream);
     rc = launch_binning(P, R, width, height, g, radii, b, img, f.debug, stream);
     if (rc != LG_OK) return rc;
     stage_end(ST_BINNING, stream);
@@ -353,7 +365,17 @@ int lg_state_read(const char* name, int P, int channels, int width, int height, 
         char* p = const_cast<char*>(binning_state);
         BinningState b = BinningState::from_chunk(p, (size_t)R);
         if (!strcmp(name, "point_list")) { src = b.point_list; bytes = 4 * (size_t)R; }
-        else if (!strcmp(name, "point_list_keys")) { src = b.point_list_keys; bytes = 8 * (size_t)R; }
+        else if (!strcmp(name, "point_list_keys")) {
+            // the 64-bit (tile | depth) keys of the reference are never materialised by the two-level sort; rebuild
+            // them from the sorted tile ids and the depths for inspection
+            if (!geometry_state || dst_bytes < 8 * (size_t)R) {
+                set_error("lg_state_read: 'point_list_keys' needs the geometry state and %zu bytes", 8 * (size_t)R);
+                return LG_ERR_INVALID_ARGUMENT;
+            }
+            char* gp = const_cast<char*>(geometry_state);
+            GeometryState g = GeometryState::from_chunk(gp, (size_t)P, channels);
+            return launch_rebuild_keys(R, g, b, (unsigned long long*)dst, stream);
+        }
     }
     if (!src) {
         set_error("lg_state_read: unknown array '%s' (or its state buffer was not given)", name);

@@ -1,6 +1,17 @@
-// binning.cu — tile binning: (tile | depth) key emission, stable radix sort, tile-range identification.
-// Replaces duplicateWithKeys + cub::DeviceRadixSort::SortPairs + cudaMemset + identifyTileRanges
-// (DGR/cuda_rasterizer/rasterizer_impl.cu:70-138, 292-321).
+// binning.cu — tile binning.  Produces what duplicateWithKeys + cub::DeviceRadixSort::SortPairs + cudaMemset +
+// identifyTileRanges produce in the reference (DGR/cuda_rasterizer/rasterizer_impl.cu:70-138, 292-321): the list of
+// Gaussian ids ordered by (tile, depth bits, Gaussian id) and the [begin, end) range of every tile.
+//
+// The reference sorts R = sum(tiles_touched) 64-bit (tile | depth) keys.  The same total order is reached with far
+// less traffic by a two-level LSD scheme:
+//   1. order the P Gaussians by their 32 depth bits (stable, so equal depths stay in ascending-id order);
+//   2. emit one (tile id, Gaussian id) pair per overlap while walking the Gaussians in that order, so that inside
+//      every tile the pairs already appear in (depth, id) order;
+//   3. stable-sort the R pairs by the tile id alone (ceil(log2 T) = 12..13 bits: two 8-bit passes).
+// Stable LSD sorting by the minor key first and the major key second is exactly a sort by (tile, depth, id) — the
+// order the reference's stable 44..45-bit sort yields (a Gaussian appears at most once per tile, so the order is
+// total and every correct sort reproduces the reference list bit for bit).  P-sized passes replace four of the six
+// R-sized passes and the R-sized passes move 8 bytes per pair instead of 12.
 #include "common.cuh"
 
 namespace lg {
@@ -13,34 +24,98 @@ int higher_msb(uint32_t n) {
     return b < 1 ? 1 : b;
 }
 
-// One (key, value) per Gaussian/tile overlap, row-major over the Gaussian's tile rectangle, at
-// offsets[idx-1] .. offsets[idx]-1 — the order the reference's per-thread double loop produces.  Rectangles of
-// more than EMIT_COOP tiles are written cooperatively by the whole warp (coalesced 8-byte stores) instead of by
-// one thread.
-#define EMIT_COOP 8
-__global__ void __launch_bounds__(256) emit_keys_kernel(int P, const float2* __restrict__ xy,
-                                                        const float* __restrict__ depths,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        const int* __restrict__ radii, unsigned long long* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, int grid_x, int grid_y) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0, off = 0, n = 0, dbits = 0;
-    if (idx < P) {
-        const int r = radii[idx];
-        if (r > 0) {
-            const float2 p = xy[idx];
-            lg_get_rect(p.x, p.y, r, grid_x, grid_y, x0, y0, x1, y1);
-            n = (x1 - x0) * (y1 - y0);
-            off = idx == 0 ? 0u : offsets[idx - 1];
-            dbits = __float_as_uint(depths[idx]);
+#define EMIT_BLOCK 256
+#define EMIT_COOP 8  // rectangles of more tiles than this are written by the whole warp (coalesced stores)
+
+// Walks the Gaussians in depth order.  Thread i takes Gaussian order[i], learns where its pairs start from a fused
+// exclusive scan of tiles_touched in that order (block scan + decoupled look-back over blocks taken in ticket
+// order), and writes one (tile, id) pair per tile of its rectangle, row-major as the reference's double loop
+// (rasterizer_impl.cu:93-108; the order inside one Gaussian is irrelevant to the result, tiles being distinct).
+__global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ tiles_touched,
+                                                                const float2* __restrict__ xy,
+                                                                const int* __restrict__ radii,
+                                                                uint32_t* __restrict__ tile_keys,
+                                                                uint32_t* __restrict__ ids, int grid_x, int grid_y,
+                                                                unsigned long long* scan_state, uint32_t* ticket) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
+    __shared__ uint32_t s_block_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int i = (int)(tile * EMIT_BLOCK + threadIdx.x);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+    uint32_t id = 0, n = 0;
+    if (i < P) {
+        id = order[i];
+        n = tiles_touched[id];
+    }
+    // ---- exclusive scan of n over the depth-ordered Gaussians
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t ws = lane < EMIT_BLOCK / 32 ? s_warp_sums[lane] : 0u;
+        uint32_t wincl = ws;
+#pragma unroll
+        for (int o = 1; o < EMIT_BLOCK / 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
+            if (lane >= (unsigned)o) wincl += t;
         }
+        if (lane < EMIT_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
+        const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, EMIT_BLOCK / 32 - 1);
+        // descriptor = (flag << 32) | value; flag 1 = block aggregate, 2 = inclusive prefix
+        volatile unsigned long long* st = scan_state;
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = (2ull << 32) | block_total;
+        } else {
+            if (lane == 0) st[tile] = (1ull << 32) | block_total;
+            int base = (int)tile - 1;
+            while (true) {
+                const int j = base - (int)lane;
+                unsigned long long d = 2ull << 32;  // virtual predecessor of block 0: inclusive prefix 0
+                if (j >= 0) {
+                    do { d = st[j]; } while ((d >> 32) == 0ull);
+                }
+                const uint32_t flag = (uint32_t)(d >> 32), val = (uint32_t)d;
+                const unsigned done_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                uint32_t contrib = val;
+                if (done_mask) {
+                    const int first = __ffs(done_mask) - 1;  // nearest predecessor holding an inclusive prefix
+                    contrib = lane <= (unsigned)first ? val : 0u;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                exclusive += contrib;
+                if (done_mask) break;
+                base -= 32;
+            }
+            if (lane == 0) st[tile] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
+        }
+        if (lane == 0) s_block_prefix = exclusive;
+    }
+    __syncthreads();
+    uint32_t off = s_block_prefix + s_warp_sums[warp] + incl - n;
+
+    // ---- emission
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (n > 0) {
+        const float2 p = xy[id];
+        lg_get_rect(p.x, p.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
     }
     if (n > 0 && n <= EMIT_COOP) {
         for (uint32_t y = y0; y < y1; y++)
             for (uint32_t x = x0; x < x1; x++) {
-                keys[off] = ((unsigned long long)(y * (uint32_t)grid_x + x) << 32) | dbits;
-                vals[off] = (uint32_t)idx;
+                tile_keys[off] = y * (uint32_t)grid_x + x;
+                ids[off] = id;
                 off++;
             }
     }
@@ -51,25 +126,24 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, const float2* __r
         const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
         const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
         const uint32_t bn = __shfl_sync(0xffffffffu, n, src), boff = __shfl_sync(0xffffffffu, off, src);
-        const uint32_t bd = __shfl_sync(0xffffffffu, dbits, src);
-        const uint32_t bidx = (uint32_t)(idx - (int)lane + src);
-        for (uint32_t i = lane; i < bn; i += 32) {
-            const uint32_t y = by0 + i / bw, x = bx0 + i % bw;
-            keys[boff + i] = ((unsigned long long)(y * (uint32_t)grid_x + x) << 32) | bd;
-            vals[boff + i] = bidx;
+        const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
+        for (uint32_t k = lane; k < bn; k += 32) {
+            const uint32_t y = by0 + k / bw, x = bx0 + k % bw;
+            tile_keys[boff + k] = y * (uint32_t)grid_x + x;
+            ids[boff + k] = bid;
         }
     }
 }
 
-// identifyTileRanges (rasterizer_impl.cu:116-138); tiles with no entries keep (0,0) from the memset.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const unsigned long long* __restrict__ keys,
+// identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted tile ids; tiles with no entries keep (0,0).
+__global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
                                                           uint2* __restrict__ ranges) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    const uint32_t cur = tile_keys[idx];
     if (idx == 0) ranges[cur].x = 0;
     else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        const uint32_t prev = tile_keys[idx - 1];
         if (cur != prev) {
             ranges[prev].y = idx;
             ranges[cur].x = idx;
@@ -78,30 +152,62 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const unsi
     if (idx == L - 1) ranges[cur].y = L;
 }
 
+// inspection only (lg_state_read "point_list_keys"): the reference's sorted 64-bit keys
+__global__ void __launch_bounds__(256) rebuild_keys_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
+                                                           const uint32_t* __restrict__ point_list,
+                                                           const float* __restrict__ depths,
+                                                           unsigned long long* __restrict__ keys) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    keys[idx] = ((unsigned long long)tile_keys[idx] << 32) | __float_as_uint(depths[point_list[idx]]);
+}
+
+// step 1: Gaussian ids in (depth bits, id) order -> g.depth_ids[0] (four 8-bit passes: the result is back in buffer 0)
+int launch_depth_order(int P, GeometryState& g, bool debug, cudaStream_t stream) {
+    bool in_b = false;
+    int rc = radix_sort_pairs_u32(g.depth_keys[0], g.depth_keys[1], g.depth_ids[0], g.depth_ids[1], (size_t)P, 0, 32,
+                                  g.sort_temp, g.sort_temp_bytes, debug, stream, &in_b);
+    if (rc != LG_OK) return rc;
+    if (in_b) {
+        set_error("depth ordering: unexpected pass parity");
+        return LG_ERR_UNSUPPORTED;
+    }
+    return LG_OK;
+}
+
+// steps 2 and 3 + tile ranges
 int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
                    ImageState& img, bool debug, cudaStream_t stream) {
     const int gx = num_tiles_x(W), gy = num_tiles_y(H);
     const int T = gx * gy;
     LG_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, stream));
     if (R <= 0) return LG_OK;
-    const int end_bit = 32 + higher_msb((uint32_t)T);
+    const int end_bit = higher_msb((uint32_t)T);
     const int passes = radix_sort_num_passes(0, end_bit);
-    // ping-pong so that the sorted list ends in point_list_keys / point_list
-    uint64_t* ka = (passes & 1) ? b.point_list_keys_unsorted : b.point_list_keys;
-    uint64_t* kb = (passes & 1) ? b.point_list_keys : b.point_list_keys_unsorted;
+    // ping-pong so that the sorted list ends in tile_keys / point_list
+    uint32_t* ka = (passes & 1) ? b.tile_keys_unsorted : b.tile_keys;
+    uint32_t* kb = (passes & 1) ? b.tile_keys : b.tile_keys_unsorted;
     uint32_t* va = (passes & 1) ? b.point_list_unsorted : b.point_list;
     uint32_t* vb = (passes & 1) ? b.point_list : b.point_list_unsorted;
-    emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.means2D, g.depths, g.point_offsets, radii,
-                                                          reinterpret_cast<unsigned long long*>(ka), va, gx, gy);
+    const int blocks = (P + EMIT_BLOCK - 1) / EMIT_BLOCK;
+    LG_CUDA(cudaMemsetAsync(g.emit_scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
+    emit_pairs_kernel<<<blocks, EMIT_BLOCK, 0, stream>>>(P, g.depth_ids[0], g.tiles_touched, g.means2D, radii, ka, va, gx,
+                                                         gy, g.emit_scan_state, g.counters + 2);
     LG_LAUNCH_CHECK(debug, stream);
     bool in_b = false;
-    int rc = radix_sort_pairs_u64(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
+    int rc = radix_sort_pairs_u32(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
                                   &in_b);
     if (rc != LG_OK) return rc;
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R,
-                                                            reinterpret_cast<unsigned long long*>(b.point_list_keys),
-                                                            img.ranges);
+    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);
     LG_LAUNCH_CHECK(debug, stream);
+    return LG_OK;
+}
+
+int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,
+                        cudaStream_t stream) {
+    if (R <= 0) return LG_OK;
+    rebuild_keys_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, b.point_list, g.depths, keys_out);
+    LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
 

@@ -59,8 +59,14 @@ struct GeometryState {
     uint32_t* tiles_touched;  // P
     uint32_t* point_offsets;  // P (inclusive scan of tiles_touched)
     unsigned long long* scan_state;  // one descriptor per 256-Gaussian block (decoupled look-back)
-    uint32_t* counters;       // [0] ticket, [1] num_rendered, [2..] spare
+    uint32_t* counters;       // [0] preprocess ticket, [1] num_rendered, [2] emit ticket, [3..] spare
     float* grad_scratch;      // backward only: 12 floats / Gaussian packed 2-D gradient record
+    // depth ordering of the Gaussians (binning.cu): ping-pong (depth bits, Gaussian id) pairs + radix-sort scratch
+    uint32_t* depth_keys[2];  // P each
+    uint32_t* depth_ids[2];   // P each
+    unsigned long long* emit_scan_state;  // look-back descriptors of the key-emission scan
+    char* sort_temp;
+    size_t sort_temp_bytes;
     static GeometryState from_chunk(char*& chunk, size_t P, int channels);
 };
 size_t geometry_state_bytes(size_t P, int channels);
@@ -74,10 +80,10 @@ struct ImageState {
 size_t image_state_bytes(size_t W, size_t H);
 
 struct BinningState {
-    uint32_t* point_list;            // R sorted Gaussian ids
+    uint32_t* point_list;            // R Gaussian ids sorted by (tile, depth, id)
     uint32_t* point_list_unsorted;   // R
-    uint64_t* point_list_keys;       // R sorted keys
-    uint64_t* point_list_keys_unsorted;  // R
+    uint32_t* tile_keys;             // R tile ids, sorted
+    uint32_t* tile_keys_unsorted;    // R
     char* sort_temp;                 // radix-sort scratch
     size_t sort_temp_bytes;
     static BinningState from_chunk(char*& chunk, size_t R);
@@ -111,8 +117,11 @@ struct ForwardArgs {
 };
 
 int launch_preprocess(const ForwardArgs& a, GeometryState& g, int* radii, cudaStream_t stream);
+int launch_depth_order(int P, GeometryState& g, bool debug, cudaStream_t stream);
 int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
                    ImageState& img, bool debug, cudaStream_t stream);
+int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,
+                        cudaStream_t stream);
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream);
@@ -256,6 +265,45 @@ __device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, uint
     }
     __syncwarp();
     return cnt;
+}
+
+// A warp's 32 Gaussians own a contiguous block of 32 rows x M3 floats of a (P, M3) array.  Copy `count` floats of that
+// block between global memory and a shared-memory tile whose row stride `row` is odd (bank-conflict-free row walks),
+// with fully coalesced 128-byte global accesses and LG_ROW_BATCH independent loads in flight per lane.  Rows whose bit
+// in `row_mask` is clear are skipped.
+#define LG_ROW_BATCH 12
+__device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ src, float* tile, int M3, int row,
+                                                     int count, unsigned lane, unsigned row_mask) {
+    int g = (int)lane / M3, k = (int)lane % M3;
+    const int dg = 32 / M3, dk = 32 % M3;
+    for (int e0 = (int)lane; e0 < count; e0 += 32 * LG_ROW_BATCH) {
+        float v[LG_ROW_BATCH];
+        int off[LG_ROW_BATCH];
+#pragma unroll
+        for (int u = 0; u < LG_ROW_BATCH; u++) {
+            const int e = e0 + 32 * u;
+            const bool on = e < count && ((row_mask >> g) & 1u);
+            off[u] = on ? g * row + k : -1;
+            v[u] = on ? __ldg(src + e) : 0.0f;
+            g += dg;
+            k += dk;
+            if (k >= M3) { k -= M3; g++; }
+        }
+#pragma unroll
+        for (int u = 0; u < LG_ROW_BATCH; u++)
+            if (off[u] >= 0) tile[off[u]] = v[u];
+    }
+}
+__device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, const float* tile, int M3, int row,
+                                                     int count, unsigned lane) {
+    int g = (int)lane / M3, k = (int)lane % M3;
+    const int dg = 32 / M3, dk = 32 % M3;
+    for (int e = (int)lane; e < count; e += 32) {
+        dst[e] = tile[g * row + k];
+        g += dg;
+        k += dk;
+        if (k >= M3) { k -= M3; g++; }
+    }
 }
 
 // 128-bit read-only streaming load

@@ -70,15 +70,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
     if (STAGED) {
         const long long left = (long long)a.P - (long long)warp_first;
         warp_floats = left <= 0 ? 0 : (int)(left < 32 ? left : 32) * M3;
-        const float* src = a.shs + warp_first * M3;
-        int g = (int)lane / M3, k = (int)lane % M3;
-        const int dg = 32 / M3, dk = 32 % M3;
-        for (int e = (int)lane; e < warp_floats; e += 32) {
-            s_wtile[g * row + k] = __ldg(src + e);
-            g += dg;
-            k += dk;
-            if (k >= M3) { k -= M3; g++; }
-        }
+        lg_warp_rows_to_tile(a.shs + warp_first * M3, s_wtile, M3, row, warp_floats, lane, 0xffffffffu);
     }
     __syncthreads();
     if (idx < a.P) {
@@ -392,15 +384,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
 
     if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
         __syncwarp();
-        float* dst = a.dL_dsh + warp_first * M3;
-        int g = (int)lane / M3, k = (int)lane % M3;
-        const int dg = 32 / M3, dk = 32 % M3;
-        for (int e = (int)lane; e < warp_floats; e += 32) {
-            dst[e] = s_wtile[g * row + k];
-            g += dg;
-            k += dk;
-            if (k >= M3) { k -= M3; g++; }
-        }
+        lg_warp_tile_to_rows(a.dL_dsh + warp_first * M3, s_wtile, M3, row, warp_floats, lane);
     }
 }
 

@@ -42,6 +42,8 @@ struct PreArgs {
     uint8_t* __restrict__ clamped;
     uint32_t* __restrict__ tiles_touched;
     uint32_t* __restrict__ point_offsets;
+    uint32_t* __restrict__ depth_keys;
+    uint32_t* __restrict__ depth_ids;
     unsigned long long* scan_state;
     uint32_t* counters;
 };
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     uint32_t tiles = 0;
     int radius_out = 0;
     bool need_sh = false;
+    float depth_out = 0.0f;
     float px = 0.0f, py = 0.0f, pz = 0.0f;
     if (idx < a.P) {
         px = __ldg(a.means3D + 3 * (size_t)idx + 0);
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                 if (n != 0) {
                     need_sh = a.colors_precomp == nullptr;
                     a.depths[idx] = depth;
+                    depth_out = depth;
                     a.means2D[idx] = make_float2(pix_x, pix_y);
                     const float opacity = __ldg(a.opacities + idx);
                     a.conic_opacity[idx] = make_float4(con_x, con_y, con_z, F_MUL(h_scaling, opacity));
@@ -245,6 +249,9 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         }
         a.radii[idx] = radius_out;
         a.tiles_touched[idx] = tiles;
+        // input of the depth ordering (binning.cu): Gaussians that emit no key sort behind every real depth
+        a.depth_keys[idx] = tiles ? __float_as_uint(depth_out) : 0xffffffffu;
+        a.depth_ids[idx] = (uint32_t)idx;
     }
 
     // ---- SH -> RGB (forward.cu:20-71) for the Gaussians that survived culling; needs only 1e-5 image parity, the
@@ -262,15 +269,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
             const size_t warp_first = (size_t)tile * PRE_BLOCK + (size_t)warp * 32u;
             const long long left = (long long)a.P - (long long)warp_first;
             const int warp_floats = (int)(left < 32 ? left : 32) * M3;
-            const float* src = a.shs + warp_first * M3;
-            int g = (int)lane / M3, k = (int)lane % M3;
-            const int dg = 32 / M3, dk = 32 % M3;
-            for (int e = (int)lane; e < warp_floats; e += 32) {
-                if ((need_mask >> g) & 1u) s_wtile[g * row + k] = __ldg(src + e);
-                g += dg;
-                k += dk;
-                if (k >= M3) { k -= M3; g++; }
-            }
+            lg_warp_rows_to_tile(a.shs + warp_first * M3, s_wtile, M3, row, warp_floats, lane, need_mask);
             __syncwarp();
             sh = s_wtile + lane * row;
         }
@@ -427,7 +426,8 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     a.prefiltered = f.prefiltered; a.antialiasing = f.antialiasing;
     a.radii = radii; a.means2D = g.means2D; a.depths = g.depths; a.cov3Ds = g.cov3D; a.rgb = g.rgb;
     a.conic_opacity = g.conic_opacity; a.clamped = g.clamped; a.tiles_touched = g.tiles_touched;
-    a.point_offsets = g.point_offsets; a.scan_state = g.scan_state; a.counters = g.counters;
+    a.point_offsets = g.point_offsets; a.depth_keys = g.depth_keys[0]; a.depth_ids = g.depth_ids[0];
+    a.scan_state = g.scan_state; a.counters = g.counters;
     const int blocks = (f.P + PRE_BLOCK - 1) / PRE_BLOCK;
     LG_CUDA(cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
     LG_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 8, stream));
