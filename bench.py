@@ -103,6 +103,8 @@ class Stepper:
         gen = torch.Generator(device=device).manual_seed(1234)
         self.dL = torch.randn((3, HEIGHT, WIDTH), device=device, generator=gen)
         self.means2D = torch.zeros((P, 3), device=device, requires_grad=True)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copy_done = torch.cuda.Event()
         if impl == "ours":
             from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
             self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
@@ -142,13 +144,19 @@ class Stepper:
         self.exchange()
 
     def step_e2e(self, host_cam, host_gt, dev_gt):
-        """inputs of the step come from pinned host memory; the loss value goes back to the host"""
+        """inputs of the step come from pinned host memory; the loss value goes back to the host.  The camera (needed
+        first) is copied on the compute stream; the 7.7 MB ground-truth image is copied on a side stream while the
+        rasterizer runs and joined right before the loss (same harness for both implementations)."""
         self.zero_grads()
         cam = dict(host_cam)
         for k in ("viewmatrix", "projmatrix", "campos"):
             cam[k] = host_cam[k].to(self.device, non_blocking=True)
-        dev_gt.copy_(host_gt, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            dev_gt.copy_(host_gt, non_blocking=True)  # the previous step's readers finished: it ended in .item()
+            self.copy_done.record(self.copy_stream)
         color, radii, invd = self.render(cam)
+        main.wait_event(self.copy_done)
         loss = (color - dev_gt).abs().mean()
         loss.backward()
         self.exchange()

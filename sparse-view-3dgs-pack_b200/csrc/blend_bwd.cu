@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
             s_id[tid] = id;
             const float2 m = means2D[id];
             const float4 cq = conic_opacity[id];
-            mask = lg_patch_mask(m.x, m.y, lg_cutoff_radius2(cq), tile_x0, tile_y0);
+            mask = lg_patch_mask(m.x, m.y, cq, tile_x0, tile_y0);
             s_xy[tid] = m;
             s_co[tid] = cq;
 #pragma unroll

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
             const uint32_t id = point_list[range.x + progress];
             const float2 m = means2D[id];
             const float4 co = conic_opacity[id];
-            mask = lg_patch_mask(m.x, m.y, lg_cutoff_radius2(co), tile_x0, tile_y0);
+            mask = lg_patch_mask(m.x, m.y, co, tile_x0, tile_y0);
             s_xy[tid] = m;
             s_co[tid] = co;
 #pragma unroll

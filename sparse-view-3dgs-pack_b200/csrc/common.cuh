@@ -211,42 +211,51 @@ __device__ __forceinline__ void lg_get_rect(float px, float py, int radius, int 
              (uint32_t)max(0, __float2int_rz(F_MUL(F_ADD(F_ADD(F_ADD(py, r), 16.0f), -1.0f), 0.0625f))));
 }
 
-// Conservative per-Gaussian cut-off used by the blend kernels to let a whole warp (an 8x4 pixel patch) skip a list
-// entry: alpha = o * exp(power) >= 1/255 needs power >= -ln(255 o), and power(p) <= -0.5 * lambda_min(Q) * |p - mean|^2
-// (Q = conic).  Returns r2 such that |p - mean|^2 > r2  ==>  alpha < 1/255 with a 1 % margin in alpha — five orders of
-// magnitude above the fp32 rounding of `power`, so the skip can never change a decision the reference takes.
-__device__ __forceinline__ float lg_cutoff_radius2(float4 conic_opacity) {
+// Which 8x4 pixel patches (= warps) of a 16x16 tile can a list entry contribute to at all?
+// alpha = o * exp(power) >= 1/255 needs q := a dx^2 + 2 b dx dy + c dy^2 = -2 power <= 2 ln(255 o).  For every patch
+// the exact minimum of the convex quadratic q over the patch rectangle (pixel centres x0..x0+7, y0..y0+3, taken as
+// a continuous box, so a lower bound of q on the pixels) is compared with that threshold: if the mean lies in the
+// box the minimum is 0, otherwise it sits on the box edge(s) facing the mean, where q is a 1-D parabola whose
+// minimiser is clamped to the edge.  Bit (r*2 + k) of the result is clear only if every pixel of patch (row r,
+// column k) fails the reference's alpha test (forward.cu:358-361), with a margin (1 % in alpha, 0.1 % in q) that is
+// four orders of magnitude above the fp32 rounding of `power`; skipping such an entry for the whole warp therefore
+// never changes a decision the reference takes.  Degenerate inputs (non-positive or NaN a, c; NaN opacity) keep all
+// bits set.
+__device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float4 conic_opacity, float tx0, float ty0) {
     const float a = conic_opacity.x, b = conic_opacity.y, c = conic_opacity.z, o = conic_opacity.w;
-    const float mid = 0.5f * (a + c);
-    const float lam_min = mid - sqrtf(fmaxf(0.25f * (a - c) * (a - c) + b * b, 0.0f));
-    const float k = 0.5f * lam_min * 0.999f;
-    if (!(k > 0.0f) || !(o > 0.0f)) return k > 0.0f ? -1.0f : 3.0e38f;  // o <= 0 never contributes; bad conic: never skip
-    const float L = __logf(255.0f * o) + 0.01f;
-    return L / k;  // negative when o < 1/255: every pixel is skipped
-}
-
-// 8-bit mask over the eight 8x4 pixel patches (= warps) of a 16x16 tile: bit (r*2 + k) is set when the patch whose
-// pixel centres span x in [tx0+8k, tx0+8k+7], y in [ty0+4r, ty0+4r+3] has a pixel within the cut-off radius of the
-// Gaussian mean.  A clear bit means alpha < 1/255 on every pixel of that patch (see lg_cutoff_radius2).
-__device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float r2cut, float tx0, float ty0) {
-    float ex2[2], ey2[4];
+    if (o <= 0.0f) return 0u;                                       // alpha <= 0 on every pixel
+    if (!(a > 0.0f) || !(c > 0.0f) || !(o > 0.0f)) return 0xffu;
+    const float qmax = 2.002f * (__logf(255.0f * o) + 0.01f);       // negative when o < 1/255: nothing survives
+    const float nb_over_c = -b * __fdividef(1.0f, c), nb_over_a = -b * __fdividef(1.0f, a);
+    float xlo[2], xhi[2], ex[2], ax2[2], bx2[2], ty[2];
+    bool in_x[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const float x0 = tx0 + 8.0f * k;
-        const float e = mx - fminf(fmaxf(mx, x0), x0 + 7.0f);
-        ex2[k] = e * e;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const float y0 = ty0 + 4.0f * r;
-        const float e = my - fminf(fmaxf(my, y0), y0 + 3.0f);
-        ey2[r] = e * e;
+        xlo[k] = tx0 + 8.0f * k - mx;
+        xhi[k] = xlo[k] + 7.0f;
+        in_x[k] = xlo[k] <= 0.0f && xhi[k] >= 0.0f;
+        ex[k] = xlo[k] > 0.0f ? xlo[k] : xhi[k];  // offset of the box edge facing the mean
+        ax2[k] = a * ex[k] * ex[k];
+        bx2[k] = 2.0f * b * ex[k];
+        ty[k] = nb_over_c * ex[k];                // unconstrained minimiser of q along that edge
     }
     unsigned m = 0;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < 4; r++) {
+        const float ylo = ty0 + 4.0f * r - my, yhi = ylo + 3.0f;
+        const bool in_y = ylo <= 0.0f && yhi >= 0.0f;
+        const float ey = ylo > 0.0f ? ylo : yhi;
+        const float cy2 = c * ey * ey, by2 = 2.0f * b * ey, tx = nb_over_a * ey;
 #pragma unroll
-        for (int k = 0; k < 2; k++) m |= (ex2[k] + ey2[r] <= r2cut) ? (1u << (r * 2 + k)) : 0u;
+        for (int k = 0; k < 2; k++) {
+            const float dy = fminf(fmaxf(ty[k], ylo), yhi);
+            const float q1 = in_x[k] ? 3.0e38f : fmaf(dy, fmaf(c, dy, bx2[k]), ax2[k]);
+            const float dx = fminf(fmaxf(tx, xlo[k]), xhi[k]);
+            const float q2 = in_y ? 3.0e38f : fmaf(dx, fmaf(a, dx, by2), cy2);
+            const float qmin = (in_x[k] && in_y) ? 0.0f : fminf(q1, q2);
+            m |= (qmin > qmax) ? 0u : (1u << (r * 2 + k));
+        }
+    }
     return m;
 }
 
