@@ -41,6 +41,7 @@ GeometryState GeometryState::from_chunk(char*& chunk, size_t P, int channels) {
         carve(chunk, g.depth_keys[k], P);
         carve(chunk, g.depth_ids[k], P);
     }
+    carve(chunk, g.rect_packed, P);
     carve(chunk, g.emit_scan_state, blocks + 1);
     g.sort_temp_bytes = radix_sort_temp_bytes(P, 4);
     carve(chunk, g.sort_temp, g.sort_temp_bytes);

@@ -33,12 +33,17 @@ int higher_msb(uint32_t n) {
 // (rasterizer_impl.cu:93-108; the order inside one Gaussian is irrelevant to the result, tiles being distinct).
 __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ tiles_touched,
+                                                                const uint32_t* __restrict__ rect_packed,
                                                                 const float2* __restrict__ xy,
                                                                 const int* __restrict__ radii,
                                                                 uint32_t* __restrict__ tile_keys,
                                                                 uint32_t* __restrict__ ids, int grid_x, int grid_y,
-                                                                unsigned long long* scan_state, uint32_t* ticket) {
+                                                                unsigned long long* scan_state, uint32_t* ticket,
+                                                                uint32_t* tile_hist, uint32_t mask0, uint32_t mask1) {
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_hist[2 * 256];  // digit histograms of the tile ids emitted by this block (two 8-bit places)
+    s_hist[threadIdx.x] = 0;
+    s_hist[256 + threadIdx.x] = 0;
     __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
     __shared__ uint32_t s_block_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -48,9 +53,20 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
     uint32_t id = 0, n = 0;
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     if (i < P) {
         id = order[i];
-        n = tiles_touched[id];
+        if (rect_packed) {  // one 4-byte gather gives both the count and the rectangle
+            const uint32_t r = rect_packed[id];
+            x0 = r & 255u; y0 = (r >> 8) & 255u; x1 = (r >> 16) & 255u; y1 = r >> 24;
+            n = (x1 - x0) * (y1 - y0);
+        } else {
+            n = tiles_touched[id];
+            if (n > 0) {
+                const float2 p = xy[id];
+                lg_get_rect(p.x, p.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
+            }
+        }
     }
     // ---- exclusive scan of n over the depth-ordered Gaussians
     uint32_t incl = n;
@@ -106,17 +122,15 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
     uint32_t off = s_block_prefix + s_warp_sums[warp] + incl - n;
 
     // ---- emission
-    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    if (n > 0) {
-        const float2 p = xy[id];
-        lg_get_rect(p.x, p.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
-    }
     if (n > 0 && n <= EMIT_COOP) {
         for (uint32_t y = y0; y < y1; y++)
             for (uint32_t x = x0; x < x1; x++) {
-                tile_keys[off] = y * (uint32_t)grid_x + x;
+                const uint32_t t = y * (uint32_t)grid_x + x;
+                tile_keys[off] = t;
                 ids[off] = id;
                 off++;
+                atomicAdd(&s_hist[t & mask0], 1u);
+                atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
             }
     }
     unsigned big = __ballot_sync(0xffffffffu, n > EMIT_COOP);
@@ -129,9 +143,18 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
         const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
         for (uint32_t k = lane; k < bn; k += 32) {
             const uint32_t y = by0 + k / bw, x = bx0 + k % bw;
-            tile_keys[boff + k] = y * (uint32_t)grid_x + x;
+            const uint32_t t = y * (uint32_t)grid_x + x;
+            tile_keys[boff + k] = t;
             ids[boff + k] = bid;
+            atomicAdd(&s_hist[t & mask0], 1u);
+            atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
         }
+    }
+    __syncthreads();
+    {
+        const uint32_t c0 = s_hist[threadIdx.x], c1 = s_hist[256 + threadIdx.x];
+        if (c0) atomicAdd(tile_hist + threadIdx.x, c0);
+        if (c1) atomicAdd(tile_hist + 256 + threadIdx.x, c1);
     }
 }
 
@@ -165,8 +188,9 @@ __global__ void __launch_bounds__(256) rebuild_keys_kernel(uint32_t L, const uin
 // step 1: Gaussian ids in (depth bits, id) order -> g.depth_ids[0] (four 8-bit passes: the result is back in buffer 0)
 int launch_depth_order(int P, GeometryState& g, bool debug, cudaStream_t stream) {
     bool in_b = false;
-    int rc = radix_sort_pairs_u32(g.depth_keys[0], g.depth_keys[1], g.depth_ids[0], g.depth_ids[1], (size_t)P, 0, 32,
-                                  g.sort_temp, g.sort_temp_bytes, debug, stream, &in_b);
+    // the digit histograms were accumulated by the preprocess kernel
+    int rc = radix_sort_pairs_u32_prehist(g.depth_keys[0], g.depth_keys[1], g.depth_ids[0], g.depth_ids[1], (size_t)P, 0,
+                                          32, g.sort_temp, g.sort_temp_bytes, debug, stream, &in_b);
     if (rc != LG_OK) return rc;
     if (in_b) {
         set_error("depth ordering: unexpected pass parity");
@@ -191,11 +215,23 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
     uint32_t* vb = (passes & 1) ? b.point_list : b.point_list_unsorted;
     const int blocks = (P + EMIT_BLOCK - 1) / EMIT_BLOCK;
     LG_CUDA(cudaMemsetAsync(g.emit_scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
-    emit_pairs_kernel<<<blocks, EMIT_BLOCK, 0, stream>>>(P, g.depth_ids[0], g.tiles_touched, g.means2D, radii, ka, va, gx,
-                                                         gy, g.emit_scan_state, g.counters + 2);
-    LG_LAUNCH_CHECK(debug, stream);
     bool in_b = false;
-    int rc = radix_sort_pairs_u32(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
+    int rc;
+    // the emission kernel accumulates the digit histograms of the tile ids it writes (no separate histogram pass);
+    // beyond 16 tile-id bits (more than 65535 tiles) the generic path recomputes them
+    rc = radix_sort_clear(b.sort_temp, (size_t)R, passes, stream);
+    if (rc != LG_OK) return rc;
+    const uint32_t mask0 = (1u << (end_bit < 8 ? end_bit : 8)) - 1u;
+    const uint32_t mask1 = end_bit > 8 ? (1u << (end_bit - 8 < 8 ? end_bit - 8 : 8)) - 1u : 0u;
+    emit_pairs_kernel<<<blocks, EMIT_BLOCK, 0, stream>>>(
+        P, g.depth_ids[0], g.tiles_touched, (gx <= 255 && gy <= 255) ? g.rect_packed : nullptr, g.means2D, radii, ka, va,
+        gx, gy, g.emit_scan_state, g.counters + 2, radix_sort_hist_ptr(b.sort_temp), mask0, mask1);
+    LG_LAUNCH_CHECK(debug, stream);
+    if (passes <= 2)
+        rc = radix_sort_pairs_u32_prehist(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug,
+                                          stream, &in_b);
+    else
+        rc = radix_sort_pairs_u32(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
                                   &in_b);
     if (rc != LG_OK) return rc;
     tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);

@@ -64,6 +64,7 @@ struct GeometryState {
     // depth ordering of the Gaussians (binning.cu): ping-pong (depth bits, Gaussian id) pairs + radix-sort scratch
     uint32_t* depth_keys[2];  // P each
     uint32_t* depth_ids[2];   // P each
+    uint32_t* rect_packed;    // P: tile rectangle x0 | y0 << 8 | x1 << 16 | y1 << 24 (grids up to 255 x 255 tiles)
     unsigned long long* emit_scan_state;  // look-back descriptors of the key-emission scan
     char* sort_temp;
     size_t sort_temp_bytes;
@@ -174,6 +175,11 @@ int radix_sort_pairs_u64(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, u
 int radix_sort_pairs_u32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
                          int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
                          bool* result_in_b);
+uint32_t* radix_sort_hist_ptr(char* temp);  // [pass * 256 + digit] counters a producer kernel may fill itself ...
+int radix_sort_clear(char* temp, size_t n, int passes, cudaStream_t stream);  // ... after this, and then call:
+int radix_sort_pairs_u32_prehist(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                                 int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug,
+                                 cudaStream_t stream, bool* result_in_b);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
 }  // namespace lg

@@ -44,6 +44,8 @@ struct PreArgs {
     uint32_t* __restrict__ point_offsets;
     uint32_t* __restrict__ depth_keys;
     uint32_t* __restrict__ depth_ids;
+    uint32_t* __restrict__ rect_packed;
+    uint32_t* depth_hist;  // 4 x 256 digit counters of the depth keys (radix-sort scratch), accumulated here
     unsigned long long* scan_state;
     uint32_t* counters;
 };
@@ -126,6 +128,9 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     __shared__ uint32_t s_warp_sums[PRE_BLOCK / 32];
     __shared__ uint32_t s_block_prefix;
     __shared__ float s_cam[35];  // view 0..15, proj 16..31, campos 32..34
+    __shared__ uint32_t s_hist[4 * 256];
+#pragma unroll
+    for (int k = 0; k < 4; k++) s_hist[k * 256 + threadIdx.x] = 0;
 
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.counters[0], 1u);  // dynamic tile id: look-back never waits on an unscheduled block
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.viewmatrix + threadIdx.x);
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     int radius_out = 0;
     bool need_sh = false;
     float depth_out = 0.0f;
+    uint32_t rect_out = 0;
     float px = 0.0f, py = 0.0f, pz = 0.0f;
     if (idx < a.P) {
         px = __ldg(a.means3D + 3 * (size_t)idx + 0);
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                     need_sh = a.colors_precomp == nullptr;
                     a.depths[idx] = depth;
                     depth_out = depth;
+                    rect_out = x0 | (y0 << 8) | (x1 << 16) | (y1 << 24);
                     a.means2D[idx] = make_float2(pix_x, pix_y);
                     const float opacity = __ldg(a.opacities + idx);
                     a.conic_opacity[idx] = make_float4(con_x, con_y, con_z, F_MUL(h_scaling, opacity));
@@ -250,8 +257,12 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         a.radii[idx] = radius_out;
         a.tiles_touched[idx] = tiles;
         // input of the depth ordering (binning.cu): Gaussians that emit no key sort behind every real depth
-        a.depth_keys[idx] = tiles ? __float_as_uint(depth_out) : 0xffffffffu;
+        const uint32_t dkey = tiles ? __float_as_uint(depth_out) : 0xffffffffu;
+        a.depth_keys[idx] = dkey;
         a.depth_ids[idx] = (uint32_t)idx;
+        a.rect_packed[idx] = rect_out;
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(&s_hist[k * 256 + ((dkey >> (8 * k)) & 255u)], 1u);
     }
 
     // ---- SH -> RGB (forward.cu:20-71) for the Gaussians that survived culling; needs only 1e-5 image parity, the
@@ -400,6 +411,11 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     }
     __syncthreads();
     if (idx < a.P) a.point_offsets[idx] = s_block_prefix + s_warp_sums[warp] + incl;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t c = s_hist[k * 256 + threadIdx.x];
+        if (c) atomicAdd(a.depth_hist + k * 256 + threadIdx.x, c);
+    }
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -427,10 +443,15 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     a.radii = radii; a.means2D = g.means2D; a.depths = g.depths; a.cov3Ds = g.cov3D; a.rgb = g.rgb;
     a.conic_opacity = g.conic_opacity; a.clamped = g.clamped; a.tiles_touched = g.tiles_touched;
     a.point_offsets = g.point_offsets; a.depth_keys = g.depth_keys[0]; a.depth_ids = g.depth_ids[0];
+    a.rect_packed = g.rect_packed; a.depth_hist = radix_sort_hist_ptr(g.sort_temp);
     a.scan_state = g.scan_state; a.counters = g.counters;
     const int blocks = (f.P + PRE_BLOCK - 1) / PRE_BLOCK;
     LG_CUDA(cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
     LG_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 8, stream));
+    {   // the kernel also accumulates the digit histograms of the depth keys for the depth ordering that follows
+        int rc = radix_sort_clear(g.sort_temp, (size_t)f.P, 4, stream);
+        if (rc != LG_OK) return rc;
+    }
     const int M3 = 3 * f.M;
     if (f.colors_precomp == nullptr && M3 <= PRE_MAX_ROW) {
         const size_t smem = sizeof(float) * PRE_BLOCK * (size_t)(M3 | 1);

@@ -14,6 +14,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = 16;       // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LB_WIN = 8;     // look-back descriptors fetched per round trip
 
 constexpr uint32_t LB_PARTIAL = 1u << 30;
 constexpr uint32_t LB_INCLUSIVE = 2u << 30;
@@ -161,14 +162,34 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
     const uint32_t excl_in_tile = wbase + incl - tile_count;
     s.tile_excl[tid] = excl_in_tile;
 
-    // decoupled look-back for digit `tid`
+    // decoupled look-back for digit `tid`, RS_LB_WIN predecessors per round trip: the descriptor loads of a window
+    // are independent, so the chain costs one memory latency per window instead of one per predecessor
     uint32_t prev = 0;
     if (tile > 0) {
-        for (int j = (int)tile - 1; j >= 0; j--) {
-            uint32_t v;
-            do { v = lookback[(size_t)j * RS_RADIX + tid]; } while ((v & LB_FLAGS) == 0u);
-            prev += v & LB_VALUE;
-            if (v & LB_INCLUSIVE) break;
+        int j = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t v[RS_LB_WIN];
+#pragma unroll
+            for (int w = 0; w < RS_LB_WIN; w++) {
+                const int jj = j - w;
+                v[w] = LB_INCLUSIVE + 0u;
+                if (jj >= 0) v[w] = lookback[(size_t)jj * RS_RADIX + tid];
+            }
+            int consumed = 0;
+            bool stalled = false;
+#pragma unroll
+            for (int w = 0; w < RS_LB_WIN; w++) {
+                if (!done && !stalled) {
+                    if ((v[w] & LB_FLAGS) == 0u) stalled = true;  // not published yet: poll again from here
+                    else {
+                        prev += v[w] & LB_VALUE;
+                        consumed++;
+                        if (v[w] & LB_INCLUSIVE) done = true;
+                    }
+                }
+            }
+            j -= consumed;
         }
         lookback[(size_t)tile * RS_RADIX + tid] = ((prev + tile_count) & LB_VALUE) | LB_INCLUSIVE;
     }
@@ -218,13 +239,36 @@ size_t radix_sort_temp_bytes(size_t n, int key_bytes) {
 
 int radix_sort_num_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + RS_BITS - 1) / RS_BITS; }
 
+// The digit histograms live at the start of the scratch buffer: counter [pass * 256 + digit].  A producer kernel may
+// fill them itself (after radix_sort_clear) and then call the *_prehist entry point, which skips the histogram pass.
+uint32_t* radix_sort_hist_ptr(char* temp) {
+    char* p = temp;
+    uint32_t* hist;
+    carve(p, hist, RS_MAX_PASSES * RS_RADIX);
+    return hist;
+}
+
+int radix_sort_clear(char* temp, size_t n, int passes, cudaStream_t stream) {
+    const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    char* p = temp;
+    uint32_t* hist;
+    uint32_t* tickets;
+    uint32_t* lookback;
+    carve(p, hist, RS_MAX_PASSES * RS_RADIX);
+    carve(p, tickets, 32);
+    carve(p, lookback, RS_MAX_PASSES * tiles * RS_RADIX);
+    const size_t zero_bytes = (size_t)((char*)(lookback + (size_t)passes * tiles * RS_RADIX) - (char*)hist);
+    LG_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, stream));
+    return LG_OK;
+}
+
 // Sorts n pairs on key bits [begin_bit, end_bit).  Input in (keys_a, vals_a); buffers are ping-ponged and BOTH are
 // clobbered.  The sorted result lands in (keys_b, vals_b) when the pass count is odd, else in (keys_a, vals_a);
 // *result_in_b tells which.
 template <typename K>
 static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n, int begin_bit,
                                  int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
-                                 bool* result_in_b) {
+                                 bool* result_in_b, bool have_hist) {
     const int passes = radix_sort_num_passes(begin_bit, end_bit);
     *result_in_b = (passes & 1) != 0;
     if (n == 0 || passes == 0) {
@@ -251,12 +295,13 @@ static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_
     carve(p, hist, RS_MAX_PASSES * RS_RADIX);
     carve(p, tickets, 32);
     carve(p, lookback, RS_MAX_PASSES * tiles * RS_RADIX);
-    const size_t zero_bytes = (size_t)((char*)(lookback + (size_t)passes * tiles * RS_RADIX) - (char*)hist);
-    LG_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, stream));
-
-    const int hist_blocks = (int)min((size_t)LG_NUM_SMS * 8, (n + 255) / 256);
-    rs_histogram_kernel<K><<<hist_blocks, 256, 0, stream>>>(keys_a, (uint32_t)n, begin_bit, end_bit, passes, hist);
-    LG_LAUNCH_CHECK(debug, stream);
+    if (!have_hist) {
+        int rc = radix_sort_clear(temp, n, passes, stream);
+        if (rc != LG_OK) return rc;
+        const int hist_blocks = (int)min((size_t)LG_NUM_SMS * 8, (n + 255) / 256);
+        rs_histogram_kernel<K><<<hist_blocks, 256, 0, stream>>>(keys_a, (uint32_t)n, begin_bit, end_bit, passes, hist);
+        LG_LAUNCH_CHECK(debug, stream);
+    }
     rs_scan_hist_kernel<<<passes, RS_RADIX, 0, stream>>>(hist);
     LG_LAUNCH_CHECK(debug, stream);
 
@@ -288,14 +333,22 @@ int radix_sort_pairs_u64(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, u
                          bool* result_in_b) {
     return radix_sort_pairs_impl<unsigned long long>(reinterpret_cast<unsigned long long*>(keys_a),
                                                      reinterpret_cast<unsigned long long*>(keys_b), vals_a, vals_b, n,
-                                                     begin_bit, end_bit, temp, temp_bytes, debug, stream, result_in_b);
+                                                     begin_bit, end_bit, temp, temp_bytes, debug, stream, result_in_b,
+                                                     false);
 }
 
 int radix_sort_pairs_u32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
                          int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug, cudaStream_t stream,
                          bool* result_in_b) {
     return radix_sort_pairs_impl<uint32_t>(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
-                                           debug, stream, result_in_b);
+                                           debug, stream, result_in_b, false);
+}
+
+int radix_sort_pairs_u32_prehist(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
+                                 int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug,
+                                 cudaStream_t stream, bool* result_in_b) {
+    return radix_sort_pairs_impl<uint32_t>(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                           debug, stream, result_in_b, true);
 }
 
 }  // namespace lg
