@@ -13,14 +13,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
-LIBNAME = "liblgdwt_b200.so"
+LIBNAME = os.environ.get("LGDWT_LIBNAME", "liblgdwt_b200.so")  # tuning variants: another name + LGDWT_EXTRA_FLAGS
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
-]
+] + os.environ.get("LGDWT_EXTRA_FLAGS", "").split()
+if LIBNAME != "liblgdwt_b200.so":
+    OBJDIR = os.path.join(HERE, "build", LIBNAME)
 
 
 def _sources():

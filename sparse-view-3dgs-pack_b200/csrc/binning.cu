@@ -25,12 +25,16 @@ int higher_msb(uint32_t n) {
 }
 
 #define EMIT_BLOCK 256
+#define EMIT_IPT 4   // Gaussians per thread
+#define EMIT_TILE (EMIT_BLOCK * EMIT_IPT)
 #define EMIT_COOP 8  // rectangles of more tiles than this are written by the whole warp (coalesced stores)
 
-// Walks the Gaussians in depth order.  Thread i takes Gaussian order[i], learns where its pairs start from a fused
-// exclusive scan of tiles_touched in that order (block scan + decoupled look-back over blocks taken in ticket
-// order), and writes one (tile, id) pair per tile of its rectangle, row-major as the reference's double loop
-// (rasterizer_impl.cu:93-108; the order inside one Gaussian is irrelevant to the result, tiles being distinct).
+// Walks the Gaussians in depth order.  A thread takes EMIT_IPT consecutive entries of `order`, learns where their
+// pairs start from a fused exclusive scan of the tile counts in that order (block scan + decoupled look-back over
+// blocks taken in ticket order), and writes one (tile, id) pair per tile of each rectangle, row-major as the
+// reference's double loop (rasterizer_impl.cu:93-108; the order inside one Gaussian is irrelevant to the result,
+// its tiles being distinct).  The block also accumulates the digit histograms of the tile ids it writes, which the
+// tile-id sort that follows would otherwise need a pass of its own for.
 __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ tiles_touched,
                                                                 const uint32_t* __restrict__ rect_packed,
@@ -41,35 +45,41 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
                                                                 unsigned long long* scan_state, uint32_t* ticket,
                                                                 uint32_t* tile_hist, uint32_t mask0, uint32_t mask1) {
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
+    __shared__ uint32_t s_block_prefix;
     __shared__ uint32_t s_hist[2 * 256];  // digit histograms of the tile ids emitted by this block (two 8-bit places)
     s_hist[threadIdx.x] = 0;
     s_hist[256 + threadIdx.x] = 0;
-    __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
-    __shared__ uint32_t s_block_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int i = (int)(tile * EMIT_BLOCK + threadIdx.x);
+    const int i0 = (int)(tile * EMIT_TILE + threadIdx.x * EMIT_IPT);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
-    uint32_t id = 0, n = 0;
-    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    if (i < P) {
-        id = order[i];
-        if (rect_packed) {  // one 4-byte gather gives both the count and the rectangle
-            const uint32_t r = rect_packed[id];
-            x0 = r & 255u; y0 = (r >> 8) & 255u; x1 = (r >> 16) & 255u; y1 = r >> 24;
-            n = (x1 - x0) * (y1 - y0);
-        } else {
-            n = tiles_touched[id];
-            if (n > 0) {
-                const float2 p = xy[id];
-                lg_get_rect(p.x, p.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
+    uint32_t id[EMIT_IPT], n[EMIT_IPT], x0[EMIT_IPT], y0[EMIT_IPT], x1[EMIT_IPT], y1[EMIT_IPT];
+#pragma unroll
+    for (int u = 0; u < EMIT_IPT; u++) id[u] = (i0 + u < P) ? order[i0 + u] : 0u;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < EMIT_IPT; u++) {
+        n[u] = 0; x0[u] = y0[u] = x1[u] = y1[u] = 0;
+        if (i0 + u < P) {
+            if (rect_packed) {  // one 4-byte gather gives both the count and the rectangle
+                const uint32_t r = rect_packed[id[u]];
+                x0[u] = r & 255u; y0[u] = (r >> 8) & 255u; x1[u] = (r >> 16) & 255u; y1[u] = r >> 24;
+                n[u] = (x1[u] - x0[u]) * (y1[u] - y0[u]);
+            } else {
+                n[u] = tiles_touched[id[u]];
+                if (n[u] > 0) {
+                    const float2 p = xy[id[u]];
+                    lg_get_rect(p.x, p.y, radii[id[u]], grid_x, grid_y, x0[u], y0[u], x1[u], y1[u]);
+                }
             }
         }
+        mine += n[u];
     }
-    // ---- exclusive scan of n over the depth-ordered Gaussians
-    uint32_t incl = n;
+    // ---- exclusive scan of the tile counts over the depth-ordered Gaussians
+    uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -87,68 +97,45 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
         }
         if (lane < EMIT_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
         const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, EMIT_BLOCK / 32 - 1);
-        // descriptor = (flag << 32) | value; flag 1 = block aggregate, 2 = inclusive prefix
-        volatile unsigned long long* st = scan_state;
-        uint32_t exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = (2ull << 32) | block_total;
-        } else {
-            if (lane == 0) st[tile] = (1ull << 32) | block_total;
-            int base = (int)tile - 1;
-            while (true) {
-                const int j = base - (int)lane;
-                unsigned long long d = 2ull << 32;  // virtual predecessor of block 0: inclusive prefix 0
-                if (j >= 0) {
-                    do { d = st[j]; } while ((d >> 32) == 0ull);
-                }
-                const uint32_t flag = (uint32_t)(d >> 32), val = (uint32_t)d;
-                const unsigned done_mask = __ballot_sync(0xffffffffu, flag == 2u);
-                uint32_t contrib = val;
-                if (done_mask) {
-                    const int first = __ffs(done_mask) - 1;  // nearest predecessor holding an inclusive prefix
-                    contrib = lane <= (unsigned)first ? val : 0u;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                exclusive += contrib;
-                if (done_mask) break;
-                base -= 32;
-            }
-            if (lane == 0) st[tile] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
-        }
+        const uint32_t exclusive = lg_lookback_exclusive(scan_state, tile, block_total, lane);
         if (lane == 0) s_block_prefix = exclusive;
     }
     __syncthreads();
-    uint32_t off = s_block_prefix + s_warp_sums[warp] + incl - n;
+    uint32_t off = s_block_prefix + s_warp_sums[warp] + incl - mine;
 
     // ---- emission
-    if (n > 0 && n <= EMIT_COOP) {
-        for (uint32_t y = y0; y < y1; y++)
-            for (uint32_t x = x0; x < x1; x++) {
+#pragma unroll
+    for (int u = 0; u < EMIT_IPT; u++) {
+        if (n[u] > 0 && n[u] <= EMIT_COOP) {
+            uint32_t o = off;
+            for (uint32_t y = y0[u]; y < y1[u]; y++)
+                for (uint32_t x = x0[u]; x < x1[u]; x++) {
+                    const uint32_t t = y * (uint32_t)grid_x + x;
+                    tile_keys[o] = t;
+                    ids[o] = id[u];
+                    o++;
+                    atomicAdd(&s_hist[t & mask0], 1u);
+                    atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
+                }
+        }
+        unsigned big = __ballot_sync(0xffffffffu, n[u] > EMIT_COOP);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0[u], src), by0 = __shfl_sync(0xffffffffu, y0[u], src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, x1[u], src) - bx0;
+            const uint32_t bn = __shfl_sync(0xffffffffu, n[u], src), boff = __shfl_sync(0xffffffffu, off, src);
+            const uint32_t bid = __shfl_sync(0xffffffffu, id[u], src);
+            for (uint32_t k = lane; k < bn; k += 32) {
+                const uint32_t y = by0 + k / bw, x = bx0 + k % bw;
                 const uint32_t t = y * (uint32_t)grid_x + x;
-                tile_keys[off] = t;
-                ids[off] = id;
-                off++;
+                tile_keys[boff + k] = t;
+                ids[boff + k] = bid;
                 atomicAdd(&s_hist[t & mask0], 1u);
                 atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
             }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, n > EMIT_COOP);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-        const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
-        const uint32_t bn = __shfl_sync(0xffffffffu, n, src), boff = __shfl_sync(0xffffffffu, off, src);
-        const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
-        for (uint32_t k = lane; k < bn; k += 32) {
-            const uint32_t y = by0 + k / bw, x = bx0 + k % bw;
-            const uint32_t t = y * (uint32_t)grid_x + x;
-            tile_keys[boff + k] = t;
-            ids[boff + k] = bid;
-            atomicAdd(&s_hist[t & mask0], 1u);
-            atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
         }
+        off += n[u];
     }
     __syncthreads();
     {
@@ -213,7 +200,7 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
     uint32_t* kb = (passes & 1) ? b.tile_keys : b.tile_keys_unsorted;
     uint32_t* va = (passes & 1) ? b.point_list_unsorted : b.point_list;
     uint32_t* vb = (passes & 1) ? b.point_list : b.point_list_unsorted;
-    const int blocks = (P + EMIT_BLOCK - 1) / EMIT_BLOCK;
+    const int blocks = (P + EMIT_TILE - 1) / EMIT_TILE;
     LG_CUDA(cudaMemsetAsync(g.emit_scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
     bool in_b = false;
     int rc;

@@ -321,6 +321,58 @@ __device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, co
     }
 }
 
+// Decoupled look-back of a single-pass prefix sum, executed by one full warp of the block holding ticket `tile`.
+// Descriptor = (flag << 32) | value; flag 0 = not published, 1 = the block's own total, 2 = inclusive prefix.
+// Publishes this block's total, adds up the predecessors' descriptors back to the nearest inclusive prefix, publishes
+// the block's inclusive prefix and returns its exclusive prefix to every lane.  Each lane fetches LG_LB_DEPTH
+// descriptors per round trip (32 * LG_LB_DEPTH predecessors per memory latency): when a whole wave of blocks starts
+// together nobody holds an inclusive prefix yet and block t must add ~t totals, so the width of the window, not the
+// arithmetic, sets the length of the chain.  Blocks take their tickets in launch order, so every predecessor is
+// running or finished and will publish (no deadlock).
+#define LG_LB_DEPTH 4
+__device__ __forceinline__ uint32_t lg_lookback_exclusive(volatile unsigned long long* st, uint32_t tile,
+                                                          uint32_t block_total, unsigned lane) {
+    if (tile == 0) {
+        if (lane == 0) st[0] = (2ull << 32) | block_total;
+        return 0u;
+    }
+    if (lane == 0) st[tile] = (1ull << 32) | block_total;
+    uint32_t exclusive = 0;
+    int base = (int)tile - 1;
+    while (true) {
+        unsigned long long d[LG_LB_DEPTH];
+#pragma unroll
+        for (int k = 0; k < LG_LB_DEPTH; k++) {
+            const int j = base - (int)lane - 32 * k;
+            d[k] = 2ull << 32;  // virtual predecessor of block 0: inclusive prefix 0
+            if (j >= 0) d[k] = st[j];
+        }
+        bool finished = false;
+#pragma unroll
+        for (int k = 0; k < LG_LB_DEPTH; k++) {
+            if (!finished) {
+                const int j = base - (int)lane - 32 * k;
+                while ((d[k] >> 32) == 0ull) d[k] = st[j];
+                const uint32_t flag = (uint32_t)(d[k] >> 32), val = (uint32_t)d[k];
+                const unsigned done_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                uint32_t contrib = val;
+                if (done_mask) {
+                    const int first = __ffs(done_mask) - 1;  // nearest predecessor holding an inclusive prefix
+                    contrib = lane <= (unsigned)first ? val : 0u;
+                    finished = true;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                exclusive += contrib;
+            }
+        }
+        if (finished) break;
+        base -= 32 * LG_LB_DEPTH;
+    }
+    if (lane == 0) st[tile] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
+    return exclusive;
+}
+
 // 128-bit read-only streaming load
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 #endif

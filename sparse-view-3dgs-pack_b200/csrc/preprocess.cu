@@ -371,39 +371,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         }
         if (lane < PRE_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
         const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, PRE_BLOCK / 32 - 1);
-        // descriptor = (flag << 32) | value ; flag 1 = block aggregate, 2 = inclusive prefix
-        volatile unsigned long long* st = a.scan_state;
-        uint32_t exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = (2ull << 32) | block_total;
-        } else {
-            if (lane == 0) st[tile] = (1ull << 32) | block_total;
-            int base = (int)tile - 1;
-            while (true) {
-                const int j = base - (int)lane;
-                unsigned long long d = 2ull << 32;  // virtual predecessor of tile 0: inclusive prefix 0
-                if (j >= 0) {
-                    do { d = st[j]; } while ((d >> 32) == 0ull);
-                }
-                const uint32_t flag = (uint32_t)(d >> 32);
-                const uint32_t val = (uint32_t)d;
-                const unsigned done_mask = __ballot_sync(0xffffffffu, flag == 2u);
-                if (done_mask) {
-                    const int first = __ffs(done_mask) - 1;  // nearest predecessor holding an inclusive prefix
-                    uint32_t contrib = lane <= (unsigned)first ? val : 0u;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                    exclusive += contrib;
-                    break;
-                }
-                uint32_t contrib = val;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                exclusive += contrib;
-                base -= 32;
-            }
-            if (lane == 0) st[tile] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
-        }
+        const uint32_t exclusive = lg_lookback_exclusive(a.scan_state, tile, block_total, lane);
         if (lane == 0) {
             s_block_prefix = exclusive;
             if ((size_t)(tile + 1) * PRE_BLOCK >= (size_t)a.P) a.counters[1] = exclusive + block_total;  // num_rendered

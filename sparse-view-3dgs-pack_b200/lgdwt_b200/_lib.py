@@ -9,7 +9,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "liblgdwt_b200.so")
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", os.environ.get("LGDWT_LIBNAME", "liblgdwt_b200.so"))
 
 LG_OK = 0
 LG_ERR_INVALID_ARGUMENT = 1
