@@ -2,9 +2,11 @@
 """bench.py — headline benchmark of the B200-native LGDWT-GS hot path.
 
 Metric (BASELINE.json): rasterize forward+backward per view at 1 M Gaussians, 800x800, SH degree 3, reported as
-whole-job views/s (ms/view = ms_per_step at N = 1); at N > 1 every rank renders its own view of the step (weak
-scaling by camera view) and the per-Gaussian parameter gradients (59 floats = 236 B each) are summed with ONE NCCL
-all-reduce inside the timed step — the path's only exchange step.
+whole-job views/s.  A step is a batch of VIEWS_PER_RANK = 4 views per rank (8 ranks x 4 = the 32-view batch of
+BASELINE config 5; per-rank work is the same at every N: weak scaling by camera view): every view is rendered and
+back-propagated, the parameter gradients (59 floats = 236 B per Gaussian) of the rank's views are accumulated in one
+flat bucket by the backward kernel itself, and at N > 1 the bucket is summed over ranks with ONE NCCL all-reduce
+inside the timed step — the path's only exchange step.  ms/view = ms_per_step / 4 (also printed as ms_per_view).
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
@@ -37,6 +39,7 @@ P_GAUSSIANS = 1_000_000
 WIDTH = HEIGHT = 800
 SH_DEGREE = 3
 N_CAMERAS = 8
+VIEWS_PER_RANK = 4  # views per rank per step (gradient accumulation); x 8 ranks = the 32-view batch of config 5
 FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: not in MEASURED_PEAKS.json
 
 
@@ -99,68 +102,85 @@ class Stepper:
         self.impl, self.p, self.device, self.world = impl, params, device, world
         self.bg = torch.zeros(3, device=device)
         P = params["means3D"].shape[0]
-        self.bucket = torch.zeros(59 * P, device=device) if world > 1 else None
+        self.P = P
         gen = torch.Generator(device=device).manual_seed(1234)
         self.dL = torch.randn((3, HEIGHT, WIDTH), device=device, generator=gen)
         self.means2D = torch.zeros((P, 3), device=device, requires_grad=True)
         self.copy_stream = torch.cuda.Stream(device=device)
-        self.copy_done = torch.cuda.Event()
+        self.copy_done = [torch.cuda.Event() for _ in range(VIEWS_PER_RANK)]
+        self.dev_gt = [torch.empty((3, HEIGHT, WIDTH), device=device) for _ in range(VIEWS_PER_RANK)]
+        # the flat gradient bucket (what a data-parallel step all-reduces): means3D 3 | shs 48 | opacity 1 | scales 3 | rot 4
+        self.bucket = torch.zeros(59 * P, device=device)
+        self.fields = (("means3D", 3), ("shs", 48), ("opacities", 1), ("scales", 3), ("rotations", 4))
+        views, off = {}, 0
+        for k, w in self.fields:
+            views[k] = self.bucket[off * P:(off + w) * P].view(params[k].shape)
+            off += w
+        self.views = views
         if impl == "ours":
-            from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+            from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, GradSinks
             self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
+            self.sinks = GradSinks(views["means3D"], views["shs"], views["opacities"], views["scales"],
+                                   views["rotations"])
         else:
             from oracle import ref_cuda
             self.ref = ref_cuda
 
-    def render(self, cam):
+    def render(self, cam, first):
         p = self.p
         if self.impl == "ours":
             rs = self.RS(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], self.bg, 1.0, cam["viewmatrix"],
                          cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, False)
+            self.sinks.accumulate = not first  # the first view of a step overwrites the bucket: no zero-fill pass
             return self.R(rs)(means3D=p["means3D"], means2D=self.means2D, shs=p["shs"], opacities=p["opacities"],
-                              scales=p["scales"], rotations=p["rotations"])
+                              scales=p["scales"], rotations=p["rotations"], grad_sinks=self.sinks)
         return self.ref.RefRasterize.apply(p["means3D"], self.means2D, p["shs"], p["opacities"], p["scales"],
                                            p["rotations"], cam, self.bg, SH_DEGREE)
 
-    def zero_grads(self):
-        for t in list(self.p.values()) + [self.means2D]:
-            t.grad = None
+    def begin_step(self):
+        self.means2D.grad = None
+        if self.impl != "ours":  # stock path: autograd sums the views into .grad
+            for t in self.p.values():
+                t.grad = None
 
     def exchange(self):
         """the path's only collective: sum the 236 B/Gaussian gradient bucket over ranks"""
         if self.world <= 1:
             return
-        off = 0
-        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
-            g = self.p[k].grad.reshape(-1)
-            self.bucket[off:off + g.numel()].copy_(g)
-            off += g.numel()
+        if self.impl != "ours":
+            for k, _ in self.fields:
+                self.views[k].copy_(self.p[k].grad)
         dist.all_reduce(self.bucket)
 
-    def step_resident(self, cam):
-        self.zero_grads()
-        color, radii, invd = self.render(cam)
-        color.backward(self.dL)
+    def step_resident(self, cams):
+        self.begin_step()
+        for v, cam in enumerate(cams):
+            color, radii, invd = self.render(cam, v == 0)
+            color.backward(self.dL)
         self.exchange()
 
-    def step_e2e(self, host_cam, host_gt, dev_gt):
-        """inputs of the step come from pinned host memory; the loss value goes back to the host.  The camera (needed
-        first) is copied on the compute stream; the 7.7 MB ground-truth image is copied on a side stream while the
-        rasterizer runs and joined right before the loss (same harness for both implementations)."""
-        self.zero_grads()
-        cam = dict(host_cam)
-        for k in ("viewmatrix", "projmatrix", "campos"):
-            cam[k] = host_cam[k].to(self.device, non_blocking=True)
+    def step_e2e(self, host_cams, host_gts):
+        """every view's inputs come from pinned host memory; the step's loss goes back to the host.  The camera
+        (needed first) is copied on the compute stream; the 7.7 MB ground-truth image is copied on a side stream while
+        the rasterizer runs and joined right before the loss (same harness for both implementations)."""
+        self.begin_step()
         main = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self.copy_stream):
-            dev_gt.copy_(host_gt, non_blocking=True)  # the previous step's readers finished: it ended in .item()
-            self.copy_done.record(self.copy_stream)
-        color, radii, invd = self.render(cam)
-        main.wait_event(self.copy_done)
-        loss = (color - dev_gt).abs().mean()
-        loss.backward()
+        total = torch.zeros((), device=self.device)
+        for v, (host_cam, host_gt) in enumerate(zip(host_cams, host_gts)):
+            cam = dict(host_cam)
+            for k in ("viewmatrix", "projmatrix", "campos"):
+                cam[k] = host_cam[k].to(self.device, non_blocking=True)
+            with torch.cuda.stream(self.copy_stream):
+                # readers of this buffer belong to the previous step, which ended in .item()
+                self.dev_gt[v].copy_(host_gt, non_blocking=True)
+                self.copy_done[v].record(self.copy_stream)
+            color, radii, invd = self.render(cam, v == 0)
+            main.wait_event(self.copy_done[v])
+            loss = (color - self.dev_gt[v]).abs().mean()
+            loss.backward()
+            total += loss.detach()
         self.exchange()
-        return float(loss.item())
+        return float(total.item())
 
 
 def timed_loop(fn, steps, world, device):
@@ -234,7 +254,9 @@ def main():
     sc, cams, params = make_workload(device)
     cam_devs = [cam_dict(c, device) for c in cams]
     stepper = Stepper("ours" if impl == "ours" else "ref", params, device, world)
-    pick = lambda i: cam_devs[(i * world + rank) % len(cam_devs)]
+    V = VIEWS_PER_RANK
+    # step i of rank r renders views (i*world + r)*V .. +V-1 of the camera ring
+    pick = lambda i: [cam_devs[((i * world + rank) * V + v) % len(cam_devs)] for v in range(V)]
 
     from lgdwt_b200 import _lib
     # ---- value: inputs resident in HBM
@@ -242,24 +264,24 @@ def main():
         stepper.step_resident(pick(i))
     launches0 = _lib.lib.lg_launch_count()
     if impl == "ours":
-        _lib.stage_timing(min(K, 256))
+        _lib.stage_timing(min(K * V, 256))
     sampler = ClockSampler(local)
     sampler.start()
     ms_total = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device)
     clocks = sampler.stop()
     launches = _lib.lib.lg_launch_count() - launches0
     ms_step = ms_total / K
-    value = world * K / (ms_total / 1e3)
+    value = world * K * V / (ms_total / 1e3)
 
     # ---- per-stage times recorded during that same timed region
     stages, roofline = None, None
     if impl == "ours":
-        rows = [_lib.read_stage_times(s) for s in range(min(K, 256))]
+        rows = [_lib.read_stage_times(s) for s in range(min(K * V, 256))]
         _lib.stage_timing(0)
         mean_ms = {k: float(np.mean([r[k] for r in rows if r[k] >= 0])) for k in _lib.STAGES}
         from diff_gaussian_rasterization import _RasterizeGaussians
         # work terms of the metric camera (step 0's view on rank 0)
-        stepper.step_resident(cam_devs[0])
+        stepper.step_resident([cam_devs[0]])
         lc = _RasterizeGaussians.last_call
         counts = torch.zeros(2, dtype=torch.int64, device=device)
         _lib.check(_lib.lib.lg_blend_work_count(lc["P"], lc["channels"], lc["W"], lc["H"], lc["num_rendered"],
@@ -300,7 +322,7 @@ def main():
                          "frac": round(ach / peak, 4)}
         dom = max(_lib.STAGES, key=lambda k: mean_ms[k])
         roofline = dict(stages[dom])
-        roofline.update({"kernel": dom, "traffic": None, "share_of_step": round(mean_ms[dom] / ms_step, 3),
+        roofline.update({"kernel": dom, "traffic": None, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
                          "peak_source": hbm_src if roofline["bound"] == "hbm" else
                          "nominal FP32 SIMT peak 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak in "
                          "MEASURED_PEAKS.json)",
@@ -314,25 +336,28 @@ def main():
             d[k] = d[k].pin_memory()
         host_cams.append(d)
     rng = np.random.default_rng(7)
-    host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory() for _ in range(2)]
-    dev_gt = torch.empty((3, HEIGHT, WIDTH), device=device)
-    e2e_fn = lambda i: stepper.step_e2e(host_cams[(i * world + rank) % len(host_cams)], host_gts[i % 2], dev_gt)
+    host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory()
+                for _ in range(len(host_cams))]
+    ring = lambda i: [((i * world + rank) * V + v) % len(host_cams) for v in range(V)]
+    e2e_fn = lambda i: stepper.step_e2e([host_cams[j] for j in ring(i)], [host_gts[j] for j in ring(i)])
     for i in range(W):
         e2e_fn(i)
     ms_e2e = timed_loop(e2e_fn, K, world, device)
-    e2e_value = world * K / (ms_e2e / 1e3)
-    h2d = 3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4
+    e2e_value = world * K * V / (ms_e2e / 1e3)
+    h2d = V * (3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4)
     e2e = {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_step": round(ms_e2e / K, 4),
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4}
+           "ms_per_view": round(ms_e2e / K / V, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     line = {
         "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)", "value": round(value, 3),
         "unit": "views/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_step, 4),
+        "ms_per_view": round(ms_step / V, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, one view "
-                               "per rank per step, rasterize forward+backward" +
-                               (" + NCCL all-reduce of the 236 B/Gaussian gradient bucket" if world > 1 else ""),
-                   "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
+        "config": {"workload": "1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, %d views per "
+                               "rank per step (global view batch %d), rasterize forward+backward with the gradients "
+                               "of the rank's views accumulated in one flat bucket" % (V, V * world) +
+                               (" + one NCCL all-reduce of the 236 B/Gaussian bucket per step" if world > 1 else ""),
+                   "views_per_rank_per_step": V, "global_view_batch": V * world, "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                    "cameras": N_CAMERAS, "parallelism": "view-parallel dp%d" % world,
                    "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 43 MB of sort keys per step)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

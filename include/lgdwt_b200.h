@@ -124,6 +124,22 @@ int lg_rasterize_backward(
     int debug,
     void* stream);
 
+/* Same call with gradient accumulation (no counterpart in the reference, which always overwrites freshly zeroed
+ * tensors and leaves the summation over views to autograd): when `accumulate` is non-zero the PARAMETER gradients
+ * dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale and dL_drot are added to the values already in the buffers instead of
+ * overwriting them, so a view batch sums its gradients in one flat bucket (the buffer a data-parallel step
+ * all-reduces) without a separate read-modify-write pass per view.  The screen-space / per-stage outputs
+ * (dL_dmean2D, dL_dconic, dL_dcolor, dL_dinvdepth, dL_dcov3D) are always overwritten. */
+int lg_rasterize_backward_ex(
+    int P, int D, int M, int R, int channels, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+    const int* radii, char* geometry_state, char* binning_state, char* image_state, const float* dL_dpix,
+    const float* dL_dinvdepth_pix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+    int antialiasing, int debug, void* stream, int accumulate);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (DGR/cuda_rasterizer/rasterizer.h:24-29,
  * rasterizer_impl.cu:54-66,141-153; torch glue DGR/rasterize_points.cu:225-244).  present: (P) uint8/bool. */
 int lg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

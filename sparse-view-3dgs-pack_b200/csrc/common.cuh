@@ -151,6 +151,7 @@ struct BackwardArgs {
     float focal_x, focal_y;
     bool antialiasing;
     bool has_invdepth;
+    bool accumulate;  // add to dL_dmean3D / dL_dsh / dL_dopacity / dL_dscale / dL_drot instead of overwriting them
     float* dL_dmean2D;
     float* dL_dconic;
     float* dL_dopacity;
@@ -310,11 +311,11 @@ __device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ s
     }
 }
 __device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, const float* tile, int M3, int row,
-                                                     int count, unsigned lane) {
+                                                     int count, unsigned lane, bool accumulate) {
     int g = (int)lane / M3, k = (int)lane % M3;
     const int dg = 32 / M3, dk = 32 % M3;
     for (int e = (int)lane; e < count; e += 32) {
-        dst[e] = tile[g * row + k];
+        dst[e] = accumulate ? dst[e] + tile[g * row + k] : tile[g * row + k];
         g += dg;
         k += dk;
         if (k >= M3) { k -= M3; g++; }

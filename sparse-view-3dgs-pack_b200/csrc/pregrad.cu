@@ -25,7 +25,7 @@ struct PreGradArgs {
     const float* __restrict__ proj;
     const float* __restrict__ campos;
     float focal_x, focal_y, tan_fovx, tan_fovy;
-    int antialiasing, has_invdepth, sh_path, scale_path;
+    int antialiasing, has_invdepth, sh_path, scale_path, accumulate;
     const float* __restrict__ rec;
     float* __restrict__ dL_dmean2D;
     float* __restrict__ dL_dconic;
@@ -368,12 +368,23 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
             dq[3] = 2 * qr * (dMt[0][1] - dMt[1][0]) + 2 * qx * (dMt[2][0] + dMt[0][2]) + 2 * qy * (dMt[1][2] + dMt[2][1]) -
                     4 * qz * (dMt[1][1] + dMt[0][0]);
         }
+        if (a.accumulate) {
+            const float4 old = reinterpret_cast<const float4*>(a.dL_drot)[i];
+            dq[0] += old.x; dq[1] += old.y; dq[2] += old.z; dq[3] += old.w;
+#pragma unroll
+            for (int k = 0; k < 3; k++) ds[k] += a.dL_dscale[3 * i + k];
+        }
         a.dL_dscale[3 * i + 0] = ds[0];
         a.dL_dscale[3 * i + 1] = ds[1];
         a.dL_dscale[3 * i + 2] = ds[2];
         reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
 
+    if (a.accumulate) {
+        dopacity += a.dL_dopacity[i];
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] += a.dL_dmean3D[3 * i + k];
+    }
     a.dL_dopacity[i] = dopacity;
     a.dL_dmean3D[3 * i + 0] = dmean[0];
     a.dL_dmean3D[3 * i + 1] = dmean[1];
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
 
     if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
         __syncwarp();
-        lg_warp_tile_to_rows(a.dL_dsh + warp_first * M3, s_wtile, M3, row, warp_floats, lane);
+        lg_warp_tile_to_rows(a.dL_dsh + warp_first * M3, s_wtile, M3, row, warp_floats, lane, a.accumulate != 0);
     }
 }
 
@@ -397,7 +408,7 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
     a.cov3Ds = b.cov3D_precomp ? b.cov3D_precomp : g.cov3D;
     a.view = b.viewmatrix; a.proj = b.projmatrix; a.campos = b.campos;
     a.focal_x = b.focal_x; a.focal_y = b.focal_y; a.tan_fovx = b.tan_fovx; a.tan_fovy = b.tan_fovy;
-    a.antialiasing = b.antialiasing; a.has_invdepth = b.has_invdepth;
+    a.antialiasing = b.antialiasing; a.has_invdepth = b.has_invdepth; a.accumulate = b.accumulate ? 1 : 0;
     a.sh_path = (b.shs != nullptr && b.dL_dsh != nullptr && b.M > 0) ? 1 : 0;
     a.scale_path = (b.scales != nullptr && b.rotations != nullptr) ? 1 : 0;
     a.rec = g.grad_scratch;
@@ -411,6 +422,10 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
                                      (int)(sizeof(float) * 256 * (PG_MAX_ROW | 1))));
         preprocess_backward_kernel<true><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
     } else {
+        if (a.sh_path && a.accumulate) {
+            set_error("gradient accumulation needs SH rows of at most %d floats (got %d)", PG_MAX_ROW, M3);
+            return LG_ERR_UNSUPPORTED;
+        }
         preprocess_backward_kernel<false><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
     }
     LG_LAUNCH_CHECK(debug, stream);

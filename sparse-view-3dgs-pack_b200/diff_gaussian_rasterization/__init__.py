@@ -6,7 +6,10 @@ GaussianRasterizer :158-207, _RasterizeGaussians :44-141): same names, argument 
 MS/gaussian_renderer/__init__.py, train.py, train_nir.py and render.py run unchanged.
 
 Extensions (not in the reference): colors_precomp may carry 1..4 channels (RGB+NIR in one pass); kernels run on
-the current torch stream instead of the legacy default stream; gradient buffers are not pre-zeroed by the caller.
+the current torch stream instead of the legacy default stream; gradient buffers are not pre-zeroed by the caller;
+`GaussianRasterizer.forward(..., grad_sinks=GradSinks(...))` makes the backward write (or accumulate) the parameter
+gradients straight into caller-owned tensors — e.g. slices of the flat bucket a data-parallel step all-reduces —
+instead of returning fresh tensors for autograd to add up.
 `SparseGaussianAdam` is intentionally NOT exported: its presence would switch the callers to the `separate_sh`
 calling convention the bundled reference surface does not have.
 """
@@ -18,7 +21,21 @@ import torch.nn as nn
 
 from lgdwt_b200 import _lib
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "GradSinks", "rasterize_gaussians"]
+
+
+class GradSinks:
+    """Caller-owned destinations for the parameter gradients of one rasterizer call (extension, see module docstring).
+
+    means3D (P,3), shs (P,M,3), opacities (P,1), scales (P,3), rotations (P,4): contiguous fp32 CUDA tensors (typically
+    views of one flat bucket).  With accumulate=False the backward overwrites them, with accumulate=True it adds to
+    them.  The autograd gradients of those five inputs are then None (nothing for autograd to add a second time);
+    means2D still receives its gradient the usual way (densification statistics read means2D.grad)."""
+    __slots__ = ("means3D", "shs", "opacities", "scales", "rotations", "accumulate")
+
+    def __init__(self, means3D, shs, opacities, scales, rotations, accumulate=False):
+        self.means3D, self.shs, self.opacities, self.scales, self.rotations = means3D, shs, opacities, scales, rotations
+        self.accumulate = bool(accumulate)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -48,9 +65,9 @@ def _f32c(t):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, grad_sinks=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, grad_sinks)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -58,8 +75,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, grad_sinks=None):
         rs = raster_settings
+        ctx.sinks = grad_sinks
         if means3D.dim() != 2 or means3D.size(1) != 3:
             # same check and exception type as AT_ERROR in DGR/rasterize_points.cu:58-60
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -130,14 +148,28 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_out_depth = _f32c(grad_out_depth)  # None => the inverse-depth branch is skipped entirely
 
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
-        dL_dmeans3D, dL_dmeans2D = new(P, 3), new(P, 3)
-        dL_dcolors, dL_dopacity, dL_dcov3D = new(P, C), new(P, 1), new(P, 6)
-        dL_dsh = new(P, M, 3) if has_sh else None
-        dL_dscales = new(P, 3) if has_scales else None
-        dL_drotations = new(P, 4) if has_scales else None
+        sinks = ctx.sinks
+        if sinks is not None:
+            if not (has_sh and has_scales):
+                raise RuntimeError("grad_sinks needs the SH + scale/rotation input path")
+            for name, shape in (("means3D", (P, 3)), ("shs", (P, M, 3)), ("opacities", (P, 1)), ("scales", (P, 3)),
+                                ("rotations", (P, 4))):
+                t = getattr(sinks, name)
+                if (t is None or t.dtype != torch.float32 or not t.is_contiguous() or t.device != device
+                        or t.numel() != P * shape[-1] * (shape[1] if len(shape) == 3 else 1)):
+                    raise RuntimeError("grad_sinks.%s must be a contiguous fp32 CUDA tensor of shape %s" % (name, shape))
+            dL_dmeans3D, dL_dsh, dL_dopacity = sinks.means3D, sinks.shs, sinks.opacities
+            dL_dscales, dL_drotations = sinks.scales, sinks.rotations
+            dL_dmeans2D, dL_dcolors, dL_dcov3D = new(P, 3), new(P, C), new(P, 6)
+        else:
+            dL_dmeans3D, dL_dmeans2D = new(P, 3), new(P, 3)
+            dL_dcolors, dL_dopacity, dL_dcov3D = new(P, C), new(P, 1), new(P, 6)
+            dL_dsh = new(P, M, 3) if has_sh else None
+            dL_dscales = new(P, 3) if has_scales else None
+            dL_drotations = new(P, 4) if has_scales else None
         if P > 0:
             with torch.cuda.device(device):
-                rc = _lib.lib.lg_rasterize_backward(
+                rc = _lib.lib.lg_rasterize_backward_ex(
                     P, int(rs.sh_degree), M, ctx.num_rendered, C,
                     _lib.ptr(bg_c), W, H,
                     _lib.ptr(means3D_c), _lib.ptr(sh_c), _lib.ptr(colors_c), _lib.ptr(opac_c), _lib.ptr(scales_c),
@@ -149,11 +181,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _lib.ptr(dL_dmeans2D), None, _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors), None,
                     _lib.ptr(dL_dmeans3D), _lib.ptr(dL_dcov3D), _lib.ptr(dL_dsh), _lib.ptr(dL_dscales),
                     _lib.ptr(dL_drotations), int(bool(rs.antialiasing)), int(bool(rs.debug)),
-                    _lib.stream_ptr(device))
+                    _lib.stream_ptr(device), int(sinks is not None and sinks.accumulate))
             _lib.check(rc, RuntimeError)
-        # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        elif sinks is not None and not sinks.accumulate:
+            for t in (dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations):
+                t.zero_()
+        if sinks is not None:  # the gradients live in the caller's tensors; autograd has nothing to add
+            return (None, dL_dmeans2D, None, None, None, None, None, None, None, None)
+        # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, sinks)
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors if has_colors else None, dL_dopacity, dL_dscales,
-                dL_drotations, dL_dcov3D if has_cov else None, None)
+                dL_drotations, dL_dcov3D if has_cov else None, None, None)
 
 
 class GaussianRasterizer(nn.Module):
@@ -177,7 +214,7 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, grad_sinks=None):
         rs = self.raster_settings
         # same validation, exception type and messages as DGR/dgr_3dgs/__init__.py:178-182
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -186,4 +223,4 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, rs)
+                                   cov3D_precomp, rs, grad_sinks)

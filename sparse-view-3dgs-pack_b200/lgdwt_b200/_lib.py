@@ -53,6 +53,8 @@ def _load():
     lib.lg_rasterize_backward.restype = i
     lib.lg_rasterize_backward.argtypes = (
         [i, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f] + [_P] * 16 + [i, i, _P])
+    lib.lg_rasterize_backward_ex.restype = i
+    lib.lg_rasterize_backward_ex.argtypes = lib.lg_rasterize_backward.argtypes + [i]
     lib.lg_mark_visible.restype = i
     lib.lg_mark_visible.argtypes = [i, _P, _P, _P, _P, _P]
     lib.lg_state_read.restype = i

@@ -80,6 +80,52 @@ def test_public_operator_autograd_matches_oracle():
         assert rel <= 2e-3, "%s relative error vs oracle %g" % (k, rel)
 
 
+def test_grad_sinks_overwrite_and_accumulate():
+    """GradSinks extension: the backward writes the parameter gradients into caller-owned slices of one flat bucket;
+    accumulate=False overwrites (garbage in the bucket is ignored), accumulate=True adds a second view on top — equal to
+    what autograd's own accumulation of the plain operator gives."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, GradSinks
+    sc, cam, bg, ex = golden_inputs.raster_case("g_sh")
+    names = ("means3D", "shs", "opacities", "scales", "rotations")
+    p = {k: T(getattr(sc, k)).requires_grad_(True) for k in names}
+    P = p["means3D"].shape[0]
+    rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, T(bg), 1.0,
+                                       T(cam.viewmatrix), T(cam.projmatrix), 3, T(cam.campos), False, False, False)
+    dL = [T(ex["dL_dpix"]), T(ex["dL_dpix"][::-1].copy() * 0.5)]
+
+    def run(sinks, d):
+        m2 = torch.zeros((P, 3), device=dev, requires_grad=True)
+        color, _, _ = GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, shs=p["shs"], opacities=p["opacities"],
+                                             scales=p["scales"], rotations=p["rotations"], grad_sinks=sinks)
+        color.backward(d)
+        return m2.grad
+
+    for t in p.values():
+        t.grad = None
+    m2_plain = run(None, dL[0])
+    run(None, dL[1])
+    want = {k: p[k].grad.clone() for k in names}      # autograd summed the two calls
+    for t in p.values():
+        t.grad = None
+
+    bucket = torch.full((59 * P,), float("nan"), device=dev)  # overwrite mode must not read the old contents
+    widths, views, off = (3, 48, 1, 3, 4), {}, 0
+    for k, w in zip(names, widths):
+        views[k] = bucket[off * P:(off + w) * P].view(p[k].shape)
+        off += w
+    sinks = GradSinks(views["means3D"], views["shs"], views["opacities"], views["scales"], views["rotations"])
+    m2_sink = run(sinks, dL[0])
+    assert all(p[k].grad is None for k in names)      # nothing handed to autograd a second time
+    assert torch.isfinite(bucket).all()
+    rel = (m2_sink - m2_plain).abs().max() / m2_plain.abs().max()
+    assert rel <= 1e-4
+    sinks.accumulate = True
+    run(sinks, dL[1])
+    for k in names:
+        rel = float((views[k] - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-12))
+        assert rel <= 1e-4, "%s: accumulated sink differs from autograd accumulation by %g" % (k, rel)
+
+
 def test_four_channel_rgb_nir_render_matches_oracle():
     """N-channel generalisation: one 4-channel pass == the oracle's 4-channel blend (and == two reference-style
     3-channel passes on the shared channels)."""
