@@ -10,7 +10,9 @@
 
 namespace lg {
 
-#define BWD_BATCH 256
+#ifndef BWD_BATCH
+#define BWD_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
+#endif
 #define LG_REC 12  // floats per packed gradient record: mean2D.xy, conic.xyw, opacity, invdepth, colour[C], pad
 
 // Sum N per-lane values over the 32 lanes of a warp.  On return lane L holds in `out` the warp total of value
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     __shared__ float4 s_co[BWD_BATCH];
     __shared__ __align__(16) float s_feat[BWD_BATCH * FS];  // C colours then 1/depth
     __shared__ uint8_t s_mask[BWD_BATCH];                    // per staged entry: which of the 8 patches it can touch
-    __shared__ uint8_t s_list[LG_TILE_PIX / 32][BWD_BATCH];  // per warp: compacted slots it must evaluate
+    __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH];  // per warp: compacted slots it must evaluate
     __shared__ uint32_t s_max;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -114,21 +116,25 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
         __syncthreads();
         // ---- stage one batch, back to front, with the per-patch reach mask of every entry
         const uint32_t batch_base = (uint32_t)i * BWD_BATCH;
-        const uint32_t progress = batch_base + tid;
-        unsigned mask = 0;
-        if (progress < n_eff) {
-            const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
-            s_id[tid] = id;
-            const float2 m = means2D[id];
-            const float4 cq = conic_opacity[id];
-            mask = lg_patch_mask(m.x, m.y, cq, tile_x0, tile_y0);
-            s_xy[tid] = m;
-            s_co[tid] = cq;
 #pragma unroll
-            for (int c = 0; c < C; c++) s_feat[tid * FS + c] = colors[(size_t)id * C + c];
-            if (INVD) s_feat[tid * FS + C] = 1.0f / depths[id];
+        for (int u = 0; u < BWD_BATCH / LG_TILE_PIX; u++) {
+            const unsigned slot = u * LG_TILE_PIX + tid;
+            const uint32_t progress = batch_base + slot;
+            unsigned mask = 0;
+            if (progress < n_eff) {
+                const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
+                s_id[slot] = id;
+                const float2 m = means2D[id];
+                const float4 cq = conic_opacity[id];
+                mask = lg_patch_mask(m.x, m.y, cq, tile_x0, tile_y0);
+                s_xy[slot] = m;
+                s_co[slot] = cq;
+#pragma unroll
+                for (int c = 0; c < C; c++) s_feat[slot * FS + c] = colors[(size_t)id * C + c];
+                if (INVD) s_feat[slot * FS + C] = 1.0f / depths[id];
+            }
+            s_mask[slot] = (uint8_t)mask;
         }
-        s_mask[tid] = (uint8_t)mask;
         __syncthreads();
         const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - batch_base);
         // slots whose list position is behind this warp's last contributor are dropped with the unreachable ones:

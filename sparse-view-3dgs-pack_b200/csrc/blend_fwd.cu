@@ -14,7 +14,9 @@
 
 namespace lg {
 
-#define BLEND_BATCH 256
+#ifndef BLEND_BATCH
+#define BLEND_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
+#endif
 
 template <int C>
 struct FeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
     __shared__ float4 s_co[BLEND_BATCH];
     __shared__ __align__(16) float s_feat[BLEND_BATCH * FS];  // C colours then 1/depth
     __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
-    __shared__ uint8_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
+    __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -56,20 +58,24 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
     for (int i = 0; i < rounds; i++, to_do -= BLEND_BATCH) {
         if (__syncthreads_count(done) == LG_TILE_PIX) break;
         // ---- stage one batch of the tile's depth-sorted list, with the per-patch reach mask of every entry
-        const uint32_t progress = (uint32_t)i * BLEND_BATCH + tid;
-        unsigned mask = 0;
-        if (range.x + progress < range.y) {
-            const uint32_t id = point_list[range.x + progress];
-            const float2 m = means2D[id];
-            const float4 co = conic_opacity[id];
-            mask = lg_patch_mask(m.x, m.y, co, tile_x0, tile_y0);
-            s_xy[tid] = m;
-            s_co[tid] = co;
 #pragma unroll
-            for (int c = 0; c < C; c++) s_feat[tid * FS + c] = features[(size_t)id * C + c];
-            s_feat[tid * FS + C] = F_RCP(depths[id]);
+        for (int u = 0; u < BLEND_BATCH / LG_TILE_PIX; u++) {
+            const unsigned slot = u * LG_TILE_PIX + tid;
+            const uint32_t progress = (uint32_t)i * BLEND_BATCH + slot;
+            unsigned mask = 0;
+            if (range.x + progress < range.y) {
+                const uint32_t id = point_list[range.x + progress];
+                const float2 m = means2D[id];
+                const float4 co = conic_opacity[id];
+                mask = lg_patch_mask(m.x, m.y, co, tile_x0, tile_y0);
+                s_xy[slot] = m;
+                s_co[slot] = co;
+#pragma unroll
+                for (int c = 0; c < C; c++) s_feat[slot * FS + c] = features[(size_t)id * C + c];
+                s_feat[slot * FS + C] = F_RCP(depths[id]);
+            }
+            s_mask[slot] = (uint8_t)mask;
         }
-        s_mask[tid] = (uint8_t)mask;
         __syncthreads();
         const int batch = min(BLEND_BATCH, to_do);
         // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)

@@ -268,7 +268,8 @@ __device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float4 con
 
 // Warp `w` turns the per-entry patch masks of a staged batch into its own compacted, order-preserving list of the
 // entry slots in [lo, hi) that can reach its patch.  Returns the list length.  Only warp w reads list_w afterwards.
-__device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, uint8_t* list_w, unsigned w, unsigned lane,
+typedef uint16_t lg_slot_t;  // index of a staged list entry inside its batch
+__device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, lg_slot_t* list_w, unsigned w, unsigned lane,
                                                      int lo, int hi) {
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
@@ -276,7 +277,7 @@ __device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, uint
         const int slot = base + (int)lane;
         const bool bit = slot >= lo && slot < hi && ((s_mask[slot] >> w) & 1u);
         const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        if (bit) list_w[cnt + __popc(bal & lt)] = (uint8_t)slot;
+        if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)slot;
         cnt += __popc(bal);
     }
     __syncwarp();
