@@ -47,9 +47,6 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, 
     valid = cnt >= 1;
 }
 
-template <int C>
-struct BwdFeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
-
 // Per-Gaussian record accumulated here (LG_REC floats, consumed by preprocess_backward_kernel):
 //   [0] sum w*dx   [1] sum w*dy   [2] sum w*dx^2   [3] sum w*dx*dy   [4] sum w*dy^2   [5] sum w
 //   [6] sum alpha*T*dL/dinvdepth_pix   [7..7+C) sum alpha*T*dL/dpix_c
@@ -57,7 +54,7 @@ struct BwdFeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
 // (backward.cu:598-632) are linear in these moments with per-Gaussian coefficients (conic, opacity), so the
 // coefficients are applied once per Gaussian in the per-Gaussian kernel instead of once per (pixel, Gaussian) hit.
 template <int C, bool INVD>
-__global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
+__global__ void __launch_bounds__(LG_TILE_PIX, 4) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
@@ -65,11 +62,9 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec) {
     constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
     constexpr int VC = 6 + (INVD ? 1 : 0);      // first colour slot among the reduced values
-    constexpr int FS = BwdFeatStride<C>::value;
-    __shared__ uint32_t s_id[BWD_BATCH];
-    __shared__ float2 s_xy[BWD_BATCH];
-    __shared__ float4 s_co[BWD_BATCH];
-    __shared__ __align__(16) float s_feat[BWD_BATCH * FS];  // C colours then 1/depth
+    // one staged entry = three float4: (mean.x, mean.y, Gaussian id, 1/depth) (conic a, b, c, opacity) (colours, C <= 4),
+    // read as warp-wide broadcasts from a single base address
+    __shared__ float4 s_ent[BWD_BATCH * 3];
     __shared__ uint8_t s_mask[BWD_BATCH];                    // per staged entry: which of the 8 patches it can touch
     __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH];  // per warp: compacted slots it must evaluate
     __shared__ uint32_t s_max;
@@ -123,15 +118,15 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
             unsigned mask = 0;
             if (progress < n_eff) {
                 const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
-                s_id[slot] = id;
                 const float2 m = means2D[id];
                 const float4 cq = conic_opacity[id];
                 mask = lg_patch_mask(m.x, m.y, cq, tile_x0, tile_y0);
-                s_xy[slot] = m;
-                s_co[slot] = cq;
+                float fv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int c = 0; c < C; c++) s_feat[slot * FS + c] = colors[(size_t)id * C + c];
-                if (INVD) s_feat[slot * FS + C] = 1.0f / depths[id];
+                for (int c = 0; c < C; c++) fv[c] = colors[(size_t)id * C + c];
+                s_ent[slot * 3 + 0] = make_float4(m.x, m.y, __uint_as_float(id), INVD ? 1.0f / depths[id] : 0.0f);
+                s_ent[slot * 3 + 1] = cq;
+                s_ent[slot * 3 + 2] = make_float4(fv[0], fv[1], fv[2], fv[3]);
             }
             s_mask[slot] = (uint8_t)mask;
         }
@@ -145,8 +140,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
         for (int k = 0; k < cnt; k++) {
             const int j = s_list[warp][k];
             const uint32_t rel = n_eff - 1u - (batch_base + (uint32_t)j);  // 0-based position in the tile's list
-            const float2 xy = s_xy[j];
-            const float4 co = s_co[j];
+            const float4 xy = s_ent[j * 3 + 0];
+            const float4 co = s_ent[j * 3 + 1];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
             const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
@@ -159,11 +154,12 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
 #pragma unroll
             for (int n = 0; n < NV; n++) v[n] = 0.0f;
             if (hit) {
-                const float rinv = __fdividef(1.0f, 1.0f - alpha);  // 1 - alpha in [0.01, 1]
+                float rinv;  // 1 - alpha lies in [0.01, 1]: the bare MUFU.RCP needs no range fix-up
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(1.0f - alpha));
                 T = T * rinv;
                 const float aT = alpha * T;
                 float dL_dalpha = 0.0f;
-                const float4 f4 = *reinterpret_cast<const float4*>(&s_feat[j * FS]);
+                const float4 f4 = s_ent[j * 3 + 2];
                 const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
                 for (int c = 0; c < C; c++) {
@@ -174,7 +170,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
                     v[VC + c] = aT * dL_dpixel[c];
                 }
                 if (INVD) {
-                    const float invd = (FS == 4) ? fv[C < 4 ? C : 3] : s_feat[j * FS + C];
+                    const float invd = xy.w;
                     accum_invd_rec = fmaf(last_alpha, last_invd - accum_invd_rec, accum_invd_rec);
                     last_invd = invd;
                     dL_dalpha = fmaf(invd - accum_invd_rec, dL_invd, dL_dalpha);
@@ -196,7 +192,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_backward_kernel(
             bool ok;
             warp_multi_reduce<NV>(v, lane, total, slot, ok);
             if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
-            if (ok) atomicAdd(grad_rec + (size_t)s_id[j] * LG_REC + slot, total);
+            if (ok) atomicAdd(grad_rec + (size_t)__float_as_uint(xy.z) * LG_REC + slot, total);
         }
     }
 }

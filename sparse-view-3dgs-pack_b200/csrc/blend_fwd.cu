@@ -19,18 +19,14 @@ namespace lg {
 #endif
 
 template <int C>
-struct FeatStride { static constexpr int value = (C + 1 <= 4) ? 4 : 8; };
-
-template <int C>
-__global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
+__global__ void __launch_bounds__(LG_TILE_PIX, 5) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth) {
-    constexpr int FS = FeatStride<C>::value;
-    __shared__ float2 s_xy[BLEND_BATCH];
-    __shared__ float4 s_co[BLEND_BATCH];
-    __shared__ __align__(16) float s_feat[BLEND_BATCH * FS];  // C colours then 1/depth
+    // one staged entry = three float4: (mean.x, mean.y, -, 1/depth) (conic a, b, c, opacity) (colours, C <= 4), read
+    // as warp-wide broadcasts from a single base address
+    __shared__ float4 s_ent[BLEND_BATCH * 3];
     __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
     __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
 
@@ -68,11 +64,12 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
                 const float2 m = means2D[id];
                 const float4 co = conic_opacity[id];
                 mask = lg_patch_mask(m.x, m.y, co, tile_x0, tile_y0);
-                s_xy[slot] = m;
-                s_co[slot] = co;
+                float fv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int c = 0; c < C; c++) s_feat[slot * FS + c] = features[(size_t)id * C + c];
-                s_feat[slot * FS + C] = F_RCP(depths[id]);
+                for (int c = 0; c < C; c++) fv[c] = features[(size_t)id * C + c];
+                s_ent[slot * 3 + 0] = make_float4(m.x, m.y, 0.0f, F_RCP(depths[id]));
+                s_ent[slot * 3 + 1] = co;
+                s_ent[slot * 3 + 2] = make_float4(fv[0], fv[1], fv[2], fv[3]);
             }
             s_mask[slot] = (uint8_t)mask;
         }
@@ -83,8 +80,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
         const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
         for (int k = 0; !done && k < cnt; k++) {
             const int j = s_list[warp][k];
-            const float2 xy = s_xy[j];
-            const float4 co = s_co[j];
+            const float4 xy = s_ent[j * 3 + 0];
+            const float4 co = s_ent[j * 3 + 1];
             const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
             // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
             const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
@@ -97,19 +94,11 @@ __global__ void __launch_bounds__(LG_TILE_PIX) blend_forward_kernel(
                 done = true;
                 continue;
             }
-            if constexpr (FS == 4) {
-                const float4 f = *reinterpret_cast<const float4*>(&s_feat[j * 4]);
-                const float fv[4] = {f.x, f.y, f.z, f.w};
+            const float4 f = s_ent[j * 3 + 2];
+            const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-                for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
-                acc_invd = F_FMA(T, F_MUL(alpha, fv[C]), acc_invd);
-            } else {
-                const float4 f = *reinterpret_cast<const float4*>(&s_feat[j * 8]);
-                const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-                for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
-                acc_invd = F_FMA(T, F_MUL(alpha, s_feat[j * 8 + C]), acc_invd);
-            }
+            for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
+            acc_invd = F_FMA(T, F_MUL(alpha, xy.w), acc_invd);
             T = test_T;
             last_contributor = batch_base + (uint32_t)j + 1u;  // 1-based position in the tile list (forward.cu:345,381)
         }

@@ -20,7 +20,8 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #endif
 constexpr int RS_TILE = RS_THREADS * RS_IPT;
 constexpr int RS_MAX_PASSES = 8;
-constexpr int RS_LB_WIN = 32;    // look-back descriptors fetched per round trip
+constexpr int RS_LB_WIN = 16;     // group descriptors fetched per round trip
+constexpr int RS_GROUP = 32;      // tiles per look-back group    // look-back descriptors fetched per round trip
 
 constexpr uint32_t LB_PARTIAL = 1u << 30;
 constexpr uint32_t LB_INCLUSIVE = 2u << 30;
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
                                                                  uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                                  uint32_t digit_mask,
                                                                  const uint32_t* __restrict__ global_offsets,
-                                                                 volatile uint32_t* lookback, uint32_t* ticket) {
+                                                                 volatile uint32_t* lookback,
+                                                                 volatile uint32_t* group_desc, uint32_t* ticket) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem<K>& s = *reinterpret_cast<RsSmem<K>*>(rs_smem_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -166,8 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
         }
     }
     // publish this tile's digit count as early as possible
-    if (tile == 0) lookback[tid] = tile_count | LB_INCLUSIVE;
-    else lookback[(size_t)tile * RS_RADIX + tid] = tile_count | LB_PARTIAL;
+    lookback[(size_t)tile * RS_RADIX + tid] = tile_count | LB_PARTIAL;
 
     // exclusive scan of tile_count over digits (in-tile bucket starts)
     uint32_t incl = tile_count;
@@ -198,53 +199,73 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
         }
     }
 
-    // decoupled look-back for digit `tid`.  When a whole wave of tiles starts together nobody holds an inclusive
-    // prefix yet and tile t has to add up the aggregates of ~t predecessors, so after a short first probe (the
-    // steady-state case: the nearest predecessors are already inclusive) the descriptors are fetched RS_LB_WIN at a
-    // time — independent loads, one memory latency per window instead of one per predecessor.
+    // Two-level decoupled look-back for digit `tid`.  When a whole wave of W tiles starts together nobody holds an
+    // inclusive prefix yet, and a flat look-back makes tile t add up the totals of ~t predecessors: O(W^2) descriptor
+    // traffic per wave, which is what bounded this pass (measured: time ~ 12 us + 26 ns per tile).  Tiles are
+    // therefore grouped by RS_GROUP consecutive tickets:
+    //   - a tile adds the totals of the (< RS_GROUP) earlier tiles of its own group (one window of independent loads);
+    //   - the last tile of a group publishes the group total, looks back over the earlier GROUP descriptors to the
+    //     nearest inclusive one, and publishes the group's inclusive prefix;
+    //   - every other tile takes the inclusive prefix of the preceding group.
+    // Tickets are taken in launch order, so everything a tile waits for belongs to a running or finished tile.
     uint32_t prev = 0;
-    if (tile > 0) {
-        int j = (int)tile - 1;
-        bool done = false;
-        {   // first probe: 2 predecessors
-            uint32_t v0 = lookback[(size_t)j * RS_RADIX + tid];
-            uint32_t v1 = LB_INCLUSIVE + 0u;
-            if (j >= 1) v1 = lookback[(size_t)(j - 1) * RS_RADIX + tid];
-            if ((v0 & LB_FLAGS) != 0u) {
-                prev += v0 & LB_VALUE;
-                j--;
-                if (v0 & LB_INCLUSIVE) done = true;
-                else if ((v1 & LB_FLAGS) != 0u) {
-                    prev += v1 & LB_VALUE;
-                    j--;
-                    if (v1 & LB_INCLUSIVE) done = true;
+    {
+        const uint32_t grp = tile / RS_GROUP, l = tile % RS_GROUP;
+#pragma unroll
+        for (int w0 = 0; w0 < RS_GROUP - 1; w0 += RS_LB_WIN) {  // windows of RS_LB_WIN independent descriptor loads
+            if ((uint32_t)w0 < l) {
+                uint32_t v[RS_LB_WIN];
+#pragma unroll
+                for (int w = 0; w < RS_LB_WIN; w++) {
+                    v[w] = LB_PARTIAL + 0u;
+                    if ((uint32_t)(w0 + w) < l) v[w] = lookback[(size_t)(tile - 1u - (w0 + w)) * RS_RADIX + tid];
                 }
-            }
-        }
-        while (!done) {
-            uint32_t v[RS_LB_WIN];
 #pragma unroll
-            for (int w = 0; w < RS_LB_WIN; w++) {
-                const int jj = j - w;
-                v[w] = LB_INCLUSIVE + 0u;
-                if (jj >= 0) v[w] = lookback[(size_t)jj * RS_RADIX + tid];
-            }
-            int consumed = 0;
-            bool stalled = false;
-#pragma unroll
-            for (int w = 0; w < RS_LB_WIN; w++) {
-                if (!done && !stalled) {
-                    if ((v[w] & LB_FLAGS) == 0u) stalled = true;  // not published yet: poll again from here
-                    else {
+                for (int w = 0; w < RS_LB_WIN; w++) {
+                    if ((uint32_t)(w0 + w) < l) {
+                        while ((v[w] & LB_FLAGS) == 0u) v[w] = lookback[(size_t)(tile - 1u - (w0 + w)) * RS_RADIX + tid];
                         prev += v[w] & LB_VALUE;
-                        consumed++;
-                        if (v[w] & LB_INCLUSIVE) done = true;
                     }
                 }
             }
-            j -= consumed;
         }
-        lookback[(size_t)tile * RS_RADIX + tid] = ((prev + tile_count) & LB_VALUE) | LB_INCLUSIVE;
+        if (l == RS_GROUP - 1) {  // group closer
+            const uint32_t group_total = prev + tile_count;
+            uint32_t before = 0;
+            if (grp > 0) {
+                group_desc[(size_t)grp * RS_RADIX + tid] = (group_total & LB_VALUE) | LB_PARTIAL;
+                int j = (int)grp - 1;
+                bool done = false;
+                while (!done) {
+                    uint32_t g[RS_LB_WIN];
+#pragma unroll
+                    for (int w = 0; w < RS_LB_WIN; w++) {
+                        g[w] = LB_INCLUSIVE + 0u;
+                        if (j - w >= 0) g[w] = group_desc[(size_t)(j - w) * RS_RADIX + tid];
+                    }
+                    int consumed = 0;
+                    bool stalled = false;
+#pragma unroll
+                    for (int w = 0; w < RS_LB_WIN; w++) {
+                        if (!done && !stalled) {
+                            if ((g[w] & LB_FLAGS) == 0u) stalled = true;  // not published yet: poll again from here
+                            else {
+                                before += g[w] & LB_VALUE;
+                                consumed++;
+                                if (g[w] & LB_INCLUSIVE) done = true;
+                            }
+                        }
+                    }
+                    j -= consumed;
+                }
+            }
+            group_desc[(size_t)grp * RS_RADIX + tid] = ((before + group_total) & LB_VALUE) | LB_INCLUSIVE;
+            prev += before;
+        } else if (grp > 0) {
+            uint32_t g;
+            do { g = group_desc[(size_t)(grp - 1u) * RS_RADIX + tid]; } while ((g & LB_INCLUSIVE) == 0u);
+            prev += g & LB_VALUE;
+        }
     }
     s.digit_off[tid] = global_offsets[tid] + prev - excl_in_tile;
     __syncthreads();
@@ -273,7 +294,8 @@ size_t radix_sort_temp_bytes(size_t n, int key_bytes) {
     size_t b = 0;
     b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * RS_RADIX, 128);          // histograms / global offsets
     b += align_up(sizeof(uint32_t) * 32, 128);                                // tickets (one per pass)
-    b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * tiles * RS_RADIX, 128);  // look-back descriptors
+    b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * tiles * RS_RADIX, 128);  // look-back descriptors (tiles)
+    b += align_up(sizeof(uint32_t) * RS_MAX_PASSES * ((tiles + RS_GROUP - 1) / RS_GROUP) * RS_RADIX, 128);  // (groups)
     return b + 128;
 }
 
@@ -297,8 +319,12 @@ int radix_sort_clear(char* temp, size_t n, int passes, cudaStream_t stream) {
     carve(p, hist, RS_MAX_PASSES * RS_RADIX);
     carve(p, tickets, 32);
     carve(p, lookback, RS_MAX_PASSES * tiles * RS_RADIX);
+    const size_t groups = (tiles + RS_GROUP - 1) / RS_GROUP;
+    uint32_t* group_desc;
+    carve(p, group_desc, RS_MAX_PASSES * groups * RS_RADIX);
     const size_t zero_bytes = (size_t)((char*)(lookback + (size_t)passes * tiles * RS_RADIX) - (char*)hist);
     LG_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, stream));
+    LG_CUDA(cudaMemsetAsync(group_desc, 0, sizeof(uint32_t) * (size_t)passes * groups * RS_RADIX, stream));
     return LG_OK;
 }
 
@@ -335,6 +361,9 @@ static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_
     carve(p, hist, RS_MAX_PASSES * RS_RADIX);
     carve(p, tickets, 32);
     carve(p, lookback, RS_MAX_PASSES * tiles * RS_RADIX);
+    const size_t groups = (tiles + RS_GROUP - 1) / RS_GROUP;
+    uint32_t* group_desc;
+    carve(p, group_desc, RS_MAX_PASSES * groups * RS_RADIX);
     if (!have_hist) {
         int rc = radix_sort_clear(temp, n, passes, stream);
         if (rc != LG_OK) return rc;
@@ -360,7 +389,7 @@ static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_
         const int nb = min(RS_BITS, end_bit - shift);
         rs_onesweep_kernel<K><<<(unsigned)tiles, RS_THREADS, smem, stream>>>(
             src_k, dst_k, src_v, dst_v, (uint32_t)n, shift, (1u << nb) - 1u, hist + pass * RS_RADIX,
-            lookback + (size_t)pass * tiles * RS_RADIX, tickets + pass);
+            lookback + (size_t)pass * tiles * RS_RADIX, group_desc + (size_t)pass * groups * RS_RADIX, tickets + pass);
         LG_LAUNCH_CHECK(debug, stream);
         K* tk = src_k; src_k = dst_k; dst_k = tk;
         uint32_t* tv = src_v; src_v = dst_v; dst_v = tv;

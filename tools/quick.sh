@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU-box quick check: parity tests, then the bench line condensed to step / e2e / stage times.
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -1
 python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
