@@ -370,7 +370,14 @@ int lg_state_read(const char* name, int P, int channels, int width, int height, 
         else if (!strcmp(name, "rgb")) { src = g.rgb; bytes = 4 * (size_t)channels * P; }
         else if (!strcmp(name, "clamped")) { src = g.clamped; bytes = 3 * (size_t)P; }
         else if (!strcmp(name, "tiles_touched")) { src = g.tiles_touched; bytes = 4 * (size_t)P; }
-        else if (!strcmp(name, "point_offsets")) { src = g.point_offsets; bytes = 4 * (size_t)P; }
+        else if (!strcmp(name, "point_offsets")) {
+            // the reference's inclusive scan of tiles_touched is no longer a pipeline product: rebuilt for inspection
+            if (dst_bytes < 4 * (size_t)P) {
+                set_error("lg_state_read: 'point_offsets' needs %zu bytes", 4 * (size_t)P);
+                return LG_ERR_INVALID_ARGUMENT;
+            }
+            return launch_point_offsets(P, g, (uint32_t*)dst, stream);
+        }
         else if (!strcmp(name, "grad_record")) { src = g.grad_scratch; bytes = 48 * (size_t)P; }
     }
     if (!src && image_state) {

@@ -27,6 +27,7 @@ int higher_msb(uint32_t n) {
 #define EMIT_BLOCK 256
 #define EMIT_IPT 4   // Gaussians per thread
 #define EMIT_TILE (EMIT_BLOCK * EMIT_IPT)
+#define EMIT_CAP 5120 // pairs staged in shared memory per round (40 KB)
 #define EMIT_COOP 8  // rectangles of more tiles than this are written by the whole warp (coalesced stores)
 
 // Walks the Gaussians in depth order.  A thread takes EMIT_IPT consecutive entries of `order`, learns where their
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
                                                                 uint32_t* tile_hist, uint32_t mask0, uint32_t mask1) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
-    __shared__ uint32_t s_block_prefix;
+    __shared__ uint32_t s_block_prefix, s_block_total;
+    __shared__ uint32_t s_keys[EMIT_CAP], s_ids[EMIT_CAP];  // the block's pairs at their block-local offsets
     __shared__ uint32_t s_hist[2 * 256];  // digit histograms of the tile ids emitted by this block (two 8-bit places)
     s_hist[threadIdx.x] = 0;
     s_hist[256 + threadIdx.x] = 0;
@@ -56,27 +58,28 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
     const int i0 = (int)(tile * EMIT_TILE + threadIdx.x * EMIT_IPT);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
-    uint32_t id[EMIT_IPT], n[EMIT_IPT], x0[EMIT_IPT], y0[EMIT_IPT], x1[EMIT_IPT], y1[EMIT_IPT];
+    // per item: Gaussian id and its tile rectangle packed as xs = x0 | x1 << 16, ys = y0 | y1 << 16
+    uint32_t id[EMIT_IPT], xs[EMIT_IPT], ys[EMIT_IPT];
 #pragma unroll
     for (int u = 0; u < EMIT_IPT; u++) id[u] = (i0 + u < P) ? order[i0 + u] : 0u;
     uint32_t mine = 0;
 #pragma unroll
     for (int u = 0; u < EMIT_IPT; u++) {
-        n[u] = 0; x0[u] = y0[u] = x1[u] = y1[u] = 0;
+        xs[u] = ys[u] = 0;
         if (i0 + u < P) {
             if (rect_packed) {  // one 4-byte gather gives both the count and the rectangle
                 const uint32_t r = rect_packed[id[u]];
-                x0[u] = r & 255u; y0[u] = (r >> 8) & 255u; x1[u] = (r >> 16) & 255u; y1[u] = r >> 24;
-                n[u] = (x1[u] - x0[u]) * (y1[u] - y0[u]);
-            } else {
-                n[u] = tiles_touched[id[u]];
-                if (n[u] > 0) {
-                    const float2 p = xy[id[u]];
-                    lg_get_rect(p.x, p.y, radii[id[u]], grid_x, grid_y, x0[u], y0[u], x1[u], y1[u]);
-                }
+                xs[u] = (r & 255u) | (((r >> 16) & 255u) << 16);
+                ys[u] = ((r >> 8) & 255u) | ((r >> 24) << 16);
+            } else if (tiles_touched[id[u]] > 0) {
+                const float2 p = xy[id[u]];
+                uint32_t x0, y0, x1, y1;
+                lg_get_rect(p.x, p.y, radii[id[u]], grid_x, grid_y, x0, y0, x1, y1);
+                xs[u] = x0 | (x1 << 16);
+                ys[u] = y0 | (y1 << 16);
             }
         }
-        mine += n[u];
+        mine += ((xs[u] >> 16) - (xs[u] & 0xffffu)) * ((ys[u] >> 16) - (ys[u] & 0xffffu));
     }
     // ---- exclusive scan of the tile counts over the depth-ordered Gaussians
     uint32_t incl = mine;
@@ -98,46 +101,66 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
         if (lane < EMIT_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
         const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, EMIT_BLOCK / 32 - 1);
         const uint32_t exclusive = lg_lookback_exclusive(scan_state, tile, block_total, lane);
-        if (lane == 0) s_block_prefix = exclusive;
+        if (lane == 0) {
+            s_block_prefix = exclusive;
+            s_block_total = block_total;
+        }
     }
     __syncthreads();
-    uint32_t off = s_block_prefix + s_warp_sums[warp] + incl - mine;
-
-    // ---- emission
+    // ---- emission.  Every thread owns a run of consecutive output slots, but runs are short (3.6 pairs per Gaussian
+    // on the benchmark scene), so writing them straight to global memory touches ~11 sectors per store instruction.
+    // The block's pairs are instead laid out in shared memory at their block-local offsets and streamed out with
+    // fully coalesced stores, EMIT_CAP pairs per round (one round for all but the densest blocks).
+    const uint32_t block_base = s_block_prefix;
+    const uint32_t block_total = s_block_total;
+    const uint32_t my_first = s_warp_sums[warp] + incl - mine;  // block-local offset of this thread's first pair
+    for (uint32_t chunk = 0; chunk < block_total; chunk += EMIT_CAP) {
+        uint32_t off = my_first;
 #pragma unroll
-    for (int u = 0; u < EMIT_IPT; u++) {
-        if (n[u] > 0 && n[u] <= EMIT_COOP) {
-            uint32_t o = off;
-            for (uint32_t y = y0[u]; y < y1[u]; y++)
-                for (uint32_t x = x0[u]; x < x1[u]; x++) {
-                    const uint32_t t = y * (uint32_t)grid_x + x;
-                    tile_keys[o] = t;
-                    ids[o] = id[u];
-                    o++;
-                    atomicAdd(&s_hist[t & mask0], 1u);
-                    atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
-                }
-        }
-        unsigned big = __ballot_sync(0xffffffffu, n[u] > EMIT_COOP);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0[u], src), by0 = __shfl_sync(0xffffffffu, y0[u], src);
-            const uint32_t bw = __shfl_sync(0xffffffffu, x1[u], src) - bx0;
-            const uint32_t bn = __shfl_sync(0xffffffffu, n[u], src), boff = __shfl_sync(0xffffffffu, off, src);
-            const uint32_t bid = __shfl_sync(0xffffffffu, id[u], src);
-            for (uint32_t k = lane; k < bn; k += 32) {
-                const uint32_t y = by0 + k / bw, x = bx0 + k % bw;
-                const uint32_t t = y * (uint32_t)grid_x + x;
-                tile_keys[boff + k] = t;
-                ids[boff + k] = bid;
-                atomicAdd(&s_hist[t & mask0], 1u);
-                atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
+        for (int u = 0; u < EMIT_IPT; u++) {
+            const uint32_t x0 = xs[u] & 0xffffu, x1 = xs[u] >> 16, y0 = ys[u] & 0xffffu, y1 = ys[u] >> 16;
+            const uint32_t nu = (x1 - x0) * (y1 - y0);
+            const bool touches = nu > 0 && off < chunk + EMIT_CAP && off + nu > chunk;
+            if (touches && nu <= EMIT_COOP) {
+                uint32_t o = off;
+                for (uint32_t y = y0; y < y1; y++)
+                    for (uint32_t x = x0; x < x1; x++, o++) {
+                        const uint32_t q = o - chunk;  // wraps for o < chunk
+                        if (q < EMIT_CAP) {
+                            s_keys[q] = y * (uint32_t)grid_x + x;
+                            s_ids[q] = id[u];
+                        }
+                    }
             }
+            unsigned big = __ballot_sync(0xffffffffu, touches && nu > EMIT_COOP);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+                const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
+                const uint32_t bn = __shfl_sync(0xffffffffu, nu, src), boff = __shfl_sync(0xffffffffu, off, src);
+                const uint32_t bid = __shfl_sync(0xffffffffu, id[u], src);
+                for (uint32_t k = lane; k < bn; k += 32) {
+                    const uint32_t q = boff + k - chunk;
+                    if (q < EMIT_CAP) {
+                        s_keys[q] = (by0 + k / bw) * (uint32_t)grid_x + bx0 + k % bw;
+                        s_ids[q] = bid;
+                    }
+                }
+            }
+            off += nu;
         }
-        off += n[u];
+        __syncthreads();
+        const uint32_t count = min((uint32_t)EMIT_CAP, block_total - chunk);
+        for (uint32_t q = threadIdx.x; q < count; q += EMIT_BLOCK) {
+            const uint32_t t = s_keys[q];
+            tile_keys[block_base + chunk + q] = t;
+            ids[block_base + chunk + q] = s_ids[q];
+            atomicAdd(&s_hist[t & mask0], 1u);
+            atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     {
         const uint32_t c0 = s_hist[threadIdx.x], c1 = s_hist[256 + threadIdx.x];
         if (c0) atomicAdd(tile_hist + threadIdx.x, c0);

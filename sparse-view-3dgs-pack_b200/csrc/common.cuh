@@ -57,7 +57,7 @@ struct GeometryState {
     float4* conic_opacity;    // P
     float* rgb;               // channels * P
     uint32_t* tiles_touched;  // P
-    uint32_t* point_offsets;  // P (inclusive scan of tiles_touched)
+    uint32_t* point_offsets;  // unused by the pipeline (lg_state_read rebuilds the reference's scan on demand)
     unsigned long long* scan_state;  // one descriptor per 256-Gaussian block (decoupled look-back)
     uint32_t* counters;       // [0] preprocess ticket, [1] num_rendered, [2] emit ticket, [3..] spare
     float* grad_scratch;      // backward only: 12 floats / Gaussian packed 2-D gradient record
@@ -181,6 +181,7 @@ int radix_sort_clear(char* temp, size_t n, int passes, cudaStream_t stream);  //
 int radix_sort_pairs_u32_prehist(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, size_t n,
                                  int begin_bit, int end_bit, char* temp, size_t temp_bytes, bool debug,
                                  cudaStream_t stream, bool* result_in_b);
+int launch_point_offsets(int P, const GeometryState& g, uint32_t* offsets_out, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
 }  // namespace lg
@@ -285,41 +286,53 @@ __device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, lg_s
 }
 
 // A warp's 32 Gaussians own a contiguous block of 32 rows x M3 floats of a (P, M3) array.  Copy `count` floats of that
-// block between global memory and a shared-memory tile whose row stride `row` is odd (bank-conflict-free row walks),
-// with fully coalesced 128-byte global accesses and LG_ROW_BATCH independent loads in flight per lane.  Rows whose bit
-// in `row_mask` is clear are skipped.
+// block between global memory and a shared-memory tile whose row stride is M3 | 1 (odd: bank-conflict-free row
+// walks), with fully coalesced 128-byte global accesses and LG_ROW_BATCH independent loads in flight per lane.
+// Element e of the block lives at tile[e + e / M3] when M3 is even (row = M3 + 1) and at tile[e] when it is odd.
+// M3C is the compile-time row length (48 = SH degree 3, the standard case: the division becomes a multiply) or 0
+// for a run-time M3.
 #define LG_ROW_BATCH 12
-__device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ src, float* tile, int M3, int row,
-                                                     int count, unsigned lane, unsigned row_mask) {
-    int g = (int)lane / M3, k = (int)lane % M3;
-    const int dg = 32 / M3, dk = 32 % M3;
+template <int M3C>
+__device__ __forceinline__ int lg_tile_index(int e, int M3) {
+    if constexpr (M3C > 0) return (M3C & 1) ? e : e + e / M3C;
+    else return (M3 & 1) ? e : e + e / M3;
+}
+template <int M3C>
+__device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ src, float* tile, int M3, int count,
+                                                     unsigned lane) {
     for (int e0 = (int)lane; e0 < count; e0 += 32 * LG_ROW_BATCH) {
         float v[LG_ROW_BATCH];
-        int off[LG_ROW_BATCH];
 #pragma unroll
         for (int u = 0; u < LG_ROW_BATCH; u++) {
             const int e = e0 + 32 * u;
-            const bool on = e < count && ((row_mask >> g) & 1u);
-            off[u] = on ? g * row + k : -1;
-            v[u] = on ? __ldg(src + e) : 0.0f;
-            g += dg;
-            k += dk;
-            if (k >= M3) { k -= M3; g++; }
+            v[u] = e < count ? __ldg(src + e) : 0.0f;
         }
 #pragma unroll
-        for (int u = 0; u < LG_ROW_BATCH; u++)
-            if (off[u] >= 0) tile[off[u]] = v[u];
+        for (int u = 0; u < LG_ROW_BATCH; u++) {
+            const int e = e0 + 32 * u;
+            if (e < count) tile[lg_tile_index<M3C>(e, M3)] = v[u];
+        }
     }
 }
-__device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, const float* tile, int M3, int row,
-                                                     int count, unsigned lane, bool accumulate) {
-    int g = (int)lane / M3, k = (int)lane % M3;
-    const int dg = 32 / M3, dk = 32 % M3;
-    for (int e = (int)lane; e < count; e += 32) {
-        dst[e] = accumulate ? dst[e] + tile[g * row + k] : tile[g * row + k];
-        g += dg;
-        k += dk;
-        if (k >= M3) { k -= M3; g++; }
+template <int M3C>
+__device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, const float* tile, int M3, int count,
+                                                     unsigned lane, bool accumulate) {
+    if (accumulate) {
+        for (int e0 = (int)lane; e0 < count; e0 += 32 * LG_ROW_BATCH) {
+            float v[LG_ROW_BATCH];
+#pragma unroll
+            for (int u = 0; u < LG_ROW_BATCH; u++) {
+                const int e = e0 + 32 * u;
+                v[u] = e < count ? dst[e] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < LG_ROW_BATCH; u++) {
+                const int e = e0 + 32 * u;
+                if (e < count) dst[e] = v[u] + tile[lg_tile_index<M3C>(e, M3)];
+            }
+        }
+    } else {
+        for (int e = (int)lane; e < count; e += 32) dst[e] = tile[lg_tile_index<M3C>(e, M3)];
     }
 }
 

@@ -53,7 +53,7 @@ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 // STAGED = false (3M > PG_MAX_ROW, or no SH path) keeps direct global accesses.
 #define PG_MAX_ROW 48
 
-template <bool STAGED>
+template <bool STAGED, int M3C>
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a) {
     extern __shared__ float s_tile_dyn[];
     __shared__ float s_cam[35];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
     if (STAGED) {
         const long long left = (long long)a.P - (long long)warp_first;
         warp_floats = left <= 0 ? 0 : (int)(left < 32 ? left : 32) * M3;
-        lg_warp_rows_to_tile(a.shs + warp_first * M3, s_wtile, M3, row, warp_floats, lane, 0xffffffffu);
+        lg_warp_rows_to_tile<M3C>(a.shs + warp_first * M3, s_wtile, M3, warp_floats, lane);
     }
     __syncthreads();
     if (idx < a.P) {
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreGradArgs a)
 
     if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
         __syncwarp();
-        lg_warp_tile_to_rows(a.dL_dsh + warp_first * M3, s_wtile, M3, row, warp_floats, lane, a.accumulate != 0);
+        lg_warp_tile_to_rows<M3C>(a.dL_dsh + warp_first * M3, s_wtile, M3, warp_floats, lane, a.accumulate != 0);
     }
 }
 
@@ -418,15 +418,22 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
     const int M3 = 3 * b.M;
     if (a.sh_path && M3 <= PG_MAX_ROW) {
         const size_t smem = sizeof(float) * 256 * (size_t)(M3 | 1);
-        LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(float) * 256 * (PG_MAX_ROW | 1))));
-        preprocess_backward_kernel<true><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+        if (M3 == 48) {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true, 48>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            preprocess_backward_kernel<true, 48><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+        } else {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true, 0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * 256 * (PG_MAX_ROW | 1))));
+            preprocess_backward_kernel<true, 0><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+        }
     } else {
         if (a.sh_path && a.accumulate) {
             set_error("gradient accumulation needs SH rows of at most %d floats (got %d)", PG_MAX_ROW, M3);
             return LG_ERR_UNSUPPORTED;
         }
-        preprocess_backward_kernel<false><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
+        preprocess_backward_kernel<false, 0><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
     }
     LG_LAUNCH_CHECK(debug, stream);
     return LG_OK;

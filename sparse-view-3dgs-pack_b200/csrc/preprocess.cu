@@ -121,23 +121,19 @@ __device__ __forceinline__ void compute_cov3d(float sx0, float sy0, float sz0, f
     cov[5] = dot3_mid_first(M20, M20, M21, M21, M22, M22);   // f445
 }
 
-template <bool STAGED>
+template <bool STAGED, int M3C>
 __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     extern __shared__ float s_tile_dyn[];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp_sums[PRE_BLOCK / 32];
-    __shared__ uint32_t s_block_prefix;
     __shared__ float s_cam[35];  // view 0..15, proj 16..31, campos 32..34
     __shared__ uint32_t s_hist[4 * 256];
 #pragma unroll
     for (int k = 0; k < 4; k++) s_hist[k * 256 + threadIdx.x] = 0;
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.counters[0], 1u);  // dynamic tile id: look-back never waits on an unscheduled block
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.viewmatrix + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(a.projmatrix + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(a.cam_pos + threadIdx.x - 32);
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const int idx = (int)(tile * PRE_BLOCK + threadIdx.x);
     const float* V = s_cam;
     const float* PM = s_cam + 16;
@@ -280,7 +276,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
             const size_t warp_first = (size_t)tile * PRE_BLOCK + (size_t)warp * 32u;
             const long long left = (long long)a.P - (long long)warp_first;
             const int warp_floats = (int)(left < 32 ? left : 32) * M3;
-            lg_warp_rows_to_tile(a.shs + warp_first * M3, s_wtile, M3, row, warp_floats, lane, need_mask);
+            lg_warp_rows_to_tile<M3C>(a.shs + warp_first * M3, s_wtile, M3, warp_floats, lane);
             __syncwarp();
             sh = s_wtile + lane * row;
         }
@@ -351,38 +347,48 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         }
     }
 
-    // ---- fused inclusive scan of tiles_touched: block scan + decoupled look-back across blocks
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t incl = tiles;
+    // ---- num_rendered = sum of tiles_touched (the only scan product the pipeline still needs: the pair offsets are
+    // computed in depth order by the emission kernel, binning.cu); one atomic per warp
+    {
+        uint32_t sum = tiles;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += n;
-    }
-    if (lane == 31) s_warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t ws = lane < PRE_BLOCK / 32 ? s_warp_sums[lane] : 0u;
-        uint32_t wincl = ws;
-#pragma unroll
-        for (int o = 1; o < PRE_BLOCK / 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, wincl, o);
-            if (lane >= (unsigned)o) wincl += n;
-        }
-        if (lane < PRE_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
-        const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, PRE_BLOCK / 32 - 1);
-        const uint32_t exclusive = lg_lookback_exclusive(a.scan_state, tile, block_total, lane);
-        if (lane == 0) {
-            s_block_prefix = exclusive;
-            if ((size_t)(tile + 1) * PRE_BLOCK >= (size_t)a.P) a.counters[1] = exclusive + block_total;  // num_rendered
-        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if ((threadIdx.x & 31u) == 0 && sum) atomicAdd(&a.counters[1], sum);
     }
     __syncthreads();
-    if (idx < a.P) a.point_offsets[idx] = s_block_prefix + s_warp_sums[warp] + incl;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t c = s_hist[k * 256 + threadIdx.x];
         if (c) atomicAdd(a.depth_hist + k * 256 + threadIdx.x, c);
+    }
+}
+
+// inspection only (lg_state_read "point_offsets"): the reference's inclusive scan of tiles_touched
+// (rasterizer_impl.cu:280); one block walks the array with a running prefix
+__global__ void __launch_bounds__(1024) point_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched,
+                                                             uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_running;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int base = 0; base < P; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t v = i < P ? tiles_touched[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_running;
+        for (unsigned w = 0; w < warp; w++) before += s_warp[w];
+        if (i < P) offsets[i] = before + incl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_running = before + incl;
+        __syncthreads();
     }
 }
 
@@ -414,7 +420,6 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     a.rect_packed = g.rect_packed; a.depth_hist = radix_sort_hist_ptr(g.sort_temp);
     a.scan_state = g.scan_state; a.counters = g.counters;
     const int blocks = (f.P + PRE_BLOCK - 1) / PRE_BLOCK;
-    LG_CUDA(cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
     LG_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 8, stream));
     {   // the kernel also accumulates the digit histograms of the depth keys for the depth ordering that follows
         int rc = radix_sort_clear(g.sort_temp, (size_t)f.P, 4, stream);
@@ -423,13 +428,25 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     const int M3 = 3 * f.M;
     if (f.colors_precomp == nullptr && M3 <= PRE_MAX_ROW) {
         const size_t smem = sizeof(float) * PRE_BLOCK * (size_t)(M3 | 1);
-        LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(float) * PRE_BLOCK * (PRE_MAX_ROW | 1))));
-        preprocess_kernel<true><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+        if (M3 == 48) {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+            preprocess_kernel<true, 48><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+        } else {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * PRE_BLOCK * (PRE_MAX_ROW | 1))));
+            preprocess_kernel<true, 0><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+        }
     } else {
-        preprocess_kernel<false><<<blocks, PRE_BLOCK, 0, stream>>>(a);
+        preprocess_kernel<false, 0><<<blocks, PRE_BLOCK, 0, stream>>>(a);
     }
     LG_LAUNCH_CHECK(f.debug, stream);
+    return LG_OK;
+}
+
+int launch_point_offsets(int P, const GeometryState& g, uint32_t* offsets_out, cudaStream_t stream) {
+    point_offsets_kernel<<<1, 1024, 0, stream>>>(P, g.tiles_touched, offsets_out);
+    LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
 
