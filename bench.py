@@ -322,7 +322,15 @@ def main():
                          "frac": round(ach / peak, 4)}
         dom = max(_lib.STAGES, key=lambda k: mean_ms[k])
         roofline = dict(stages[dom])
-        roofline.update({"kernel": dom, "traffic": None, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["kernels"]
+            for name, recs in tr.items():
+                if name.startswith(dom + "_kernel") or name.startswith(dom.replace("blend_", "blend_") + "_kernel"):
+                    traffic = int(recs[0]["dram_read_bytes"] + recs[0]["dram_write_bytes"])
+        except Exception:
+            pass
+        roofline.update({"kernel": dom, "traffic": traffic, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
                          "peak_source": hbm_src if roofline["bound"] == "hbm" else
                          "nominal FP32 SIMT peak 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak in "
                          "MEASURED_PEAKS.json)",
