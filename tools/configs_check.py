@@ -1,0 +1,76 @@
+"""BASELINE configs 3/4/5 at full size: ours vs the reference shim (bit-exact state, image error, fwd/bwd ms).
+Not part of the test-suite; run on a GPU box:  python tools/configs_check.py [cfg3|cfg4|cfg5|all]"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "sparse-view-3dgs-pack_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import helpers  # noqa: E402
+from lgdwt_b200 import scenes  # noqa: E402
+from bringup import timeit  # noqa: E402
+
+
+def cfg(name):
+    if name == "cfg3":   # LLFF-style: 1008x756, ~500k Gaussians, forward-facing slab
+        return scenes.slab_scene(500_000, seed=2), scenes.look_at_camera(1008, 756, 1.05, 2 * math.atan(math.tan(0.525) * 756 / 1008), (0.0, 0.0, 0.0), target=(0.0, 0.0, 5.0))
+    if name == "cfg4":   # RGB+NIR scale: 1296x964, 1M Gaussians
+        return scenes.trained_like_scene(1_000_000, seed=4), scenes.look_at_camera(1296, 964, 0.8, 2 * math.atan(math.tan(0.4) * 964 / 1296), (0.0, 0.0, -4.03))
+    if name == "cfg5":   # Mip-NeRF360 scale: 1920x1080, 6M Gaussians
+        sc = scenes.trained_like_scene(6_000_000, seed=5, sigma_xyz=1.2, clip=3.0, log_scale_mean=math.log(0.006))
+        return sc, scenes.look_at_camera(1920, 1080, 1.0, 2 * math.atan(math.tan(0.5) * 1080 / 1920), (0.0, 0.0, -5.0))
+    raise SystemExit("unknown config " + name)
+
+
+def main():
+    names = sys.argv[1:] or ["all"]
+    if names == ["all"]:
+        names = ["cfg3", "cfg4", "cfg5"]
+    for name in names:
+        sc, cam = cfg(name)
+        t, c = helpers.scene_to_torch(sc), helpers.cam_to_torch(cam)
+        bg = torch.zeros(3, device="cuda")
+        dL = torch.randn((3, cam.image_height, cam.image_width), device="cuda")
+        ours = helpers.run_ours(t, c, cam, bg, want_state=True)
+        print("== %s: P=%d %dx%d num_rendered=%d visible=%d" % (name, sc.means3D.shape[0], cam.image_width,
+                                                               cam.image_height, ours["num_rendered"],
+                                                               int((ours["radii"] > 0).sum())))
+        have_ref = helpers.load_ref() is not None
+        if have_ref:
+            ref = helpers.run_ref(t, c, cam, bg, want_state=True)
+            bad = []
+            for k in ("radii", "tiles_touched", "point_list_keys", "point_list", "ranges", "n_contrib", "final_T"):
+                a, b = ours[k], ref[k]
+                if a.dtype == torch.float32:
+                    a, b = a.view(torch.int32), b.view(torch.int32)
+                if a.shape != b.shape or not bool((a == b).all()):
+                    bad.append(k)
+            print("   bit-exact vs reference:", "ALL EQUAL" if not bad else "DIFFERS: %s" % bad,
+                  "| image max abs err %.3g" % float((ours["color"] - ref["color"]).abs().max()))
+            del ref
+        f_ours = lambda: helpers.run_ours(t, c, cam, bg, want_state=False)
+        fo = f_ours()
+        print("   ours fwd %.3f ms, bwd %.3f ms" % (timeit(f_ours)[0], timeit(lambda: helpers.backward_ours(t, c, cam, bg, fo, dL, None))[0]))
+        if have_ref:
+            f_ref = lambda: helpers.run_ref(t, c, cam, bg, want_state=False)
+            fr = f_ref()
+            g_o = helpers.backward_ours(t, c, cam, bg, fo, dL, None)
+            g_r = helpers.backward_ref(t, c, cam, bg, fr, dL, None)
+            worst = 0.0
+            for k in ("dL_dmean3D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot"):
+                if g_o.get(k) is None or g_r.get(k) is None:
+                    continue
+                a, b = g_o[k].double().reshape(-1), g_r[k].double().reshape(-1)
+                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
+            print("   ref  fwd %.3f ms, bwd %.3f ms | worst gradient rel err %.3g" % (
+                timeit(f_ref)[0], timeit(lambda: helpers.backward_ref(t, c, cam, bg, fr, dL, dL[:1].contiguous()))[0], worst))
+        del ours, fo
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
