@@ -205,6 +205,19 @@ int lg_dwt_loss_backward(const float* pred, const float* gt, int C, int H, int W
                          const uint8_t* patch_mask, const float* out_losses,
                          float* dL_dpred, void* stream);
 
+/* Fused photometric terms of the iteration's base loss (LG/train.py:128,182-188): out_losses[0] = mean |pred - gt|
+ * (l1_loss, LG/utils/loss_utils.py:40-41), out_losses[1] = mean SSIM map (ssim/_ssim, LG/utils/loss_utils.py:58-86:
+ * 11x11 Gaussian window sigma 1.5, zero "same" padding, C1 = 0.01^2, C2 = 0.03^2; same semantics as the optional
+ * fusedssim CUDA path, LG/utils/loss_utils.py:16-37).  pred, gt: (C,H,W) device fp32.  With want_backward != 0 the
+ * forward leaves three derivative maps in the workspace, which lg_photometric_loss_backward turns into
+ * dL_dpred = g_l1 * d(l1)/dpred + g_ssim * d(ssim)/dpred (g_*: device scalars or NULL = 0).  workspace: device
+ * scratch of >= lg_photometric_workspace_bytes(C,H,W) bytes, kept by the caller between forward and backward. */
+size_t lg_photometric_workspace_bytes(int C, int H, int W);
+int lg_photometric_loss_forward(const float* pred, const float* gt, int C, int H, int W, float* out_losses,
+                                char* workspace, size_t workspace_bytes, int want_backward, void* stream);
+int lg_photometric_loss_backward(const float* pred, const float* gt, int C, int H, int W, const char* workspace,
+                                 const float* g_l1, const float* g_ssim, float* dL_dpred, void* stream);
+
 /* Single-level Haar analysis (the pytorch_wavelets.DWTForward(J=1,'symmetric','db1') call sites at
  * LG/utils/loss_utils.py:140-148).  x (N*C,H,W) -> ll (N*C,H2,W2), yh (N*C,3,H2,W2) with H2=(H+1)/2.
  * and its adjoint (for autograd through the compat module).                                              */

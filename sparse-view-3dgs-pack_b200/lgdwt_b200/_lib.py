@@ -36,7 +36,7 @@ def _load():
     lib.lg_abi_version.restype = ctypes.c_int
     lib.lg_last_error.restype = ctypes.c_char_p
     for name in ("lg_geometry_state_bytes", "lg_image_state_bytes", "lg_binning_state_bytes", "lg_knn_workspace_bytes",
-                 "lg_dwt_workspace_bytes"):
+                 "lg_dwt_workspace_bytes", "lg_photometric_workspace_bytes"):
         getattr(lib, name).restype = ctypes.c_size_t
     lib.lg_geometry_state_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.lg_image_state_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
@@ -66,6 +66,11 @@ def _load():
                                         ctypes.c_size_t, _P]
     lib.lg_dwt_loss_backward.restype = i
     lib.lg_dwt_loss_backward.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, f, f, _P, _P, _P, _P, _P, _P]
+    lib.lg_photometric_workspace_bytes.argtypes = [i, i, i]
+    lib.lg_photometric_loss_forward.restype = i
+    lib.lg_photometric_loss_forward.argtypes = [_P, _P, i, i, i, _P, _P, ctypes.c_size_t, i, _P]
+    lib.lg_photometric_loss_backward.restype = i
+    lib.lg_photometric_loss_backward.argtypes = [_P, _P, i, i, i, _P, _P, _P, _P, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

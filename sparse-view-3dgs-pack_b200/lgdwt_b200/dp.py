@@ -130,12 +130,14 @@ def default_render(act, cam, bg, sh_degree=3, antialiasing=False):
 
 
 def default_loss(image, gt, lambda_dssim=0.2, dwt_scale=1.0, patch_weight=0.1, cfg=None):
-    """LG/train.py:128-202 without the SSIM term (SURVEY §8f-1 lists fused SSIM as the next component): L1 plus the
-    fused DWT loss, `loss = (1-lambda)*L1 + dwt_scale*dwt + patch_weight*patch`."""
+    """The iteration loss of LG/train.py:128-202 with fused kernels: base = (1-lambda)*L1 + lambda*(1-SSIM)
+    (`fused_photometric_loss`), plus `dwt_scale * dwt + patch_weight * patch` (`fused_dwt_loss`).  `dwt_scale` is the
+    caller's running-mean ratio (train.py:190-196); three launches forward, two backward."""
     from .dwt_loss import DWTLossConfig, fused_dwt_loss
-    l1 = (image - gt).abs().mean()
+    from .photometric import fused_photometric_loss
+    l1, ssim = fused_photometric_loss(image, gt)
     dwt, patch, _ = fused_dwt_loss(image, gt, cfg or DWTLossConfig())
-    return (1.0 - lambda_dssim) * l1 + dwt_scale * dwt + patch_weight * patch
+    return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ssim) + dwt_scale * dwt + patch_weight * patch
 
 
 class ViewParallelTrainer:

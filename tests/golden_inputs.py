@@ -9,6 +9,28 @@ def dwt_case_inputs(name, C, H, W):
     return pred, gt
 
 
+PHOTOMETRIC_CASES = {  # name: (C, H, W) — sizes around / below the 32x16 tile and the 11-tap window, odd sizes, C = 4
+    "noise": (3, 72, 104),
+    "smooth_odd": (3, 67, 131),
+    "tiny": (3, 7, 9),
+    "four_channels": (4, 48, 80),
+}
+
+
+def photometric_case_inputs(name, C, H, W):
+    """render-like pair: smooth structure + texture (pure noise for the "noise" case), pred = perturbed gt in [0,1]"""
+    rng = np.random.default_rng(1000 + sum(map(ord, name)))
+    if name == "noise":
+        gt = rng.random((C, H, W)).astype(np.float32)
+    else:
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+        gt = np.stack([0.5 + 0.35 * np.sin(0.11 * (c + 1) * xx + 0.3 * c) * np.cos(0.07 * (c + 2) * yy) for c in range(C)])
+        gt = np.clip(gt + 0.08 * rng.standard_normal((C, H, W)), 0, 1).astype(np.float32)
+    pred = np.clip(0.9 * gt + 0.04 + 0.05 * rng.standard_normal((C, H, W)), 0, 1).astype(np.float32)
+    pred[:, : H // 3, : W // 4] = gt[:, : H // 3, : W // 4]  # an exactly matching region: sign(0) = 0 in the L1 gradient
+    return pred, gt
+
+
 RASTER_CASES = {
     # name: (P, seed, spacing_scale, W, H, antialiasing, mode)
     "g_sh": (800, 11, 0.11, 120, 72, False, "sh"),

@@ -289,6 +289,47 @@ def test_fused_dwt_loss_matches_reference_golden_and_oracle(name):
         assert int(details[10]) == int(mask.sum())
 
 
+@pytest.mark.parametrize("name", list(golden_inputs.PHOTOMETRIC_CASES))
+def test_fused_photometric_loss_matches_reference_golden(name):
+    """L1 + SSIM terms of the base loss: fused kernels vs outputs / autograd gradients of the reference's own
+    loss_utils.l1_loss / ssim (tolerances: 2e-6 relative on the scalars, 1e-8 + 1e-4 relative on the gradient)."""
+    from lgdwt_b200 import fused_photometric_loss
+    gold = np.load(os.path.join(GOLD, "photometric_reference.npz"))
+    C, H, W = golden_inputs.PHOTOMETRIC_CASES[name]
+    pred, gt = golden_inputs.photometric_case_inputs(name, C, H, W)
+    p = T(pred).requires_grad_(True)
+    l1, s = fused_photometric_loss(p, T(gt))
+    np.testing.assert_allclose(float(l1), gold[name + "/l1"], rtol=2e-6)
+    np.testing.assert_allclose(float(s), gold[name + "/ssim"], rtol=2e-6)
+    (0.8 * l1 + 0.2 * (1.0 - s)).backward()
+    grad = p.grad.cpu().numpy()
+    np.testing.assert_allclose(grad[:, ::3, ::5], gold[name + "/grad_sub"], atol=1e-8, rtol=1e-4)
+    st = gold[name + "/grad_stats"]
+    np.testing.assert_allclose([grad.astype(np.float64).sum(), np.abs(grad).astype(np.float64).sum()], st[:2],
+                               rtol=1e-5, atol=1e-9)
+
+
+def test_fused_photometric_loss_full_size_vs_oracle_fp64():
+    """3x800x800 (the benchmark image size) and a (1,C,H,W) input: fused kernels vs the fp64 oracle."""
+    from lgdwt_b200 import fused_photometric_loss
+    from oracle import photometric_oracle
+    pred, gt = scenes.dwt_pair(3, 800, 800, seed=3)
+    p = T(pred).unsqueeze(0).requires_grad_(True)
+    l1, s = fused_photometric_loss(p, T(gt).unsqueeze(0))
+    (0.8 * l1 + 0.2 * (1.0 - s)).backward()
+    po = torch.from_numpy(pred).double().requires_grad_(True)
+    l1o, so = photometric_oracle.photometric_terms(po, torch.from_numpy(gt).double())
+    (0.8 * l1o + 0.2 * (1.0 - so)).backward()
+    assert abs(float(l1) - float(l1o)) <= 1e-6 * float(l1o)
+    assert abs(float(s) - float(so)) <= 1e-5 * abs(float(so))
+    g, go = p.grad[0].cpu().double(), po.grad
+    assert float((g - go).abs().max()) <= 1e-9 + 1e-4 * float(go.abs().max())
+    # no gradient requested -> the forward skips the derivative maps and still returns the same scalars
+    with torch.no_grad():
+        l1n, sn = fused_photometric_loss(T(pred), T(gt))
+    assert float(l1n) == float(l1) and float(sn) == float(s)
+
+
 def test_fused_dwt_loss_full_size_config1():
     """BASELINE config 1: 3x800x800 pair, default weights — fused kernel vs the oracle (fp32 and fp64)."""
     pred, gt = scenes.dwt_pair(3, 800, 800, seed=0)

@@ -128,6 +128,20 @@ def test_dwt_oracle_matches_reference_loss_utils(name):
     np.testing.assert_allclose(p.grad.numpy()[:, ::3, ::5], gold[name + "/grad_sub"], atol=1e-9, rtol=1e-5)
 
 
+@pytest.mark.parametrize("name", list(golden_inputs.PHOTOMETRIC_CASES))
+def test_photometric_oracle_matches_reference_loss_utils(name):
+    from oracle import photometric_oracle
+    gold = np.load(os.path.join(GOLD, "photometric_reference.npz"))
+    C, H, W = golden_inputs.PHOTOMETRIC_CASES[name]
+    pred, gt = golden_inputs.photometric_case_inputs(name, C, H, W)
+    p = torch.from_numpy(pred).requires_grad_(True)
+    l1, s = photometric_oracle.photometric_terms(p, torch.from_numpy(gt))
+    np.testing.assert_allclose(float(l1), gold[name + "/l1"], rtol=1e-6)
+    np.testing.assert_allclose(float(s), gold[name + "/ssim"], rtol=1e-6)
+    (0.8 * l1 + 0.2 * (1.0 - s)).backward()
+    np.testing.assert_allclose(p.grad.numpy()[:, ::3, ::5], gold[name + "/grad_sub"], atol=1e-9, rtol=1e-5)
+
+
 def test_haar_level_closed_form():
     x = torch.arange(2 * 3 * 6 * 8, dtype=torch.float32).reshape(2, 3, 6, 8).sin()
     LL, (LH, HL, HH) = dwt_oracle.haar_dwt_level(x)
