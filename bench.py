@@ -168,8 +168,8 @@ class Stepper:
         total = torch.zeros((), device=self.device)
         for v, (host_cam, host_gt) in enumerate(zip(host_cams, host_gts)):
             cam = dict(host_cam)
-            for k in ("viewmatrix", "projmatrix", "campos"):
-                cam[k] = host_cam[k].to(self.device, non_blocking=True)
+            pk = host_cam["packed"].to(self.device, non_blocking=True)  # one 140-byte upload per view
+            cam["viewmatrix"], cam["projmatrix"], cam["campos"] = pk[:16].view(4, 4), pk[16:32].view(4, 4), pk[32:35]
             with torch.cuda.stream(self.copy_stream):
                 # readers of this buffer belong to the previous step, which ended in .item()
                 self.dev_gt[v].copy_(host_gt, non_blocking=True)
@@ -340,8 +340,7 @@ def main():
     host_cams = []
     for c in cams:
         d = cam_dict(c, "cpu")
-        for k in ("viewmatrix", "projmatrix", "campos"):
-            d[k] = d[k].pin_memory()
+        d["packed"] = torch.cat([d["viewmatrix"].reshape(-1), d["projmatrix"].reshape(-1), d["campos"].reshape(-1)]).pin_memory()
         host_cams.append(d)
     rng = np.random.default_rng(7)
     host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory()

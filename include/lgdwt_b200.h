@@ -205,6 +205,16 @@ int lg_dwt_loss_backward(const float* pred, const float* gt, int C, int H, int W
                          const uint8_t* patch_mask, const float* out_losses,
                          float* dL_dpred, void* stream);
 
+/* Fused Adam update of one flat fp32 parameter buffer (the (59 x P) buffer of the view-parallel trainer), one pass
+ * instead of torch.optim.Adam's ~10 elementwise launches per group as the reference runs it (LG/train.py:278-288,
+ * groups LG/scene/gaussian_model.py:178-211).  torch.optim.Adam semantics (no amsgrad / weight decay), bias
+ * corrections from `step` (1-based), one learning rate per contiguous segment: segment s covers elements
+ * [segment_ends[s-1], segment_ends[s]) (host arrays; the last end must equal n).  grad is read as grad * grad_scale
+ * (e.g. 1 / views for the mean over a view batch). */
+int lg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int num_segments,
+                 const long long* segment_ends, const float* lrs, float beta1, float beta2, float eps, int step,
+                 float grad_scale, void* stream);
+
 /* Fused photometric terms of the iteration's base loss (LG/train.py:128,182-188): out_losses[0] = mean |pred - gt|
  * (l1_loss, LG/utils/loss_utils.py:40-41), out_losses[1] = mean SSIM map (ssim/_ssim, LG/utils/loss_utils.py:58-86:
  * 11x11 Gaussian window sigma 1.5, zero "same" padding, C1 = 0.01^2, C2 = 0.03^2; same semantics as the optional

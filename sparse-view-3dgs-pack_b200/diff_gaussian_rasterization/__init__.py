@@ -95,9 +95,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         channels = 3 if colors_c is None else int(colors_c.size(-1))
         M = 0 if sh_c is None else int(sh_c.size(1))
 
-        color = torch.zeros((channels, H, W), dtype=torch.float32, device=device)
-        invdepth = torch.zeros((1, H, W), dtype=torch.float32, device=device)
-        radii = torch.zeros((P,), dtype=torch.int32, device=device)
+        # the library writes every element of the three outputs when P > 0 (the reference fills them first,
+        # DGR/rasterize_points.cu:62-64); P == 0 returns its fill values
+        alloc = torch.zeros if P == 0 else torch.empty
+        color = alloc((channels, H, W), dtype=torch.float32, device=device)
+        invdepth = alloc((1, H, W), dtype=torch.float32, device=device)
+        radii = alloc((P,), dtype=torch.int32, device=device)
         geom, binning, img = (_lib.ResizableBuffer(device) for _ in range(3))
         num_rendered = ctypes.c_int(0)
         with torch.cuda.device(device):

@@ -71,6 +71,9 @@ def _load():
     lib.lg_photometric_loss_forward.argtypes = [_P, _P, i, i, i, _P, _P, ctypes.c_size_t, i, _P]
     lib.lg_photometric_loss_backward.restype = i
     lib.lg_photometric_loss_backward.argtypes = [_P, _P, i, i, i, _P, _P, _P, _P, _P]
+    lib.lg_adam_step.restype = i
+    lib.lg_adam_step.argtypes = [_P, _P, _P, _P, ctypes.c_longlong, i, ctypes.POINTER(ctypes.c_longlong),
+                                 ctypes.POINTER(f), f, f, f, i, f, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

@@ -90,14 +90,31 @@ class FlatGaussians:
         return dict(means3D=leaves["xyz"], shs=shs, opacities=torch.sigmoid(leaves["opacity"]),
                     scales=torch.exp(leaves["scaling"]), rotations=torch.nn.functional.normalize(leaves["rotation"]))
 
-    def adam_step(self, cfg: AdamConfig):
-        """torch.optim.Adam semantics (bias-corrected, eps outside the sqrt) applied slab by slab, identical on
-        every rank because the reduced gradient bucket is identical."""
+    def adam_step(self, cfg: AdamConfig, grad_scale: float = 1.0):
+        """torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), one learning rate per field slab;
+        identical on every rank because the reduced gradient bucket is identical.  CUDA buffers take ONE fused
+        kernel launch (lg_adam_step, 28 B of traffic per element); the slab-by-slab torch expression below is the
+        host-side statement of the same update, used by the CPU (gloo) tests of the trainer logic."""
         self.step_count += 1
         b1, b2 = cfg.beta1, cfg.beta2
-        bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
         lrs = dict(xyz=cfg.lr_xyz, f_dc=cfg.lr_f_dc, f_rest=cfg.lr_f_rest, opacity=cfg.lr_opacity,
                    scaling=cfg.lr_scaling, rotation=cfg.lr_rotation)
+        if self.data.is_cuda:
+            import ctypes
+            from . import _lib
+            n_seg = len(FIELDS)
+            ends = (ctypes.c_longlong * n_seg)(*[self._slices[name][1] for name, _ in FIELDS])
+            lr_arr = (ctypes.c_float * n_seg)(*[float(lrs[name]) for name, _ in FIELDS])
+            with torch.cuda.device(self.data.device):
+                rc = _lib.lib.lg_adam_step(self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.data.numel(), n_seg, ends, lr_arr, b1, b2,
+                                           cfg.eps, self.step_count, float(grad_scale),
+                                           _lib.stream_ptr(self.data.device))
+            _lib.check(rc, RuntimeError)
+            return
+        bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
+        if grad_scale != 1.0:
+            self.grad.mul_(grad_scale)
         self.exp_avg.mul_(b1).add_(self.grad, alpha=1 - b1)
         self.exp_avg_sq.mul_(b2).addcmul_(self.grad, self.grad, value=1 - b2)
         for name, _ in FIELDS:
@@ -171,9 +188,8 @@ class ViewParallelTrainer:
     def step(self, cams, gts, bg, num_views_scale=True):
         loss = self.accumulate_views(cams, gts, bg)
         self.reduce_gradients()
-        if num_views_scale and len(cams) > 1:
-            self.g.grad.div_(len(cams))  # mean over the view batch
-        self.g.adam_step(self.adam)
+        scale = 1.0 / len(cams) if (num_views_scale and len(cams) > 1) else 1.0  # mean over the view batch
+        self.g.adam_step(self.adam, grad_scale=scale)
         return loss
 
     def replicas_in_sync(self):
