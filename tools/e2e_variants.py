@@ -1,0 +1,59 @@
+"""Where does the e2e step differ from the resident step?  Times harness variants of bench.Stepper (ours only)."""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "sparse-view-3dgs-pack_b200")):
+    sys.path.insert(0, p)
+import bench
+dev = torch.device("cuda", 0)
+sc, cams, params = bench.make_workload(dev)
+V = bench.VIEWS_PER_RANK
+cam_devs = [bench.cam_dict(c, dev) for c in cams]
+host_cams = []
+for c in cams:
+    d = bench.cam_dict(c, "cpu")
+    d["packed"] = torch.cat([d["viewmatrix"].reshape(-1), d["projmatrix"].reshape(-1), d["campos"].reshape(-1)]).pin_memory()
+    host_cams.append(d)
+rng = np.random.default_rng(7)
+host_gts = [torch.from_numpy(rng.random((3, bench.HEIGHT, bench.WIDTH)).astype(np.float32)).pin_memory() for _ in range(8)]
+st = bench.Stepper("ours", params, dev, 1)
+ring = lambda i: [(i * V + v) % 8 for v in range(V)]
+
+def variant(name, upload_cam, upload_gt, loss_kind, item):
+    def step(i):
+        st.begin_step()
+        main = torch.cuda.current_stream(dev)
+        total = torch.zeros((), device=dev)
+        for v, j in enumerate(ring(i)):
+            if upload_cam:
+                cam = dict(host_cams[j])
+                pk = host_cams[j]["packed"].to(dev, non_blocking=True)
+                cam["viewmatrix"], cam["projmatrix"], cam["campos"] = pk[:16].view(4, 4), pk[16:32].view(4, 4), pk[32:35]
+            else:
+                cam = cam_devs[j]
+            if upload_gt:
+                with torch.cuda.stream(st.copy_stream):
+                    st.dev_gt[v].copy_(host_gts[j], non_blocking=True)
+                    st.copy_done[v].record(st.copy_stream)
+            color, radii, invd = st.render(cam, v == 0)
+            if upload_gt:
+                main.wait_event(st.copy_done[v])
+            if loss_kind == "l1":
+                loss = (color - st.dev_gt[v]).abs().mean()
+                loss.backward()
+                total += loss.detach()
+            else:
+                color.backward(st.dL)
+        if item:
+            return float(total.item())
+    for i in range(4):
+        step(i)
+    ms = bench.timed_loop(step, 15, 1, dev) / 15 / V
+    print("%-52s %.4f ms/view" % (name, ms))
+
+variant("resident: dev cam, no gt, backward(dL), no item", False, False, "dl", False)
+variant("+ item() per step", False, False, "dl", True)
+variant("+ L1 loss (torch ops)", False, False, "l1", True)
+variant("+ camera upload", True, False, "l1", True)
+variant("+ GT upload on side stream (= e2e)", True, True, "l1", True)
+variant("GT upload only, no loss", False, True, "dl", True)
