@@ -10,6 +10,10 @@
 
 namespace lg {
 
+#ifndef BWD_MIN_BLOCKS
+#define BWD_MIN_BLOCKS 4
+#endif
+
 #ifndef BWD_BATCH
 #define BWD_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
 #endif
@@ -54,7 +58,7 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, 
 // (backward.cu:598-632) are linear in these moments with per-Gaussian coefficients (conic, opacity), so the
 // coefficients are applied once per Gaussian in the per-Gaussian kernel instead of once per (pixel, Gaussian) hit.
 template <int C, bool INVD>
-__global__ void __launch_bounds__(LG_TILE_PIX, 4) blend_backward_kernel(
+__global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,

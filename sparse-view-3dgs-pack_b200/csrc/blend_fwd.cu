@@ -14,12 +14,16 @@
 
 namespace lg {
 
+#ifndef FWD_MIN_BLOCKS
+#define FWD_MIN_BLOCKS 5
+#endif
+
 #ifndef BLEND_BATCH
 #define BLEND_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
 #endif
 
 template <int C>
-__global__ void __launch_bounds__(LG_TILE_PIX, 5) blend_forward_kernel(
+__global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
