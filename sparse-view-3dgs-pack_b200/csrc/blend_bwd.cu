@@ -10,6 +10,9 @@
 
 namespace lg {
 
+#ifndef BWD_UNROLL
+#define BWD_UNROLL 2
+#endif
 #ifndef BWD_MIN_BLOCKS
 #define BWD_MIN_BLOCKS 4
 #endif
@@ -141,8 +144,17 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
         const int first = (int)max((long long)n_eff - (long long)warp_max - (long long)batch_base, 0ll);
         if (first >= batch) continue;
         const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, first, batch);
-        for (int k = 0; k < cnt; k++) {
-            const int j = s_list[warp][k];
+        // BWD_UNROLL list entries per trip: their power / exp / alpha evaluations are independent of each other and of
+        // the pixel state, so they are issued together; the hit paths then run in list order.
+        for (int k0 = 0; k0 < cnt; k0 += BWD_UNROLL) {
+          int js[BWD_UNROLL];
+          float dxs[BWD_UNROLL], dys[BWD_UNROLL], Gs[BWD_UNROLL], alphas[BWD_UNROLL], ids[BWD_UNROLL], invds[BWD_UNROLL];
+          bool hits[BWD_UNROLL];
+          unsigned any[BWD_UNROLL];
+#pragma unroll
+          for (int u = 0; u < BWD_UNROLL; u++) {
+            const bool has = k0 + u < cnt;
+            const int j = s_list[warp][has ? k0 + u : k0];
             const uint32_t rel = n_eff - 1u - (batch_base + (uint32_t)j);  // 0-based position in the tile's list
             const float4 xy = s_ent[j * 3 + 0];
             const float4 co = s_ent[j * 3 + 1];
@@ -151,8 +163,20 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
             const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
             const float G = expf(power);
             const float alpha = fminf(0.99f, F_MUL(co.w, G));
-            const bool hit = rel < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
+            const bool hit = has && rel < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            js[u] = j; dxs[u] = dx; dys[u] = dy; Gs[u] = G; alphas[u] = alpha; ids[u] = xy.z; invds[u] = xy.w;
+            hits[u] = hit;
+            any[u] = __ballot_sync(0xffffffffu, hit);
+          }
+#pragma unroll
+          for (int u = 0; u < BWD_UNROLL; u++) {
+            if (any[u] == 0u) continue;
+            const int j = js[u];
+            const float dx = dxs[u], dy = dys[u], G = Gs[u], alpha = alphas[u];
+            const bool hit = hits[u];
+            float4 xy;
+            xy.z = ids[u];
+            xy.w = invds[u];
 
             float v[NV];
 #pragma unroll
@@ -197,6 +221,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
             warp_multi_reduce<NV>(v, lane, total, slot, ok);
             if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
             if (ok) atomicAdd(grad_rec + (size_t)__float_as_uint(xy.z) * LG_REC + slot, total);
+          }
         }
     }
 }

@@ -14,6 +14,9 @@
 
 namespace lg {
 
+#ifndef FWD_UNROLL
+#define FWD_UNROLL 4
+#endif
 #ifndef FWD_MIN_BLOCKS
 #define FWD_MIN_BLOCKS 5
 #endif
@@ -82,29 +85,48 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
         // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)
         const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, 0, batch);
         const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
-        for (int k = 0; !done && k < cnt; k++) {
-            const int j = s_list[warp][k];
-            const float4 xy = s_ent[j * 3 + 0];
-            const float4 co = s_ent[j * 3 + 1];
-            const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
-            // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
-            const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
-            const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
-            if (power > 0.0f) continue;
-            const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
-            if (test_T < 0.0001f) {
-                done = true;
-                continue;
-            }
-            const float4 f = s_ent[j * 3 + 2];
-            const float fv[4] = {f.x, f.y, f.z, f.w};
+        // Two list entries per trip: their power / exp / alpha chains are independent (only T couples the entries of
+        // a pixel), so evaluating both before applying either doubles the instruction-level parallelism of the loop
+        // and halves its overhead.  The decisions are the reference's, in the reference's order (forward.cu:349-381).
+        for (int k = 0; !done && k < cnt; k += FWD_UNROLL) {
+            int js[FWD_UNROLL];
+            float4 xys[FWD_UNROLL];
+            float alphas[FWD_UNROLL];
+            bool pass[FWD_UNROLL];
 #pragma unroll
-            for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
-            acc_invd = F_FMA(T, F_MUL(alpha, xy.w), acc_invd);
-            T = test_T;
-            last_contributor = batch_base + (uint32_t)j + 1u;  // 1-based position in the tile list (forward.cu:345,381)
+            for (int u = 0; u < FWD_UNROLL; u++) {
+                const bool has = k + u < cnt;
+                const int j = s_list[warp][has ? k + u : k];
+                const float4 xy = s_ent[j * 3 + 0];
+                const float4 co = s_ent[j * 3 + 1];
+                const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
+                // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
+                const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
+                const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
+                const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
+                js[u] = j;
+                xys[u] = xy;
+                alphas[u] = alpha;
+                pass[u] = has && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < FWD_UNROLL; u++) {
+                if (pass[u] && !done) {
+                    const float alpha = alphas[u];
+                    const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        const float4 f = s_ent[js[u] * 3 + 2];
+                        const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                        for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
+                        acc_invd = F_FMA(T, F_MUL(alpha, xys[u].w), acc_invd);
+                        T = test_T;
+                        last_contributor = batch_base + (uint32_t)js[u] + 1u;  // 1-based list position (forward.cu:345,381)
+                    }
+                }
+            }
         }
     }
 
