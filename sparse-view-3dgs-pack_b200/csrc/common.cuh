@@ -297,9 +297,26 @@ __device__ __forceinline__ int lg_tile_index(int e, int M3) {
     if constexpr (M3C > 0) return (M3C & 1) ? e : e + e / M3C;
     else return (M3 & 1) ? e : e + e / M3;
 }
+// Full-warp fast path for the standard row length 48 (SH degree 3): element e = lane + 32 u of the block lives at
+// e + e / 48 = lane + 32 u + floor(2u / 3) + (u % 3 == 1 && lane >= 16), i.e. at a compile-time offset from one of two
+// per-lane bases, so every copy is one LDG/STG plus one STS/LDS with an immediate offset and no address arithmetic.
+__device__ __forceinline__ int lg_tile_index48(int u, unsigned lane) {
+    return (int)lane + 32 * u + (2 * u) / 3 + ((u % 3 == 1) ? (int)(lane >> 4) : 0);
+}
 template <int M3C>
 __device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ src, float* tile, int M3, int count,
                                                      unsigned lane) {
+    if (M3C == 48 && count == 32 * 48) {
+#pragma unroll
+        for (int u0 = 0; u0 < 48; u0 += LG_ROW_BATCH) {
+            float v[LG_ROW_BATCH];
+#pragma unroll
+            for (int u = 0; u < LG_ROW_BATCH; u++) v[u] = __ldg(src + lane + 32 * (u0 + u));
+#pragma unroll
+            for (int u = 0; u < LG_ROW_BATCH; u++) tile[lg_tile_index48(u0 + u, lane)] = v[u];
+        }
+        return;
+    }
     for (int e0 = (int)lane; e0 < count; e0 += 32 * LG_ROW_BATCH) {
         float v[LG_ROW_BATCH];
 #pragma unroll
@@ -317,6 +334,23 @@ __device__ __forceinline__ void lg_warp_rows_to_tile(const float* __restrict__ s
 template <int M3C>
 __device__ __forceinline__ void lg_warp_tile_to_rows(float* __restrict__ dst, const float* tile, int M3, int count,
                                                      unsigned lane, bool accumulate) {
+    if (M3C == 48 && count == 32 * 48) {
+        if (accumulate) {
+#pragma unroll
+            for (int u0 = 0; u0 < 48; u0 += LG_ROW_BATCH) {
+                float v[LG_ROW_BATCH];
+#pragma unroll
+                for (int u = 0; u < LG_ROW_BATCH; u++) v[u] = dst[lane + 32 * (u0 + u)];
+#pragma unroll
+                for (int u = 0; u < LG_ROW_BATCH; u++)
+                    dst[lane + 32 * (u0 + u)] = v[u] + tile[lg_tile_index48(u0 + u, lane)];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 48; u++) dst[lane + 32 * u] = tile[lg_tile_index48(u, lane)];
+        }
+        return;
+    }
     if (accumulate) {
         for (int e0 = (int)lane; e0 < count; e0 += 32 * LG_ROW_BATCH) {
             float v[LG_ROW_BATCH];
