@@ -169,20 +169,34 @@ __global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uin
 }
 
 // identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted tile ids; tiles with no entries keep (0,0).
+// Four consecutive ids per thread (one 16-byte load + the id before them).
 __global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
                                                           uint2* __restrict__ ranges) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = tile_keys[idx];
-    if (idx == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = tile_keys[idx - 1];
-        if (cur != prev) {
-            ranges[prev].y = idx;
-            ranges[cur].x = idx;
+    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (base >= L) return;
+    uint32_t k[4];
+    if (base + 4u <= L) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + base);
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) k[i] = base + i < L ? tile_keys[base + i] : 0u;
+    }
+    uint32_t prev = base == 0 ? 0u : tile_keys[base - 1];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t idx = base + i;
+        if (idx < L) {
+            const uint32_t cur = k[i];
+            if (idx == 0) ranges[cur].x = 0;
+            else if (cur != prev) {
+                ranges[prev].y = idx;
+                ranges[cur].x = idx;
+            }
+            if (idx == L - 1) ranges[cur].y = L;
+            prev = cur;
         }
     }
-    if (idx == L - 1) ranges[cur].y = L;
 }
 
 // inspection only (lg_state_read "point_list_keys"): the reference's sorted 64-bit keys
@@ -244,7 +258,7 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
         rc = radix_sort_pairs_u32(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
                                   &in_b);
     if (rc != LG_OK) return rc;
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);
+    tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);
     LG_LAUNCH_CHECK(debug, stream);
     return LG_OK;
 }

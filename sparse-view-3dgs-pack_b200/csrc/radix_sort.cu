@@ -55,25 +55,6 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(const K* __restrict__
     }
 }
 
-// exclusive scan of each 256-bin histogram in place; one block per digit place
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_warp[RS_WARPS];
-    uint32_t* h = hist + blockIdx.x * RS_RADIX;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t v = h[threadIdx.x];
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t base = 0;
-    for (unsigned w = 0; w < warp; w++) base += s_warp[w];
-    h[threadIdx.x] = base + incl - v;
-}
-
 // ------------------------------------------------------------------ one digit pass
 template <typename K>
 struct RsSmem {
@@ -81,6 +62,7 @@ struct RsSmem {
     uint32_t tile_excl[RS_RADIX];
     uint32_t digit_off[RS_RADIX];
     uint32_t warp_sums[RS_WARPS];
+    uint32_t hist_sums[RS_WARPS];
     uint32_t tile_id;
     uint32_t vals[RS_TILE];
     K keys[RS_TILE];
@@ -91,7 +73,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                                  uint32_t digit_mask,
-                                                                 const uint32_t* __restrict__ global_offsets,
+                                                                 const uint32_t* __restrict__ global_hist,
                                                                  volatile uint32_t* lookback,
                                                                  volatile uint32_t* group_desc, uint32_t* ticket) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
@@ -101,7 +83,20 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
     if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int w = 0; w < RS_WARPS; w++) s.warp_hist[w][tid] = 0;
+    // exclusive scan of this digit place's 256-bin histogram = where every digit's run starts in the output (each
+    // block redoes this 256-element scan instead of a separate launch between the histogram and the passes)
+    const uint32_t hist_count = global_hist[tid];
+    uint32_t hist_incl = hist_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, hist_incl, o);
+        if (lane >= (unsigned)o) hist_incl += t;
+    }
+    if (lane == 31) s.hist_sums[warp] = hist_incl;
     __syncthreads();
+    uint32_t global_offset = hist_incl - hist_count;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) global_offset += (w < (int)warp) ? s.hist_sums[w] : 0u;
     const uint32_t tile = s.tile_id;
     const uint32_t tile_base = tile * RS_TILE;
     const uint32_t warp_base = tile_base + warp * (32 * RS_IPT);
@@ -267,7 +262,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const K* __rest
             prev += g & LB_VALUE;
         }
     }
-    s.digit_off[tid] = global_offsets[tid] + prev - excl_in_tile;
+    s.digit_off[tid] = global_offset + prev - excl_in_tile;
     __syncthreads();
 
     // coalesced write-out: consecutive threads hold consecutive slots of a digit run
@@ -371,9 +366,6 @@ static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_
         rs_histogram_kernel<K><<<hist_blocks, 256, 0, stream>>>(keys_a, (uint32_t)n, begin_bit, end_bit, passes, hist);
         LG_LAUNCH_CHECK(debug, stream);
     }
-    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, stream>>>(hist);
-    LG_LAUNCH_CHECK(debug, stream);
-
     static bool attr_set = false;
     const size_t smem = sizeof(RsSmem<K>);
     if (!attr_set || true) {
