@@ -16,6 +16,8 @@ from bringup import timeit  # noqa: E402
 
 
 def cfg(name):
+    if name == "cfg2":   # Blender-style init, 100k Gaussians, 800x800 (the reference's quoted small case)
+        return scenes.blender_init_scene(100_000, seed=0), scenes.metric_camera(800, 800)
     if name == "cfg3":   # LLFF-style: 1008x756, ~500k Gaussians, forward-facing slab
         return scenes.slab_scene(500_000, seed=2), scenes.look_at_camera(1008, 756, 1.05, 2 * math.atan(math.tan(0.525) * 756 / 1008), (0.0, 0.0, 0.0), target=(0.0, 0.0, 5.0))
     if name == "cfg4":   # RGB+NIR scale: 1296x964, 1M Gaussians
@@ -29,7 +31,7 @@ def cfg(name):
 def main():
     names = sys.argv[1:] or ["all"]
     if names == ["all"]:
-        names = ["cfg3", "cfg4", "cfg5"]
+        names = ["cfg2", "cfg3", "cfg4", "cfg5"]
     for name in names:
         sc, cam = cfg(name)
         t, c = helpers.scene_to_torch(sc), helpers.cam_to_torch(cam)
@@ -60,14 +62,35 @@ def main():
             fr = f_ref()
             g_o = helpers.backward_ours(t, c, cam, bg, fo, dL, None)
             g_r = helpers.backward_ref(t, c, cam, bg, fr, dL, None)
-            worst = 0.0
+            worst, detail = 0.0, []
             for k in ("dL_dmean3D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot"):
                 if g_o.get(k) is None or g_r.get(k) is None:
                     continue
                 a, b = g_o[k].double().reshape(-1), g_r[k].double().reshape(-1)
-                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
+                e = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+                detail.append("%s %.2g (|ref|max %.2g)" % (k[3:], e, float(b.abs().max())))
+                if float(b.abs().max()) > 1e-6:  # e.g. dL/drot of isotropic Gaussians is rounding noise on both sides
+                    worst = max(worst, e)
+            print("   per-tensor rel err:", "; ".join(detail))
             print("   ref  fwd %.3f ms, bwd %.3f ms | worst gradient rel err %.3g" % (
                 timeit(f_ref)[0], timeit(lambda: helpers.backward_ref(t, c, cam, bg, fr, dL, dL[:1].contiguous()))[0], worst))
+        if name == "cfg4":  # RGB+NIR: one 4-channel pass of ours vs two 3-channel passes of the reference (render + render_nir)
+            P = sc.means3D.shape[0]
+            col4 = torch.rand((P, 4), device="cuda")
+            bg4 = torch.zeros(4, device="cuda")
+            dL4 = torch.randn((4, cam.image_height, cam.image_width), device="cuda")
+            f4 = lambda: helpers.run_ours(t, c, cam, bg4, colors_precomp=col4, want_state=False)
+            fo4 = f4()
+            t_f = timeit(f4)[0]
+            t_b = timeit(lambda: helpers.backward_ours(t, c, cam, bg4, fo4, dL4, None, colors_precomp=col4))[0]
+            print("   RGB+NIR ours, ONE 4-channel pass: fwd %.3f ms, bwd %.3f ms" % (t_f, t_b))
+            if have_ref:
+                col3 = col4[:, :3].contiguous()
+                fr3 = lambda: helpers.run_ref(t, c, cam, bg, colors_precomp=col3, want_state=False)
+                fr = fr3()
+                r_f = timeit(fr3)[0]
+                r_b = timeit(lambda: helpers.backward_ref(t, c, cam, bg, fr, dL, dL[:1].contiguous(), colors_precomp=col3))[0]
+                print("   RGB+NIR reference, TWO 3-channel passes: fwd %.3f ms, bwd %.3f ms" % (2 * r_f, 2 * r_b))
         del ours, fo
         torch.cuda.empty_cache()
 
