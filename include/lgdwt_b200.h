@@ -140,6 +140,30 @@ int lg_rasterize_backward_ex(
     float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
     int antialiasing, int debug, void* stream, int accumulate);
 
+/* Same call for a trainer that keeps RAW (pre-activation) parameters (no counterpart in the reference, which leaves
+ * the activation chain rule to autograd: sigmoid / exp / normalize of LG/scene/gaussian_model.py:36-50,102-130 and
+ * their backward are ~10 P-sized PyTorch launches per view).  With raw_rot_norm != NULL (P floats = |raw rotation|,
+ * written by lg_activate_forward) `opacities`, `scales`, `rotations` must be the activated values of the raw
+ * parameters, and dL_dopacity / dL_dscale / dL_drot receive the gradients w.r.t. the RAW opacity / scaling /
+ * rotation: d/draw_opacity = d/do * o(1-o); d/draw_scaling = d/ds * s; d/draw_rot = (g - q (q.g)) / max(|raw|,1e-12).
+ * dL_dmean3D and dL_dsh are unchanged (those parameters have no activation).  NULL = lg_rasterize_backward_ex. */
+int lg_rasterize_backward_raw(
+    int P, int D, int M, int R, int channels, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+    const int* radii, char* geometry_state, char* binning_state, char* image_state, const float* dL_dpix,
+    const float* dL_dinvdepth_pix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+    int antialiasing, int debug, void* stream, int accumulate, const float* raw_rot_norm);
+
+/* Activations of the raw parameters in one pass (get_opacity / get_scaling / get_rotation,
+ * LG/scene/gaussian_model.py:102-130): opacities = sigmoid(raw) = 1/(1+exp(-x)); scales = exp(raw);
+ * rotations = raw / max(|raw|_2, 1e-12) (torch.nn.functional.normalize); rot_norm = |raw|_2.  32 B in, 36 B out per
+ * Gaussian.  xyz and the SH coefficients have no activation and are used in place. */
+int lg_activate_forward(int P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,
+                        float* opacities, float* scales, float* rotations, float* rot_norm, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (DGR/cuda_rasterizer/rasterizer.h:24-29,
  * rasterizer_impl.cu:54-66,141-153; torch glue DGR/rasterize_points.cu:225-244).  present: (P) uint8/bool. */
 int lg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
@@ -214,6 +238,45 @@ int lg_dwt_loss_backward(const float* pred, const float* gt, int C, int H, int W
 int lg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int num_segments,
                  const long long* segment_ends, const float* lrs, float beta1, float beta2, float eps, int step,
                  float grad_scale, void* stream);
+
+/* lg_adam_step with two learning rates inside a segment: segment s is a (rows, row_width[s]) array whose first
+ * row_split[s] columns use lrs[s] and the rest lrs_b[s] (the SH slab (P, 16, 3): 3 f_dc floats at feature_lr, 45
+ * f_rest floats at feature_lr / 20, LG/scene/gaussian_model.py:181-182).  row_width[s] <= 1 = a plain segment. */
+int lg_adam_step_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                       int num_segments, const long long* segment_ends, const float* lrs, const float* lrs_b,
+                       const int* row_width, const int* row_split, float beta1, float beta2, float eps, int step,
+                       float grad_scale, void* stream);
+
+/* Adaptive density control on the flat field-major parameter buffer of the view-parallel trainer
+ * (F = 11 + sh_floats floats per Gaussian: xyz 3 | SH (M,3) = f_dc then f_rest | opacity 1 | scaling 3 | rotation 4,
+ * every field a contiguous (P, w) slab; the same buffer lg_adam_step updates).  Replaces the boolean-index + torch.cat
+ * surgery of GaussianModel.densify_and_prune / densify_and_clone / densify_and_split / prune_points and the Adam-state
+ * edits (LG/scene/gaussian_model.py:331-476), add_densification_stats (:478-480) with the max_radii2D update of
+ * LG/train.py:268, and reset_opacity (:258-261).
+ *
+ * lg_densify_plan: per-Gaussian decisions from the raw scaling (P,3) / opacity (P,1) slabs and the statistics
+ *   (grad_accum, denom: P floats), thresholds as the reference passes them (max_grad = densify_grad_threshold,
+ *   min_opacity = 0.005, extent = cameras_extent, percent_dense, max_screen_size < 0 = None).  Writes, for every
+ *   output row d, src_index[d] = source row | kind << 30 (0 original, 1 clone, 2/3 first/second split child) and, for
+ *   children, eps_row[d] = row of the unit-normal sample; both arrays hold 2*P entries.  totals (device, 4 ints) =
+ *   {kept originals, kept clones, split parents S, kept split parents}; P_new = t[0] + t[1] + 2*t[3]; the caller draws
+ *   eps (2*S, 3) ~ N(0,1) (torch.normal's samples, :421-423) from a generator shared by all ranks.
+ * lg_densify_apply: one gather pass per field writes the P_new-row parameter buffer and both Adam moments (moments of
+ *   new rows zero, cat_tensors_to_optimizer :376-378).  Output order = the reference's (see csrc/densify.cu).
+ * The statistics of the new set are zeros of length P_new (densification_postfix :404-409): the caller re-allocates. */
+size_t lg_densify_scratch_bytes(int P);
+int lg_densify_plan(int P, const float* scaling, const float* opacity, const float* grad_accum, const float* denom,
+                    float max_grad, float min_opacity, float extent, float percent_dense, float max_screen_size,
+                    uint32_t* src_index, uint32_t* eps_row, int* totals, void* scratch, size_t scratch_bytes,
+                    void* stream);
+int lg_densify_apply(int P, int P_new, int sh_floats, const float* data, const float* exp_avg,
+                     const float* exp_avg_sq, float* data_new, float* exp_avg_new, float* exp_avg_sq_new,
+                     const uint32_t* src_index, const uint32_t* eps_row, const float* eps, int eps_rows, void* stream);
+/* visible = radii > 0:  grad_accum += |grad2D.xy|, denom += 1, max_radii2D = max(max_radii2D, radii) */
+int lg_densify_stats(int P, const float* grad2D, const int* radii, float* grad_accum, float* denom,
+                     float* max_radii2D, void* stream);
+/* opacity <- inverse_sigmoid(min(sigmoid(opacity), 0.01)), Adam moments of the opacity slab <- 0 */
+int lg_reset_opacity(int P, float* opacity, float* exp_avg, float* exp_avg_sq, void* stream);
 
 /* Fused photometric terms of the iteration's base loss (LG/train.py:128,182-188): out_losses[0] = mean |pred - gt|
  * (l1_loss, LG/utils/loss_utils.py:40-41), out_losses[1] = mean SSIM map (ssim/_ssim, LG/utils/loss_utils.py:58-86:

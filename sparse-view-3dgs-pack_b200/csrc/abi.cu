@@ -218,7 +218,7 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
     return rc;
 }
 
-int lg_rasterize_backward_ex(int P, int D, int M, int R, int channels, const float* background, int width, int height,
+int lg_rasterize_backward_raw(int P, int D, int M, int R, int channels, const float* background, int width, int height,
                           const float* means3D, const float* shs, const float* colors_precomp,
                           const float* opacities, const float* scales, float scale_modifier, const float* rotations,
                           const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
@@ -227,7 +227,7 @@ int lg_rasterize_backward_ex(int P, int D, int M, int R, int channels, const flo
                           const float* dL_dinvdepth_pix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolor, float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                           float* dL_dscale, float* dL_drot, int antialiasing, int debug, void* stream_v,
-                          int accumulate) {
+                          int accumulate, const float* raw_rot_norm) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (P < 0 || R < 0 || width <= 0 || height <= 0 || channels < 1 || channels > LG_MAX_CHANNELS) {
         set_error("lg_rasterize_backward: invalid sizes");
@@ -267,6 +267,7 @@ int lg_rasterize_backward_ex(int P, int D, int M, int R, int channels, const flo
     a.focal_y = height / (2.0f * tan_fovy);
     a.focal_x = width / (2.0f * tan_fovx);
     a.antialiasing = antialiasing != 0; a.has_invdepth = dL_dinvdepth_pix != nullptr; a.accumulate = accumulate != 0;
+    a.raw_rot_norm = raw_rot_norm;
     a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
     a.dL_dinvdepth = dL_dinvdepth; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh;
     a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
@@ -274,6 +275,24 @@ int lg_rasterize_backward_ex(int P, int D, int M, int R, int channels, const flo
     rc = launch_preprocess_backward(a, g, radii, debug != 0, stream);
     stage_end(ST_PREGRAD, stream);
     return rc;
+}
+
+int lg_rasterize_backward_ex(int P, int D, int M, int R, int channels, const float* background, int width, int height,
+                          const float* means3D, const float* shs, const float* colors_precomp,
+                          const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                          const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geometry_state,
+                          char* binning_state, char* image_state, const float* dL_dpix,
+                          const float* dL_dinvdepth_pix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                          float* dL_dcolor, float* dL_dinvdepth, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                          float* dL_dscale, float* dL_drot, int antialiasing, int debug, void* stream_v,
+                          int accumulate) {
+    return lg_rasterize_backward_raw(P, D, M, R, channels, background, width, height, means3D, shs, colors_precomp,
+                                     opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                                     campos, tan_fovx, tan_fovy, radii, geometry_state, binning_state, image_state,
+                                     dL_dpix, dL_dinvdepth_pix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                     dL_dinvdepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, antialiasing,
+                                     debug, stream_v, accumulate, nullptr);
 }
 
 int lg_rasterize_backward(int P, int D, int M, int R, int channels, const float* background, int width, int height,

@@ -12,6 +12,8 @@ namespace lg {
 struct AdamSegments {
     long long end[ADAM_MAX_SEGMENTS];  // exclusive end offset (elements) of every segment, ascending
     float step_size[ADAM_MAX_SEGMENTS];  // lr / (1 - b1^t)
+    float step_size_b[ADAM_MAX_SEGMENTS];  // second rate of a split segment (columns >= split of every row)
+    int width[ADAM_MAX_SEGMENTS], split[ADAM_MAX_SEGMENTS];  // width <= 1: plain segment
     int count;
 };
 
@@ -19,17 +21,39 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, co
                                                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                    long long n, AdamSegments seg, float beta1, float beta2, float eps,
                                                    float inv_sqrt_bc2, float grad_scale) {
+    // four independent elements per trip (all 16 loads issued before the first use) keep enough bytes in flight
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int s = 0;
-        while (s + 1 < seg.count && i >= seg.end[s]) s++;
-        const float g = grad[i] * grad_scale;
-        const float m = beta1 * exp_avg[i] + (1.0f - beta1) * g;
-        const float v = beta2 * exp_avg_sq[i] + (1.0f - beta2) * g * g;
-        exp_avg[i] = m;
-        exp_avg_sq[i] = v;
-        const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
-        param[i] = param[i] - seg.step_size[s] * (m / denom);
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
+        float g[4], m[4], v[4], p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * stride;
+            if (i < n) {
+                g[u] = grad[i];
+                m[u] = exp_avg[i];
+                v[u] = exp_avg_sq[i];
+                p[u] = param[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * stride;
+            if (i >= n) break;
+            int s = 0;
+            while (s + 1 < seg.count && i >= seg.end[s]) s++;
+            float step = seg.step_size[s];
+            if (seg.width[s] > 1) {
+                const long long local = i - (s ? seg.end[s - 1] : 0);
+                if ((int)(local % seg.width[s]) >= seg.split[s]) step = seg.step_size_b[s];
+            }
+            const float gs = g[u] * grad_scale;
+            const float mn = beta1 * m[u] + (1.0f - beta1) * gs;
+            const float vn = beta2 * v[u] + (1.0f - beta2) * gs * gs;
+            exp_avg[i] = mn;
+            exp_avg_sq[i] = vn;
+            const float denom = sqrtf(vn) * inv_sqrt_bc2 + eps;
+            param[i] = p[u] - step * (mn / denom);
+        }
     }
 }
 
@@ -37,9 +61,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, co
 
 using namespace lg;
 
-extern "C" int lg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
-                            int num_segments, const long long* segment_ends_host, const float* lrs_host, float beta1,
-                            float beta2, float eps, int step, float grad_scale, void* stream_v) {
+extern "C" int lg_adam_step_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                  int num_segments, const long long* segment_ends_host, const float* lrs_host,
+                                  const float* lrs_b_host, const int* row_width_host, const int* row_split_host,
+                                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || num_segments < 1 || num_segments > ADAM_MAX_SEGMENTS ||
         !segment_ends_host || !lrs_host || step < 1) {
@@ -58,6 +83,14 @@ extern "C" int lg_adam_step(float* param, const float* grad, float* exp_avg, flo
         }
         prev = seg.end[s] = segment_ends_host[s];
         seg.step_size[s] = (float)((double)lrs_host[s] / bc1);
+        seg.width[s] = row_width_host ? row_width_host[s] : 1;
+        seg.split[s] = row_split_host ? row_split_host[s] : 0;
+        seg.step_size_b[s] = (float)((double)(lrs_b_host ? lrs_b_host[s] : lrs_host[s]) / bc1);
+        if (seg.width[s] > 1 && (!lrs_b_host || seg.split[s] < 0 || seg.split[s] > seg.width[s] ||
+                                 (seg.end[s] - (s ? seg.end[s - 1] : 0)) % seg.width[s] != 0)) {
+            set_error("lg_adam_step_split: segment %d is not a whole number of rows of %d floats", s, seg.width[s]);
+            return LG_ERR_INVALID_ARGUMENT;
+        }
     }
     if (prev != n) {
         set_error("lg_adam_step: the last segment must end at n");
@@ -68,4 +101,11 @@ extern "C" int lg_adam_step(float* param, const float* grad, float* exp_avg, flo
                                             (float)(1.0 / sqrt(bc2)), grad_scale);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
+}
+
+extern "C" int lg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                            int num_segments, const long long* segment_ends_host, const float* lrs_host, float beta1,
+                            float beta2, float eps, int step, float grad_scale, void* stream_v) {
+    return lg_adam_step_split(param, grad, exp_avg, exp_avg_sq, n, num_segments, segment_ends_host, lrs_host, nullptr,
+                              nullptr, nullptr, beta1, beta2, eps, step, grad_scale, stream_v);
 }

@@ -151,6 +151,7 @@ struct BackwardArgs {
     float focal_x, focal_y;
     bool antialiasing;
     bool has_invdepth;
+    const float* raw_rot_norm;  // non-null: parameter gradients w.r.t. the raw (pre-activation) parameters
     bool accumulate;  // add to dL_dmean3D / dL_dsh / dL_dopacity / dL_dscale / dL_drot instead of overwriting them
     float* dL_dmean2D;
     float* dL_dconic;

@@ -27,6 +27,7 @@ struct PreGradArgs {
     float focal_x, focal_y, tan_fovx, tan_fovy;
     int antialiasing, has_invdepth, sh_path, scale_path, accumulate;
     const float* __restrict__ rec;
+    const float* __restrict__ rot_norm;  // non-null: emit gradients w.r.t. the RAW opacity / scaling / rotation
     float* __restrict__ dL_dmean2D;
     float* __restrict__ dL_dconic;
     float* __restrict__ dL_dopacity;
@@ -371,6 +372,20 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
             dq[3] = 2 * qr * (dMt[0][1] - dMt[1][0]) + 2 * qx * (dMt[2][0] + dMt[0][2]) + 2 * qy * (dMt[1][2] + dMt[2][1]) -
                     4 * qz * (dMt[1][1] + dMt[0][0]);
         }
+        if (a.rot_norm != nullptr && visible) {
+            // chain rule of the activations of LG/scene/gaussian_model.py:36-50 (the reference leaves it to autograd):
+            // scales = exp(raw) -> d/draw = d/dscale * scale; rotations = raw / max(|raw|, 1e-12) ->
+            // d/draw = (g - q (q . g)) / max(|raw|, 1e-12) with q the unit quaternion the forward was given
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+#pragma unroll
+            for (int k = 0; k < 3; k++) ds[k] *= a.scales[3 * i + k];
+            const float dot = q.x * dq[0] + q.y * dq[1] + q.z * dq[2] + q.w * dq[3];
+            const float inv_n = 1.0f / fmaxf(a.rot_norm[i], 1e-12f);
+            dq[0] = (dq[0] - q.x * dot) * inv_n;
+            dq[1] = (dq[1] - q.y * dot) * inv_n;
+            dq[2] = (dq[2] - q.z * dot) * inv_n;
+            dq[3] = (dq[3] - q.w * dot) * inv_n;
+        }
         if (a.accumulate) {
             const float4 old = reinterpret_cast<const float4*>(a.dL_drot)[i];
             dq[0] += old.x; dq[1] += old.y; dq[2] += old.z; dq[3] += old.w;
@@ -383,6 +398,10 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
         reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
 
+    if (a.rot_norm != nullptr) {  // opacities = sigmoid(raw) -> d/draw = d/dopacity * o (1 - o)
+        const float o = a.opacities[i];
+        dopacity *= o * (1.0f - o);
+    }
     if (a.accumulate) {
         dopacity += a.dL_dopacity[i];
 #pragma unroll
@@ -415,6 +434,7 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
     a.sh_path = (b.shs != nullptr && b.dL_dsh != nullptr && b.M > 0) ? 1 : 0;
     a.scale_path = (b.scales != nullptr && b.rotations != nullptr) ? 1 : 0;
     a.rec = g.grad_scratch;
+    a.rot_norm = (a.scale_path ? b.raw_rot_norm : nullptr);
     a.dL_dmean2D = b.dL_dmean2D; a.dL_dconic = b.dL_dconic; a.dL_dopacity = b.dL_dopacity; a.dL_dcolor = b.dL_dcolor;
     a.dL_dinvdepth = b.dL_dinvdepth; a.dL_dmean3D = b.dL_dmean3D; a.dL_dcov3D = b.dL_dcov3D; a.dL_dsh = b.dL_dsh;
     a.dL_dscale = b.dL_dscale; a.dL_drot = b.dL_drot;

@@ -30,12 +30,18 @@ class GradSinks:
     means3D (P,3), shs (P,M,3), opacities (P,1), scales (P,3), rotations (P,4): contiguous fp32 CUDA tensors (typically
     views of one flat bucket).  With accumulate=False the backward overwrites them, with accumulate=True it adds to
     them.  The autograd gradients of those five inputs are then None (nothing for autograd to add a second time);
-    means2D still receives its gradient the usual way (densification statistics read means2D.grad)."""
-    __slots__ = ("means3D", "shs", "opacities", "scales", "rotations", "accumulate")
+    means2D still receives its gradient the usual way (densification statistics read means2D.grad).
 
-    def __init__(self, means3D, shs, opacities, scales, rotations, accumulate=False):
+    raw_rot_norm (P,): when given, the rasterizer's opacities / scales / rotations inputs are declared to be
+    sigmoid / exp / normalize of a trainer's raw parameters (`lgdwt_b200.activate`), and the opacities / scales /
+    rotations sinks receive the gradients w.r.t. those RAW parameters (chain rule applied inside the
+    preprocess-backward kernel, lg_rasterize_backward_raw)."""
+    __slots__ = ("means3D", "shs", "opacities", "scales", "rotations", "accumulate", "raw_rot_norm")
+
+    def __init__(self, means3D, shs, opacities, scales, rotations, accumulate=False, raw_rot_norm=None):
         self.means3D, self.shs, self.opacities, self.scales, self.rotations = means3D, shs, opacities, scales, rotations
         self.accumulate = bool(accumulate)
+        self.raw_rot_norm = raw_rot_norm
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -172,7 +178,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             dL_drotations = new(P, 4) if has_scales else None
         if P > 0:
             with torch.cuda.device(device):
-                rc = _lib.lib.lg_rasterize_backward_ex(
+                rot_norm = None if sinks is None else sinks.raw_rot_norm
+                if rot_norm is not None and (rot_norm.dtype != torch.float32 or rot_norm.numel() != P
+                                             or not rot_norm.is_contiguous() or rot_norm.device != device):
+                    raise RuntimeError("grad_sinks.raw_rot_norm must be a contiguous fp32 CUDA tensor of P elements")
+                rc = _lib.lib.lg_rasterize_backward_raw(
                     P, int(rs.sh_degree), M, ctx.num_rendered, C,
                     _lib.ptr(bg_c), W, H,
                     _lib.ptr(means3D_c), _lib.ptr(sh_c), _lib.ptr(colors_c), _lib.ptr(opac_c), _lib.ptr(scales_c),
@@ -184,7 +194,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _lib.ptr(dL_dmeans2D), None, _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors), None,
                     _lib.ptr(dL_dmeans3D), _lib.ptr(dL_dcov3D), _lib.ptr(dL_dsh), _lib.ptr(dL_dscales),
                     _lib.ptr(dL_drotations), int(bool(rs.antialiasing)), int(bool(rs.debug)),
-                    _lib.stream_ptr(device), int(sinks is not None and sinks.accumulate))
+                    _lib.stream_ptr(device), int(sinks is not None and sinks.accumulate), _lib.ptr(rot_norm))
             _lib.check(rc, RuntimeError)
         elif sinks is not None and not sinks.accumulate:
             for t in (dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations):

@@ -55,6 +55,10 @@ def _load():
         [i, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f] + [_P] * 16 + [i, i, _P])
     lib.lg_rasterize_backward_ex.restype = i
     lib.lg_rasterize_backward_ex.argtypes = lib.lg_rasterize_backward.argtypes + [i]
+    lib.lg_rasterize_backward_raw.restype = i
+    lib.lg_rasterize_backward_raw.argtypes = lib.lg_rasterize_backward_ex.argtypes + [_P]
+    lib.lg_activate_forward.restype = i
+    lib.lg_activate_forward.argtypes = [i] + [_P] * 8
     lib.lg_mark_visible.restype = i
     lib.lg_mark_visible.argtypes = [i, _P, _P, _P, _P, _P]
     lib.lg_state_read.restype = i
@@ -74,6 +78,20 @@ def _load():
     lib.lg_adam_step.restype = i
     lib.lg_adam_step.argtypes = [_P, _P, _P, _P, ctypes.c_longlong, i, ctypes.POINTER(ctypes.c_longlong),
                                  ctypes.POINTER(f), f, f, f, i, f, _P]
+    lib.lg_adam_step_split.restype = i
+    lib.lg_adam_step_split.argtypes = [_P, _P, _P, _P, ctypes.c_longlong, i, ctypes.POINTER(ctypes.c_longlong),
+                                       ctypes.POINTER(f), ctypes.POINTER(f), ctypes.POINTER(i), ctypes.POINTER(i),
+                                       f, f, f, i, f, _P]
+    lib.lg_densify_scratch_bytes.restype = ctypes.c_size_t
+    lib.lg_densify_scratch_bytes.argtypes = [i]
+    lib.lg_densify_plan.restype = i
+    lib.lg_densify_plan.argtypes = [i, _P, _P, _P, _P, f, f, f, f, f, _P, _P, _P, _P, ctypes.c_size_t, _P]
+    lib.lg_densify_apply.restype = i
+    lib.lg_densify_apply.argtypes = [i, i, i] + [_P] * 9 + [i, _P]
+    lib.lg_densify_stats.restype = i
+    lib.lg_densify_stats.argtypes = [i] + [_P] * 6
+    lib.lg_reset_opacity.restype = i
+    lib.lg_reset_opacity.argtypes = [i] + [_P] * 4
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

@@ -3,21 +3,40 @@
 The reference is single-process, single-GPU and steps Adam after every single view (LG/train.py:105-119,278-288);
 it has no distributed code at all.  The path shards naturally by camera view: every rank holds a
 replica of the Gaussian parameters, renders its slice of the step's view batch (views r, r+N, ...), accumulates the
-parameter gradients in ONE flat fp32 bucket (59 floats = 236 B per Gaussian: xyz 3, f_dc 3, f_rest 45, opacity 1,
-scaling 3, rotation 4 — the six Adam groups of LG/scene/gaussian_model.py:178-211), and the only exchange step is a
-single in-place all-reduce of that bucket before an identical Adam update on every rank.  N = 1 with one view per
-step reproduces the reference iteration.
+parameter gradients in ONE flat fp32 bucket (59 floats = 236 B per Gaussian at SH degree 3), and the only exchange
+step is a single in-place all-reduce of that bucket before an identical Adam update on every rank.  N = 1 with one
+view per step reproduces the reference iteration.  Every `densification_interval` steps the densification statistics
+are all-reduced too (sum, sum, max) and `densify_and_prune` runs identically on every rank with unit normals drawn
+from a generator all ranks seed alike.
 
-`render_fn` / `loss_fn` are injectable so the sharding / bucketing / optimiser logic can be tested on CPU with the
-gloo backend (tests/test_dp_cpu.py); the defaults use the B200-native rasterizer and fused DWT loss.
+Storage: raw (pre-activation) parameters in one flat, field-major buffer — xyz 3 | SH 3M | opacity 1 | scaling 3 |
+rotation 4, every field a contiguous (P, w) slab.  A Gaussian's SH row is f_dc followed by f_rest, i.e. exactly the
+(P, M, 3) `shs` tensor the rasterizer takes (the reference concatenates its two parameters per call,
+LG/scene/gaussian_model.py:121-124); the six Adam groups of the reference (:178-211) remain addressable through
+`field("f_dc")` / `field("f_rest")` and keep their own learning rates (lg_adam_step_split).
+
+On CUDA the whole step runs in fused kernels: `lg_activate_forward` (sigmoid / exp / normalize), the rasterizer, the
+fused image loss, a backward whose preprocess kernel applies the activation chain rule and adds straight into the
+flat bucket (`GradSinks(raw_rot_norm=...)`), `lg_densify_stats`, `lg_adam_step_split`, `lg_densify_plan/apply`.
+`render_fn` / `loss_fn` / `densify_fn` are injectable so the sharding / bucketing / optimiser / densification
+protocol can be tested on CPU with the gloo backend (tests/test_host_cpu.py).
 """
+import ctypes
 import math
-from typing import Callable, List, NamedTuple, Optional, Sequence
+from typing import Callable, NamedTuple, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
-FIELDS = (("xyz", 3), ("f_dc", 3), ("f_rest", 45), ("opacity", 1), ("scaling", 3), ("rotation", 4))
+GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")  # the reference's Adam groups
+
+
+def fields_for(sh_degree):
+    """storage slabs of the flat buffer: (name, floats per Gaussian)"""
+    return (("xyz", 3), ("shs", 3 * (sh_degree + 1) ** 2), ("opacity", 1), ("scaling", 3), ("rotation", 4))
+
+
+FIELDS = fields_for(3)
 FLOATS_PER_GAUSSIAN = sum(w for _, w in FIELDS)  # 59
 
 
@@ -34,26 +53,56 @@ class AdamConfig(NamedTuple):
     eps: float = 1e-15
 
 
+class DensifyConfig(NamedTuple):
+    """LG/arguments/__init__.py:91-97 and the constants of LG/train.py:265-276"""
+    densify_from_iter: int = 500
+    densify_until_iter: int = 15_000
+    densification_interval: int = 100
+    opacity_reset_interval: int = 3000
+    densify_grad_threshold: float = 0.0002
+    min_opacity: float = 0.005
+    percent_dense: float = 0.01
+    size_threshold: float = 20.0  # used once iteration > opacity_reset_interval (train.py:272)
+    cameras_extent: float = 1.0
+
+
 class FlatGaussians:
-    """Raw (pre-activation) Gaussian parameters in one flat (59, P) fp32 buffer, field-major so that every field is
-    a contiguous slab (coalesced for the activation / Adam passes and a single NCCL message for the gradients)."""
+    """Raw Gaussian parameters, their gradient bucket and Adam moments in flat field-major fp32 buffers."""
 
     def __init__(self, P, device, sh_degree=3):
-        self.P, self.device, self.sh_degree = int(P), device, sh_degree
-        self.data = torch.zeros(FLOATS_PER_GAUSSIAN * self.P, dtype=torch.float32, device=device)
-        self.grad = torch.zeros_like(self.data)
-        self.exp_avg = torch.zeros_like(self.data)
-        self.exp_avg_sq = torch.zeros_like(self.data)
+        self.device, self.sh_degree = device, sh_degree
+        self.fields = fields_for(sh_degree)
+        self.floats = sum(w for _, w in self.fields)
+        self.M = (sh_degree + 1) ** 2
         self.step_count = 0
-        self._slices = {}
-        off = 0
-        for name, w in FIELDS:
-            self._slices[name] = (off * self.P, (off + w) * self.P, w)
-            off += w
+        self._install(int(P), *(torch.zeros(self.floats * int(P), dtype=torch.float32, device=device) for _ in range(3)))
 
-    def field(self, name, buf=None):
+    def _install(self, P, data, exp_avg, exp_avg_sq):
+        self.P = P
+        self.data, self.exp_avg, self.exp_avg_sq = data, exp_avg, exp_avg_sq
+        self.grad = torch.zeros_like(data)
+        self._slices, off = {}, 0
+        for name, w in self.fields:
+            self._slices[name] = (off * P, (off + w) * P, w)
+            off += w
+        self._act = None
+
+    def replace(self, P_new, data, exp_avg, exp_avg_sq):
+        """install the buffers a densification produced (every per-Gaussian side array is re-created by the caller)"""
+        assert data.numel() == exp_avg.numel() == exp_avg_sq.numel() == self.floats * P_new
+        self._install(int(P_new), data, exp_avg, exp_avg_sq)
+
+    def slab(self, name, buf=None):
         a, b, w = self._slices[name]
         return (self.data if buf is None else buf)[a:b].view(self.P, w)
+
+    def field(self, name, buf=None):
+        """(P, w) view of one of the reference's six parameter groups (f_dc / f_rest are column ranges of the SH slab)"""
+        if name == "f_dc":
+            return self.slab("shs", buf)[:, :3]
+        if name == "f_rest":
+            return self.slab("shs", buf)[:, 3:]
+        return self.slab(name, buf)
 
     @classmethod
     def from_scene(cls, scene, device):
@@ -61,55 +110,83 @@ class FlatGaussians:
         activations in LG/scene/gaussian_model.py:36-50)."""
         g = cls(scene.means3D.shape[0], device, scene.sh_degree)
         t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device)
-        g.field("xyz").copy_(t(scene.means3D))
-        g.field("f_dc").copy_(t(scene.shs[:, 0, :]))
-        g.field("f_rest").copy_(t(scene.shs[:, 1:, :]).reshape(g.P, 45))
+        g.slab("xyz").copy_(t(scene.means3D))
+        g.slab("shs").copy_(t(scene.shs).reshape(g.P, -1))
         op = t(scene.opacities).clamp(1e-6, 1 - 1e-6)
-        g.field("opacity").copy_(torch.log(op / (1 - op)))
-        g.field("scaling").copy_(torch.log(t(scene.scales)))
-        g.field("rotation").copy_(t(scene.rotations))
+        g.slab("opacity").copy_(torch.log(op / (1 - op)))
+        g.slab("scaling").copy_(torch.log(t(scene.scales)))
+        g.slab("rotation").copy_(t(scene.rotations))
         return g
 
+    # ---- generic autograd path (CPU tests, custom render functions)
     def leaves(self):
-        """Fresh autograd leaves viewing the flat buffer; their .grad is routed into the flat gradient bucket."""
-        out = {}
-        for name, _ in FIELDS:
-            leaf = self.field(name).detach().requires_grad_(True)
-            out[name] = leaf
-        return out
+        """Fresh autograd leaves viewing the flat buffer; their .grad is added into the flat gradient bucket."""
+        return {name: self.slab(name).detach().requires_grad_(True) for name, _ in self.fields}
 
     def accumulate(self, leaves):
-        for name, _ in FIELDS:
+        for name, _ in self.fields:
             g = leaves[name].grad
             if g is not None:
-                self.field(name, self.grad).add_(g)
+                self.slab(name, self.grad).add_(g)
 
     def activated(self, leaves):
         """get_xyz / get_features / get_opacity / get_scaling / get_rotation of LG/scene/gaussian_model.py:102-130"""
-        shs = torch.cat([leaves["f_dc"].view(self.P, 1, 3), leaves["f_rest"].view(self.P, 15, 3)], dim=1)
-        return dict(means3D=leaves["xyz"], shs=shs, opacities=torch.sigmoid(leaves["opacity"]),
-                    scales=torch.exp(leaves["scaling"]), rotations=torch.nn.functional.normalize(leaves["rotation"]))
+        return dict(means3D=leaves["xyz"], shs=leaves["shs"].view(self.P, self.M, 3),
+                    opacities=torch.sigmoid(leaves["opacity"]), scales=torch.exp(leaves["scaling"]),
+                    rotations=torch.nn.functional.normalize(leaves["rotation"]))
+
+    # ---- fused CUDA path
+    def activate(self):
+        """one launch: activated opacity / scale / rotation (+ |raw rotation| for the backward chain rule); xyz and
+        the SH slab are used in place.  No autograd graph: gradients flow through GradSinks."""
+        from . import _lib
+        if not self.data.is_cuda:
+            raise RuntimeError("FlatGaussians.activate: the fused path needs CUDA buffers (no CPU fallback)")
+        if self._act is None or self._act["opacities"].shape[0] != self.P:
+            new = lambda w: torch.empty((self.P, w), dtype=torch.float32, device=self.device)
+            self._act = dict(opacities=new(1), scales=new(3), rotations=new(4),
+                             rot_norm=torch.empty(self.P, dtype=torch.float32, device=self.device))
+        a = self._act
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.lg_activate_forward(self.P, _lib.ptr(self.slab("opacity")), _lib.ptr(self.slab("scaling")),
+                                              _lib.ptr(self.slab("rotation")), _lib.ptr(a["opacities"]),
+                                              _lib.ptr(a["scales"]), _lib.ptr(a["rotations"]), _lib.ptr(a["rot_norm"]),
+                                              _lib.stream_ptr(self.device))
+        _lib.check(rc, RuntimeError)
+        return dict(means3D=self.slab("xyz"), shs=self.slab("shs").view(self.P, self.M, 3), opacities=a["opacities"],
+                    scales=a["scales"], rotations=a["rotations"], rot_norm=a["rot_norm"])
+
+    def grad_sinks(self, rot_norm, accumulate):
+        from diff_gaussian_rasterization import GradSinks
+        s = lambda n: self.slab(n, self.grad)
+        return GradSinks(s("xyz"), s("shs").view(self.P, self.M, 3), s("opacity"), s("scaling"), s("rotation"),
+                         accumulate=accumulate, raw_rot_norm=rot_norm)
 
     def adam_step(self, cfg: AdamConfig, grad_scale: float = 1.0):
-        """torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), one learning rate per field slab;
+        """torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), the reference's six learning rates;
         identical on every rank because the reduced gradient bucket is identical.  CUDA buffers take ONE fused
-        kernel launch (lg_adam_step, 28 B of traffic per element); the slab-by-slab torch expression below is the
-        host-side statement of the same update, used by the CPU (gloo) tests of the trainer logic."""
+        kernel launch (lg_adam_step_split, 28 B of traffic per element); the group-by-group torch expression below is
+        the host-side statement of the same update, used by the CPU (gloo) tests of the trainer logic."""
         self.step_count += 1
         b1, b2 = cfg.beta1, cfg.beta2
         lrs = dict(xyz=cfg.lr_xyz, f_dc=cfg.lr_f_dc, f_rest=cfg.lr_f_rest, opacity=cfg.lr_opacity,
                    scaling=cfg.lr_scaling, rotation=cfg.lr_rotation)
+        if self.P == 0:
+            return
         if self.data.is_cuda:
-            import ctypes
             from . import _lib
-            n_seg = len(FIELDS)
-            ends = (ctypes.c_longlong * n_seg)(*[self._slices[name][1] for name, _ in FIELDS])
-            lr_arr = (ctypes.c_float * n_seg)(*[float(lrs[name]) for name, _ in FIELDS])
+            n_seg = len(self.fields)
+            names = [name for name, _ in self.fields]
+            ends = (ctypes.c_longlong * n_seg)(*[self._slices[n][1] for n in names])
+            lr_a = (ctypes.c_float * n_seg)(*[float(lrs["f_dc" if n == "shs" else n]) for n in names])
+            lr_b = (ctypes.c_float * n_seg)(*[float(lrs["f_rest" if n == "shs" else n]) for n in names])
+            width = (ctypes.c_int * n_seg)(*[self._slices[n][2] if n == "shs" else 1 for n in names])
+            split = (ctypes.c_int * n_seg)(*[3 if n == "shs" else 0 for n in names])
             with torch.cuda.device(self.data.device):
-                rc = _lib.lib.lg_adam_step(self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                           self.exp_avg_sq.data_ptr(), self.data.numel(), n_seg, ends, lr_arr, b1, b2,
-                                           cfg.eps, self.step_count, float(grad_scale),
-                                           _lib.stream_ptr(self.data.device))
+                rc = _lib.lib.lg_adam_step_split(self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                                 self.exp_avg_sq.data_ptr(), self.data.numel(), n_seg, ends, lr_a, lr_b,
+                                                 width, split, b1, b2, cfg.eps, self.step_count, float(grad_scale),
+                                                 _lib.stream_ptr(self.data.device))
             _lib.check(rc, RuntimeError)
             return
         bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
@@ -117,10 +194,9 @@ class FlatGaussians:
             self.grad.mul_(grad_scale)
         self.exp_avg.mul_(b1).add_(self.grad, alpha=1 - b1)
         self.exp_avg_sq.mul_(b2).addcmul_(self.grad, self.grad, value=1 - b2)
-        for name, _ in FIELDS:
-            a, b, _w = self._slices[name]
-            denom = (self.exp_avg_sq[a:b].sqrt() / math.sqrt(bc2)).add_(cfg.eps)
-            self.data[a:b].addcdiv_(self.exp_avg[a:b], denom, value=-lrs[name] / bc1)
+        for name in GROUPS:
+            denom = (self.field(name, self.exp_avg_sq).sqrt() / math.sqrt(bc2)).add_(cfg.eps)
+            self.field(name).addcdiv_(self.field(name, self.exp_avg), denom, value=-lrs[name] / bc1)
 
     def checksum(self):
         return self.data.double().sum()
@@ -131,19 +207,36 @@ def views_of_rank(num_views, rank, world):
     return list(range(rank, num_views, world))
 
 
-def default_render(act, cam, bg, sh_degree=3, antialiasing=False):
-    """One view through the B200-native operator, mirroring LG/gaussian_renderer/__init__.py:18-128."""
-    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
-    rs = GaussianRasterizationSettings(
+def _raster_settings(cam, bg, sh_degree, antialiasing):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    return GaussianRasterizationSettings(
         image_height=cam["H"], image_width=cam["W"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg,
         scale_modifier=1.0, viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], sh_degree=sh_degree,
         campos=cam["campos"], prefiltered=False, debug=False, antialiasing=antialiasing)
+
+
+def default_render(act, cam, bg, sh_degree=3, antialiasing=False):
+    """One view through the B200-native operator, mirroring LG/gaussian_renderer/__init__.py:18-128 (autograd path:
+    `act` holds differentiable activated parameters)."""
+    from diff_gaussian_rasterization import GaussianRasterizer
     means2D = torch.zeros_like(act["means3D"], requires_grad=True)
-    color, radii, invdepth = GaussianRasterizer(rs)(means3D=act["means3D"], means2D=means2D, shs=act["shs"],
-                                                     colors_precomp=None, opacities=act["opacities"],
-                                                     scales=act["scales"], rotations=act["rotations"],
-                                                     cov3D_precomp=None)
-    return color.clamp(0, 1), radii
+    color, radii, invdepth = GaussianRasterizer(_raster_settings(cam, bg, sh_degree, antialiasing))(
+        means3D=act["means3D"], means2D=means2D, shs=act["shs"], colors_precomp=None, opacities=act["opacities"],
+        scales=act["scales"], rotations=act["rotations"], cov3D_precomp=None)
+    return color.clamp(0, 1), radii, means2D
+
+
+def fused_render(g: FlatGaussians, cam, bg, accumulate, antialiasing=False):
+    """One view of the fused path: raw parameters -> lg_activate_forward -> rasterizer; the backward adds the
+    RAW-parameter gradients into g.grad.  Returns (image, radii, means2D) like the reference's render()."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    act = g.activate()
+    means2D = torch.zeros((g.P, 3), dtype=torch.float32, device=g.device, requires_grad=True)
+    color, radii, invdepth = GaussianRasterizer(_raster_settings(cam, bg, g.sh_degree, antialiasing))(
+        means3D=act["means3D"], means2D=means2D, shs=act["shs"], colors_precomp=None, opacities=act["opacities"],
+        scales=act["scales"], rotations=act["rotations"], cov3D_precomp=None,
+        grad_sinks=g.grad_sinks(act["rot_norm"], accumulate))
+    return color.clamp(0, 1), radii, means2D
 
 
 def default_loss(image, gt, lambda_dssim=0.2, dwt_scale=1.0, patch_weight=0.1, cfg=None):
@@ -157,25 +250,69 @@ def default_loss(image, gt, lambda_dssim=0.2, dwt_scale=1.0, patch_weight=0.1, c
     return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ssim) + dwt_scale * dwt + patch_weight * patch
 
 
+def _default_densify(g, stats, cfg, max_screen_size, generator):
+    from . import densify
+    return densify.densify_and_prune(g, stats, cfg.densify_grad_threshold, cfg.min_opacity, cfg.cameras_extent,
+                                     max_screen_size, generator=generator, percent_dense=cfg.percent_dense)
+
+
 class ViewParallelTrainer:
     def __init__(self, gaussians: FlatGaussians, adam: AdamConfig = AdamConfig(),
-                 render_fn: Callable = default_render, loss_fn: Callable = default_loss,
-                 group: Optional[dist.ProcessGroup] = None):
+                 render_fn: Optional[Callable] = None, loss_fn: Callable = default_loss,
+                 group: Optional[dist.ProcessGroup] = None, densify: Optional[DensifyConfig] = None,
+                 densify_fn: Optional[Callable] = None, stats_fn: Optional[Callable] = None,
+                 reset_opacity_fn: Optional[Callable] = None, seed: int = 0):
+        """render_fn=None selects the fused CUDA path (`fused_render`); a custom render_fn(act, cam, bg) ->
+        (image, radii[, viewspace_points]) runs through autograd leaves.  densify=None disables density control."""
         self.g, self.adam, self.render_fn, self.loss_fn, self.group = gaussians, adam, render_fn, loss_fn, group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
+        self.densify_cfg = densify
+        self.densify_fn = densify_fn or _default_densify
+        self.stats_fn, self.reset_opacity_fn = stats_fn, reset_opacity_fn
+        self.iteration = 0
+        self.stats = None
+        # every rank seeds this generator alike: the split samples are identical on all replicas (SURVEY.md §8e)
+        self.generator = torch.Generator(device=gaussians.device).manual_seed(seed)
+        if densify is not None:
+            self._new_stats()
+
+    def _new_stats(self):
+        from .densify import DensifyStats
+        self.stats = DensifyStats(self.g.P, self.g.device)
+
+    def _add_stats(self, viewspace, radii):
+        if self.stats is None or viewspace is None or viewspace.grad is None:
+            return
+        if self.stats_fn is not None:
+            self.stats_fn(self.stats, viewspace.grad, radii)
+        else:
+            from . import densify
+            densify.add_densification_stats(self.stats, viewspace.grad, radii)
 
     def accumulate_views(self, cams: Sequence[dict], gts: Sequence[torch.Tensor], bg: torch.Tensor):
         """forward + backward of this rank's views, gradients summed into the flat bucket; returns the local loss sum"""
-        self.g.grad.zero_()
         total = torch.zeros((), dtype=torch.float32, device=self.g.device)
-        for v in views_of_rank(len(cams), self.rank, self.world):
-            leaves = self.g.leaves()
-            image, _radii = self.render_fn(self.g.activated(leaves), cams[v], bg)
+        mine = views_of_rank(len(cams), self.rank, self.world)
+        fused = self.render_fn is None
+        if not fused or not mine:
+            self.g.grad.zero_()
+        for k, v in enumerate(mine):
+            if fused:  # the first view of the step overwrites the bucket: no zero-fill pass
+                image, radii, viewspace = fused_render(self.g, cams[v], bg, accumulate=k > 0)
+                leaves = None
+            else:
+                leaves = self.g.leaves()
+                out = self.render_fn(self.g.activated(leaves), cams[v], bg)
+                image, radii = out[0], out[1]
+                viewspace = out[2] if len(out) > 2 else None
             loss = self.loss_fn(image, gts[v])
             loss.backward()
-            self.g.accumulate(leaves)
+            if leaves is not None:
+                self.g.accumulate(leaves)
+            if self.densify_cfg is not None and self.iteration < self.densify_cfg.densify_until_iter:
+                self._add_stats(viewspace, radii)
             total += loss.detach()
         return total
 
@@ -185,16 +322,47 @@ class ViewParallelTrainer:
         if self.distributed and self.world > 1:
             dist.all_reduce(self.g.grad, op=dist.ReduceOp.SUM, group=self.group)
 
+    def reduce_stats(self):
+        """densification statistics of the ranks' view slices -> the statistics of the whole batch"""
+        if self.distributed and self.world > 1 and self.stats is not None:
+            dist.all_reduce(self.stats.xyz_gradient_accum, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.stats.denom, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.stats.max_radii2D, op=dist.ReduceOp.MAX, group=self.group)
+
+    def maybe_densify(self):
+        """the density-control schedule of LG/train.py:265-276, applied identically on every rank.  Returns True when
+        the Gaussian set was rebuilt (the reference's optimizer then has nothing to step on: the new Parameters have
+        no .grad, LG/scene/gaussian_model.py:331-409 — the Adam update of this iteration is skipped)."""
+        c, it = self.densify_cfg, self.iteration
+        if c is None or it >= c.densify_until_iter:
+            return False
+        rebuilt = False
+        if it > c.densify_from_iter and it % c.densification_interval == 0:
+            self.reduce_stats()
+            mss = c.size_threshold if it > c.opacity_reset_interval else None
+            self.densify_fn(self.g, self.stats, c, mss, self.generator)
+            self._new_stats()
+            rebuilt = True
+        if it % c.opacity_reset_interval == 0:
+            if self.reset_opacity_fn is not None:
+                self.reset_opacity_fn(self.g)
+            else:
+                from . import densify
+                densify.reset_opacity(self.g)
+        return rebuilt
+
     def step(self, cams, gts, bg, num_views_scale=True):
+        self.iteration += 1
         loss = self.accumulate_views(cams, gts, bg)
-        self.reduce_gradients()
-        scale = 1.0 / len(cams) if (num_views_scale and len(cams) > 1) else 1.0  # mean over the view batch
-        self.g.adam_step(self.adam, grad_scale=scale)
+        if not self.maybe_densify():
+            self.reduce_gradients()
+            scale = 1.0 / len(cams) if (num_views_scale and len(cams) > 1) else 1.0  # mean over the view batch
+            self.g.adam_step(self.adam, grad_scale=scale)
         return loss
 
     def replicas_in_sync(self):
-        """parameter checksum min == max over ranks"""
-        c = self.g.checksum().reshape(1)
+        """parameter count and checksum min == max over ranks"""
+        c = torch.stack([self.g.checksum(), torch.tensor(float(self.g.P), dtype=torch.float64, device=self.g.device)])
         if not (self.distributed and self.world > 1):
             return True
         lo, hi = c.clone(), c.clone()

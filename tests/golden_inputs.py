@@ -76,3 +76,48 @@ def knn_points(P=6000, seed=5):
     pts = rng.normal(0, 1.0, (P, 3)).astype(np.float32)
     pts[: P // 50] = pts[P // 50: 2 * (P // 50)]  # exact duplicates -> zero distances, like COLMAP clouds have
     return pts
+
+
+DENSIFY_CASES = {
+    # name: (P, seed, extent, max_grad, min_opacity, max_screen_size or 0 for None, log-scale centre)
+    "mixed": (1200, 21, 4.0, 0.0002, 0.005, 0, np.log(0.04)),
+    "size_threshold": (1000, 22, 4.0, 0.0002, 0.005, 20, np.log(0.12)),
+    "nothing_selected": (600, 23, 4.0, 1.0e3, 0.005, 0, np.log(0.04)),
+    "identity": (300, 24, 4.0, 1.0e3, 0.0, 0, np.log(0.04)),
+    "all_split": (400, 25, 1.0, 0.0, 0.005, 0, np.log(0.2)),
+}
+PERCENT_DENSE = 0.01  # LG/arguments/__init__.py:91
+
+
+def densify_case(name):
+    """Raw Gaussian parameters + Adam moments + densification statistics for one densify_and_prune call
+    (LG/scene/gaussian_model.py:456-476).  Everything in the reference's own tensor shapes."""
+    P, seed, extent, max_grad, min_opacity, mss, ls = DENSIFY_CASES[name]
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    d = {"xyz": f32(rng.normal(0, 1.0, (P, 3))), "f_dc": f32(rng.normal(0, 1.0, (P, 1, 3))),
+         "f_rest": f32(rng.normal(0, 0.15, (P, 15, 3))), "opacity": f32(rng.normal(-2.0, 3.0, (P, 1))),
+         "scaling": f32(rng.normal(ls, 0.7, (P, 3))), "rotation": f32(rng.normal(0, 1.0, (P, 4)))}
+    for k in list(d):
+        d["exp_avg/" + k] = f32(rng.normal(0, 1e-3, d[k].shape))
+        d["exp_avg_sq/" + k] = f32(rng.random(d[k].shape) * 1e-6)
+    denom = rng.integers(0, 4, (P, 1)).astype(np.float32)  # zeros give 0/0 = nan -> 0 (gaussian_model.py:458)
+    accum = f32(rng.random((P, 1)) * 0.0012 * np.maximum(denom, 1.0))
+    accum[denom == 0] = 0.0
+    d["xyz_gradient_accum"], d["denom"] = accum, denom
+    d["max_radii2D"] = f32(rng.integers(0, 60, P))
+    d["radii"] = rng.integers(0, 40, P).astype(np.int32)
+    cfg = dict(extent=extent, max_grad=max_grad, min_opacity=min_opacity, max_screen_size=(mss or None),
+               percent_dense=PERCENT_DENSE, seed=seed)
+    return d, cfg
+
+
+def stats_case(P=1000, seed=31):
+    """add_densification_stats + max_radii2D update inputs (LG/train.py:268-269, gaussian_model.py:478-480)"""
+    rng = np.random.default_rng(seed)
+    radii = (rng.integers(0, 50, P) * (rng.random(P) < 0.6)).astype(np.int32)
+    return {"grad2D": rng.normal(0, 1e-3, (P, 3)).astype(np.float32), "radii": radii,
+            "xyz_gradient_accum": (rng.random((P, 1)) * 1e-2).astype(np.float32),
+            "denom": rng.integers(0, 9, (P, 1)).astype(np.float32),
+            "max_radii2D": rng.integers(0, 50, P).astype(np.float32),
+            "opacity": rng.normal(-2.0, 3.0, (P, 1)).astype(np.float32)}

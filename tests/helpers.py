@@ -131,3 +131,55 @@ def rel_err(a, b):
     """max |a-b| / max(|b|_inf, eps): the per-tensor relative error of SURVEY §8c."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+# ---------------------------------------------------------------- flat Gaussian buffer <-> reference-shaped groups
+DENSIFY_GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+
+
+def flat_from_groups(dp, d, device, prefix=""):
+    """dp.FlatGaussians filled from reference-shaped arrays (tests/golden_inputs.densify_case)"""
+    P = d[prefix + "xyz"].shape[0]
+    g = dp.FlatGaussians(P, torch.device(device))
+    for buf, pre in ((g.data, ""), (g.exp_avg, "exp_avg/"), (g.exp_avg_sq, "exp_avg_sq/")):
+        for k in DENSIFY_GROUPS:
+            g.field(k, buf).copy_(torch.as_tensor(d[prefix + pre + k]).reshape(P, -1))
+    return g
+
+
+def groups_from_flat(g, buf=None):
+    shapes = {"xyz": (3,), "f_dc": (1, 3), "f_rest": (g.M - 1, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
+    return {k: g.field(k, buf).detach().cpu().reshape(g.P, *shapes[k]).clone() for k in DENSIFY_GROUPS}
+
+
+def oracle_densify_fn(g, stats, cfg, max_screen_size, generator):
+    """densify_fn for dp.ViewParallelTrainer on CPU tensors, backed by the oracle (tests only)"""
+    from oracle import densify_oracle
+    p, m, v = groups_from_flat(g), groups_from_flat(g, g.exp_avg), groups_from_flat(g, g.exp_avg_sq)
+    _, _, _, parents = densify_oracle.plan(p, stats.xyz_gradient_accum, stats.denom, cfg.densify_grad_threshold,
+                                           cfg.min_opacity, cfg.cameras_extent, max_screen_size, cfg.percent_dense)
+    eps = torch.randn((2 * parents.numel(), 3), generator=generator)
+    np_, nm, nv, counts = densify_oracle.densify_and_prune(p, m, v, stats.xyz_gradient_accum, stats.denom, eps,
+                                                           cfg.densify_grad_threshold, cfg.min_opacity,
+                                                           cfg.cameras_extent, max_screen_size, cfg.percent_dense)
+    P_new = counts["P"]
+    bufs = [torch.zeros(g.floats * P_new) for _ in range(3)]
+    g.replace(P_new, *bufs)
+    for buf, src in ((g.data, np_), (g.exp_avg, nm), (g.exp_avg_sq, nv)):
+        for k in DENSIFY_GROUPS:
+            g.field(k, buf).copy_(src[k].reshape(P_new, -1))
+    return counts
+
+
+def oracle_stats_fn(stats, grad2D, radii):
+    from oracle import densify_oracle
+    a, d, m = densify_oracle.add_densification_stats(stats.xyz_gradient_accum, stats.denom, stats.max_radii2D, grad2D,
+                                                     radii)
+    stats.xyz_gradient_accum, stats.denom, stats.max_radii2D = a, d, m
+
+
+def oracle_reset_opacity_fn(g):
+    from oracle import densify_oracle
+    g.slab("opacity").copy_(densify_oracle.reset_opacity(g.slab("opacity")))
+    g.slab("opacity", g.exp_avg).zero_()
+    g.slab("opacity", g.exp_avg_sq).zero_()

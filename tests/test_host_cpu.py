@@ -92,7 +92,10 @@ def test_scene_generators_are_deterministic_and_sane():
 _DP_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(%(root)r, "sparse-view-3dgs-pack_b200"))
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
 from lgdwt_b200 import dp
+import helpers
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 torch.manual_seed(0)
@@ -103,24 +106,36 @@ def make():
     g.data.copy_(torch.randn(g.data.shape, generator=gen) * 0.1)
     return g
 def render(act, cam, bg):   # differentiable stand-in for the rasterizer: every parameter group takes part
-    s = (act["means3D"].sum(1) + act["shs"].sum((1, 2)) + act["opacities"].sum(1) + act["scales"].sum(1) + act["rotations"].sum(1))
-    return (s[:, None] * cam["w"][None, :]).sum(0).view(1, 1, -1), None
+    P = act["means3D"].shape[0]
+    vsp = torch.zeros((P, 3), requires_grad=True)   # "screen-space points": their .grad feeds the densification stats
+    s = (act["means3D"].sum(1) + act["shs"].sum((1, 2)) + act["opacities"].sum(1) + act["scales"].sum(1)
+         + act["rotations"].sum(1) + (vsp * cam["k"]).sum(1))
+    radii = ((torch.arange(P) + cam["v"]) %% 3 != 0).int() * 5   # every view sees a different two thirds
+    return (s[:, None] * cam["w"][None, :]).sum(0).view(1, 1, -1), radii, vsp
 loss = lambda img, gt: ((img - gt) ** 2).mean()
-cams = [{"w": torch.linspace(0.1 * (v + 1), 1.0, 16)} for v in range(6)]
+cams = [{"w": torch.linspace(0.1 * (v + 1), 1.0, 16), "k": 1e-3 * (v + 1), "v": v} for v in range(6)]
+dcfg = dp.DensifyConfig(densify_from_iter=1, densify_until_iter=100, densification_interval=2, opacity_reset_interval=3,
+                        densify_grad_threshold=1e-4, cameras_extent=4.0)
+kw = dict(render_fn=render, loss_fn=loss, densify=dcfg, densify_fn=helpers.oracle_densify_fn,
+          stats_fn=helpers.oracle_stats_fn, reset_opacity_fn=helpers.oracle_reset_opacity_fn, seed=5)
 gts = [torch.full((1, 1, 16), 0.3 * v) for v in range(6)]
 g = make()
-tr = dp.ViewParallelTrainer(g, render_fn=render, loss_fn=loss)
+tr = dp.ViewParallelTrainer(g, **kw)
 assert dp.views_of_rank(6, rank, world) == list(range(rank, 6, world))
-for _ in range(3):
+sizes = []
+for _ in range(5):    # iterations 2 and 4 densify (statistics all-reduced first), iteration 3 resets the opacities
     tr.step(cams, gts, None)
-assert tr.replicas_in_sync()
+    sizes.append(g.P)
+    assert tr.replicas_in_sync()
+assert sizes[1] != P and sizes[0] == P, sizes
 if rank == 0:   # single-process accumulation over the same 6 views must give the same parameters
     dist_backup = dist.is_initialized
     g1 = make()
-    t1 = dp.ViewParallelTrainer(g1, render_fn=render, loss_fn=loss)
+    t1 = dp.ViewParallelTrainer(g1, **kw)
     t1.distributed, t1.rank, t1.world = False, 0, 1
-    for _ in range(3):
+    for _ in range(5):
         t1.step(cams, gts, None)
+    assert g1.P == g.P, (g1.P, g.P)
     err = (g1.data - g.data).abs().max().item()
     assert err < 1e-6, err
     print("DP_OK", err)
@@ -145,16 +160,16 @@ def test_flat_gaussians_adam_matches_torch_optim():
     g = dp.FlatGaussians(10, torch.device("cpu"))
     g.data.copy_(torch.randn(g.data.shape, generator=torch.Generator().manual_seed(2)))
     cfg = dp.AdamConfig()
-    ref_params = {n: g.field(n).clone().requires_grad_(True) for n, _ in dp.FIELDS}
+    ref_params = {n: g.field(n).clone().requires_grad_(True) for n in dp.GROUPS}
     lrs = dict(xyz=cfg.lr_xyz, f_dc=cfg.lr_f_dc, f_rest=cfg.lr_f_rest, opacity=cfg.lr_opacity, scaling=cfg.lr_scaling,
                rotation=cfg.lr_rotation)
-    opt = torch.optim.Adam([{"params": [ref_params[n]], "lr": lrs[n]} for n, _ in dp.FIELDS], lr=0.0, eps=1e-15)
+    opt = torch.optim.Adam([{"params": [ref_params[n]], "lr": lrs[n]} for n in dp.GROUPS], lr=0.0, eps=1e-15)
     for it in range(4):
         grads = torch.randn(g.data.shape, generator=torch.Generator().manual_seed(10 + it))
         g.grad.copy_(grads)
-        for n, _ in dp.FIELDS:
+        for n in dp.GROUPS:
             ref_params[n].grad = g.field(n, grads).clone()
         opt.step()
         g.adam_step(cfg)
-    for n, _ in dp.FIELDS:
+    for n in dp.GROUPS:
         torch.testing.assert_close(g.field(n), ref_params[n].detach(), rtol=1e-5, atol=1e-7)

@@ -385,24 +385,24 @@ def test_dp_trainer_single_gpu_step_changes_parameters_like_reference_iteration(
 
 
 def test_fused_adam_matches_torch_optim_adam():
-    """lg_adam_step on the flat (59 x P) buffer == torch.optim.Adam with one param group per field (the reference's
+    """lg_adam_step_split on the flat (59 x P) buffer == torch.optim.Adam with one param group per field (the reference's
     optimiser set-up, LG/scene/gaussian_model.py:178-211), over several steps, plus the folded 1/views gradient scale."""
     from lgdwt_b200 import dp
     P = 1237
     g = dp.FlatGaussians(P, torch.device(dev))
     g.data.copy_(torch.randn(g.data.shape, generator=torch.Generator().manual_seed(2)).to(dev))
     cfg = dp.AdamConfig()
-    ref_params = {n: g.field(n).clone().requires_grad_(True) for n, _ in dp.FIELDS}
+    ref_params = {n: g.field(n).clone().requires_grad_(True) for n in dp.GROUPS}
     lrs = dict(xyz=cfg.lr_xyz, f_dc=cfg.lr_f_dc, f_rest=cfg.lr_f_rest, opacity=cfg.lr_opacity, scaling=cfg.lr_scaling,
                rotation=cfg.lr_rotation)
-    opt = torch.optim.Adam([{"params": [ref_params[n]], "lr": lrs[n]} for n, _ in dp.FIELDS], lr=0.0, eps=1e-15)
+    opt = torch.optim.Adam([{"params": [ref_params[n]], "lr": lrs[n]} for n in dp.GROUPS], lr=0.0, eps=1e-15)
     for it in range(5):
         grads = torch.randn(g.data.shape, generator=torch.Generator().manual_seed(10 + it)).to(dev)
         scale = 0.25 if it == 3 else 1.0
         g.grad.copy_(grads)
-        for n, _ in dp.FIELDS:
+        for n in dp.GROUPS:
             ref_params[n].grad = (g.field(n, grads) * scale).clone()
         opt.step()
         g.adam_step(cfg, grad_scale=scale)
-    for n, _ in dp.FIELDS:
+    for n in dp.GROUPS:
         torch.testing.assert_close(g.field(n), ref_params[n].detach(), rtol=2e-5, atol=1e-7)

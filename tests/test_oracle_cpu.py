@@ -153,3 +153,44 @@ def test_haar_level_closed_form():
     # orthonormal transform: energy is preserved for even sizes
     e = (LL ** 2).sum() + (LH ** 2).sum() + (HL ** 2).sum() + (HH ** 2).sum()
     torch.testing.assert_close(e, (x ** 2).sum(), rtol=1e-5, atol=0)
+
+
+# ---------------------------------------------------------------- density control (oracle vs the reference class)
+@pytest.fixture(scope="module")
+def dgold():
+    return np.load(os.path.join(GOLD, "densify_reference.npz"))
+
+
+@pytest.mark.parametrize("name", list(golden_inputs.DENSIFY_CASES))
+def test_densify_oracle_matches_reference_gaussian_model(dgold, name):
+    from oracle import densify_oracle
+    d, cfg = golden_inputs.densify_case(name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    p = {k: t(d[k]) for k in densify_oracle.GROUPS}
+    m = {k: t(d["exp_avg/" + k]) for k in densify_oracle.GROUPS}
+    v = {k: t(d["exp_avg_sq/" + k]) for k in densify_oracle.GROUPS}
+    eps = t(dgold[name + "/eps"])
+    np_, nm, nv, counts = densify_oracle.densify_and_prune(
+        p, m, v, t(d["xyz_gradient_accum"]), t(d["denom"]), eps, cfg["max_grad"], cfg["min_opacity"], cfg["extent"],
+        cfg["max_screen_size"], cfg["percent_dense"])
+    assert counts["P"] == dgold[name + "/xyz"].shape[0]
+    assert 2 * counts["split_parents"] == eps.shape[0]
+    for k in densify_oracle.GROUPS:
+        np.testing.assert_allclose(np_[k].numpy(), dgold["%s/%s" % (name, k)], rtol=1e-6, atol=1e-6, err_msg=k)
+        np.testing.assert_array_equal(nm[k].numpy(), dgold["%s/exp_avg/%s" % (name, k)], err_msg=k)
+        np.testing.assert_array_equal(nv[k].numpy(), dgold["%s/exp_avg_sq/%s" % (name, k)], err_msg=k)
+    # densification_postfix: statistics restart from zero at the new size
+    assert dgold[name + "/denom"].shape[0] == counts["P"] and not dgold[name + "/denom"].any()
+    assert not dgold[name + "/max_radii2D"].any() and not dgold[name + "/xyz_gradient_accum"].any()
+
+
+def test_densify_stats_and_reset_opacity_oracle_match_reference(dgold):
+    from oracle import densify_oracle
+    s = golden_inputs.stats_case()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    a, dn, mr = densify_oracle.add_densification_stats(t(s["xyz_gradient_accum"]), t(s["denom"]), t(s["max_radii2D"]),
+                                                       t(s["grad2D"]), t(s["radii"]))
+    np.testing.assert_allclose(a.numpy(), dgold["stats/xyz_gradient_accum"].reshape(-1), rtol=1e-6, atol=0)
+    np.testing.assert_array_equal(dn.numpy(), dgold["stats/denom"].reshape(-1))
+    np.testing.assert_array_equal(mr.numpy(), dgold["stats/max_radii2D"])
+    np.testing.assert_allclose(densify_oracle.reset_opacity(t(s["opacity"])).numpy(), dgold["reset/opacity"], rtol=1e-6)

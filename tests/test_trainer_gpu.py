@@ -1,0 +1,185 @@
+"""GPU tier for the trainer-side kernels around the rasterizer: density control on the
+flat parameter buffer against the reference class's golden vectors and the CPU oracle, fused activations and their
+in-kernel chain rule against torch autograd, and the fused training step against the generic autograd step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs
+import helpers
+from lgdwt_b200 import densify, dp, scenes
+from oracle import densify_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+dev = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _stats_from(d):
+    st = densify.DensifyStats(d["denom"].shape[0], dev)
+    st.xyz_gradient_accum.copy_(T(d["xyz_gradient_accum"]).reshape(-1))
+    st.denom.copy_(T(d["denom"]).reshape(-1))
+    st.max_radii2D.copy_(T(d["max_radii2D"]).reshape(-1))
+    return st
+
+
+@pytest.mark.parametrize("name", list(golden_inputs.DENSIFY_CASES))
+def test_densify_and_prune_matches_reference_golden(name):
+    """same rows in the same order as GaussianModel.densify_and_prune, values to 1e-6, moments bit-equal"""
+    gold = np.load(os.path.join(GOLD, "densify_reference.npz"))
+    d, cfg = golden_inputs.densify_case(name)
+    g = helpers.flat_from_groups(dp, d, dev)
+    st = _stats_from(d)
+    counts = densify.densify_and_prune(g, st, cfg["max_grad"], cfg["min_opacity"], cfg["extent"],
+                                       cfg["max_screen_size"], percent_dense=cfg["percent_dense"],
+                                       eps=T(gold[name + "/eps"]))
+    assert counts["P"] == g.P == gold[name + "/xyz"].shape[0]
+    assert 2 * counts["split_parents"] == gold[name + "/eps"].shape[0]
+    p, m, v = helpers.groups_from_flat(g), helpers.groups_from_flat(g, g.exp_avg), helpers.groups_from_flat(g, g.exp_avg_sq)
+    for k in helpers.DENSIFY_GROUPS:
+        np.testing.assert_allclose(p[k].numpy(), gold["%s/%s" % (name, k)], rtol=1e-6, atol=1e-6, err_msg=k)
+        np.testing.assert_array_equal(m[k].numpy(), gold["%s/exp_avg/%s" % (name, k)], err_msg=k)
+        np.testing.assert_array_equal(v[k].numpy(), gold["%s/exp_avg_sq/%s" % (name, k)], err_msg=k)
+    assert st.denom.numel() == g.P and not st.denom.any() and not st.max_radii2D.any()
+    assert g.grad.numel() == g.data.numel() and not g.grad.any()
+
+
+def test_densify_matches_oracle_at_scale_and_edge_sizes():
+    """sizes around the 1024-row block of the plan kernels, more than one scan chunk, P = 0 and P = 1"""
+    for P, seed in ((0, 1), (1, 2), (1023, 3), (1025, 4), (300_000, 5), (1_100_000, 6)):
+        rng = np.random.default_rng(seed)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        d = {"xyz": f32(rng.normal(0, 1, (P, 3))), "f_dc": f32(rng.normal(0, 1, (P, 1, 3))),
+             "f_rest": f32(rng.normal(0, .1, (P, 15, 3))), "opacity": f32(rng.normal(-2, 3, (P, 1))),
+             "scaling": f32(rng.normal(np.log(0.04), 0.7, (P, 3))), "rotation": f32(rng.normal(0, 1, (P, 4)))}
+        for k in list(d):
+            d["exp_avg/" + k] = f32(rng.normal(0, 1e-3, d[k].shape))
+            d["exp_avg_sq/" + k] = f32(rng.random(d[k].shape) * 1e-6)
+        denom = rng.integers(0, 4, (P, 1)).astype(np.float32)
+        accum = f32(rng.random((P, 1)) * 0.0012 * np.maximum(denom, 1))
+        accum[denom == 0] = 0
+        g = helpers.flat_from_groups(dp, d, dev)
+        st = densify.DensifyStats(P, dev)
+        st.xyz_gradient_accum.copy_(T(accum).reshape(-1))
+        st.denom.copy_(T(denom).reshape(-1))
+        t = lambda a: torch.from_numpy(a)
+        pp = {k: t(d[k]) for k in densify_oracle.GROUPS}
+        _, _, _, parents = densify_oracle.plan(pp, t(accum), t(denom), 0.0002, 0.005, 4.0, 20, 0.01)
+        eps = torch.randn((2 * parents.numel(), 3), generator=torch.Generator().manual_seed(seed))
+        op, om, ov, oc = densify_oracle.densify_and_prune(
+            pp, {k: t(d["exp_avg/" + k]) for k in densify_oracle.GROUPS},
+            {k: t(d["exp_avg_sq/" + k]) for k in densify_oracle.GROUPS}, t(accum), t(denom), eps, 0.0002, 0.005, 4.0,
+            20, 0.01)
+        counts = densify.densify_and_prune(g, st, 0.0002, 0.005, 4.0, 20, eps=eps.to(dev))
+        assert counts == oc, (P, counts, oc)
+        p, m = helpers.groups_from_flat(g), helpers.groups_from_flat(g, g.exp_avg)
+        for k in helpers.DENSIFY_GROUPS:
+            torch.testing.assert_close(p[k], op[k], rtol=2e-6, atol=2e-6, msg=lambda s: "%s P=%d %s" % (k, P, s))
+            assert torch.equal(m[k], om[k]), (k, P)
+
+
+def test_densify_is_deterministic_and_generator_driven():
+    """two replicas with the same generator seed produce bit-identical sets (what keeps DP ranks in sync)"""
+    d, cfg = golden_inputs.densify_case("mixed")
+    outs = []
+    for _ in range(2):
+        g = helpers.flat_from_groups(dp, d, dev)
+        gen = torch.Generator(device=dev).manual_seed(77)
+        densify.densify_and_prune(g, _stats_from(d), cfg["max_grad"], cfg["min_opacity"], cfg["extent"], None,
+                                  generator=gen)
+        outs.append(g.data.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_densification_stats_and_reset_opacity_match_reference_golden():
+    gold = np.load(os.path.join(GOLD, "densify_reference.npz"))
+    s = golden_inputs.stats_case()
+    P = s["radii"].shape[0]
+    st = densify.DensifyStats(P, dev)
+    st.xyz_gradient_accum.copy_(T(s["xyz_gradient_accum"]).reshape(-1))
+    st.denom.copy_(T(s["denom"]).reshape(-1))
+    st.max_radii2D.copy_(T(s["max_radii2D"]))
+    densify.add_densification_stats(st, T(s["grad2D"]), T(s["radii"]))
+    np.testing.assert_allclose(st.xyz_gradient_accum.cpu().numpy(), gold["stats/xyz_gradient_accum"].reshape(-1), rtol=1e-6)
+    np.testing.assert_array_equal(st.denom.cpu().numpy(), gold["stats/denom"].reshape(-1))
+    np.testing.assert_array_equal(st.max_radii2D.cpu().numpy(), gold["stats/max_radii2D"])
+    g = dp.FlatGaussians(P, torch.device(dev))
+    g.slab("opacity").copy_(T(s["opacity"]))
+    g.exp_avg.fill_(1.0)
+    g.exp_avg_sq.fill_(2.0)
+    before = g.data.clone()
+    densify.reset_opacity(g)
+    np.testing.assert_allclose(g.slab("opacity").cpu().numpy(), gold["reset/opacity"], rtol=1e-6)
+    assert not g.slab("opacity", g.exp_avg).any() and not g.slab("opacity", g.exp_avg_sq).any()
+    a, b, _ = g._slices["opacity"]
+    keep = torch.ones_like(before, dtype=torch.bool)
+    keep[a:b] = False
+    assert torch.equal(g.data[keep], before[keep]) and bool((g.exp_avg[keep] == 1).all())
+
+
+def test_fused_activations_match_torch():
+    """lg_activate_forward vs torch.sigmoid / torch.exp / F.normalize on the same device, incl. a zero quaternion"""
+    P = 100_003
+    g = dp.FlatGaussians(P, torch.device(dev))
+    g.data.copy_(torch.randn(g.data.shape, generator=torch.Generator().manual_seed(3)).to(dev) * 2.0)
+    g.slab("rotation")[5].zero_()
+    act = g.activate()
+    o, s, r = densify_oracle.activations(g.slab("opacity"), g.slab("scaling"), g.slab("rotation"))
+    torch.testing.assert_close(act["opacities"], o, rtol=2e-7, atol=1e-9)
+    torch.testing.assert_close(act["scales"], s, rtol=2e-7, atol=0)
+    torch.testing.assert_close(act["rotations"], r, rtol=3e-7, atol=1e-9)
+    torch.testing.assert_close(act["rot_norm"], g.slab("rotation").norm(dim=1), rtol=3e-7, atol=0)
+    assert act["means3D"].data_ptr() == g.slab("xyz").data_ptr() and act["shs"].data_ptr() == g.slab("shs").data_ptr()
+
+
+def _small_training_set(P=20_000, n_views=3):
+    sc = scenes.trained_like_scene(P, seed=5, log_scale_mean=np.log(0.02))
+    g = dp.FlatGaussians.from_scene(sc, torch.device(dev))
+    g.slab("rotation").mul_(torch.rand(P, 1, device=dev) * 2 + 0.5)  # raw quaternions are not unit length
+    cams = [dp.camera_to_device(c, dev) for c in scenes.orbit_cameras(n_views, 160, 128)]
+    gts = [torch.rand(3, 128, 160, device=dev, generator=torch.Generator(device=dev).manual_seed(v)) for v in range(n_views)]
+    return g, cams, gts
+
+
+def test_fused_step_gradients_equal_autograd_through_torch_activations():
+    """raw-parameter gradients from the in-kernel chain rule (lg_rasterize_backward_raw + GradSinks accumulation over
+    three views) == autograd through torch.sigmoid / exp / normalize around the same operator"""
+    g, cams, gts = _small_training_set()
+    bg = torch.zeros(3, device=dev)
+    fused = dp.ViewParallelTrainer(g)                                   # render_fn=None -> fused path
+    loss_f = fused.accumulate_views(cams, gts, bg)
+    grad_fused = g.grad.clone()
+    generic = dp.ViewParallelTrainer(g, render_fn=dp.default_render)    # autograd leaves + torch activations
+    loss_g = generic.accumulate_views(cams, gts, bg)
+    torch.testing.assert_close(loss_f, loss_g, rtol=1e-5, atol=1e-7)
+    for name, _ in g.fields:
+        a, b = g.slab(name, grad_fused), g.slab(name, g.grad)
+        scale = float(b.abs().max())
+        assert scale > 0, name
+        err = float((a - b).abs().max()) / scale
+        assert err < 1e-3, (name, err)
+
+
+def test_trainer_single_gpu_with_density_control():
+    """fused step + statistics + densify_and_prune + opacity reset on the schedule of LG/train.py:265-276"""
+    g, cams, gts = _small_training_set(P=30_000, n_views=2)
+    cfg = dp.DensifyConfig(densify_from_iter=2, densify_until_iter=50, densification_interval=3,
+                           opacity_reset_interval=7, densify_grad_threshold=1e-7, cameras_extent=4.0)
+    tr = dp.ViewParallelTrainer(g, densify=cfg, seed=3)
+    bg = torch.zeros(3, device=dev)
+    sizes, losses = [], []
+    for _ in range(9):
+        losses.append(float(tr.step(cams, gts, bg)))
+        sizes.append(g.P)
+    assert sizes[0] == sizes[1] == 30_000 and sizes[2] != 30_000 and sizes[5] != sizes[4], sizes
+    assert torch.isfinite(g.data).all() and g.grad.numel() == g.data.numel() == g.floats * g.P
+    assert tr.stats.denom.numel() == g.P
+    assert np.isfinite(losses).all()
+    # after the reset at iteration 7 no opacity exceeds sigmoid^-1(0.01) by more than two Adam steps' worth
+    assert float(torch.sigmoid(g.slab("opacity")).max()) < 0.05
