@@ -258,6 +258,130 @@ def image_loss_section(device, hbm_peak):
             "cpu_port_ms": round(cpu_ms, 2), "cpu_threads": torch.get_num_threads(), "cpu_kind": "port"}
 
 
+def train_iteration_section(impl, device, iters=40, warm=10):
+    """BASELINE config 3: one LLFF-style training iteration (LG/train.py:105-288) at 1008x756 on the 500k-Gaussian
+    slab scene — activations, render, L1 + SSIM + global/patch DWT loss, backward, densification statistics, Adam —
+    plus one densify_and_prune call.  `ours`: raw parameters in the flat buffer, every stage a fused kernel of this
+    repo.  `reference`: the stock op chain (six nn.Parameters, torch activations, the reference CUDA rasterizer,
+    the PyTorch loss chain with its host-side running-mean ratio, torch.optim.Adam).  CUDA-event breakdown."""
+    import math
+    from lgdwt_b200 import densify, dp, scenes
+    Wd, Hd, V = 1008, 756, 3
+    sc = scenes.slab_scene(500_000, seed=2)
+    fovy = 2 * math.atan(math.tan(0.525) * Hd / Wd)
+    cams = [dp.camera_to_device(scenes.look_at_camera(Wd, Hd, 1.05, fovy, (0.25 * (k - 1), 0.0, 0.0), target=(0.0, 0.0, 5.0)),
+                                device) for k in range(V)]
+    gen = torch.Generator(device=device).manual_seed(11)
+    gts = [torch.rand((3, Hd, Wd), device=device, generator=gen) for _ in range(V)]
+    bg = torch.zeros(3, device=device)
+    g = dp.FlatGaussians.from_scene(sc, device)
+    phases = ("render", "loss", "backward", "stats", "adam")
+    marks = []
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    if impl == "ours":
+        stats = densify.DensifyStats(g.P, device)
+        rm = torch.ones((), device=device)   # running-mean DWT scale kept on the device (no .item() in the loop)
+        cfg = dp.AdamConfig()
+
+        def iteration(i, timed):
+            nonlocal rm
+            cam, gt = cams[i % V], gts[i % V]
+            t = [ev()]
+            image, radii, vsp = dp.fused_render(g, cam, bg, accumulate=False)
+            t.append(ev())
+            from lgdwt_b200 import fused_dwt_loss, fused_photometric_loss
+            l1, ssim = fused_photometric_loss(image, gt)
+            dwt, patch, _ = fused_dwt_loss(image, gt)
+            base = 0.8 * l1 + 0.2 * (1.0 - ssim)
+            rm = 0.95 * rm + 0.05 * (base / (dwt + 1e-8)).detach()
+            loss = base + rm.clamp(0.1, 10.0) * dwt + 0.1 * patch
+            t.append(ev())
+            loss.backward()
+            t.append(ev())
+            densify.add_densification_stats(stats, vsp.grad, radii)
+            t.append(ev())
+            g.adam_step(cfg)
+            t.append(ev())
+            if timed:
+                marks.append(t)
+    else:
+        from oracle import dwt_oracle, photometric_oracle, ref_cuda
+        if ref_cuda.load_ref() is None:
+            return {"unavailable": "oracle/_ref not built"}
+        P = g.P
+        raw = {k: torch.nn.Parameter(g.field(k).clone().reshape(P, *shape)) for k, shape in
+               (("xyz", (3,)), ("f_dc", (1, 3)), ("f_rest", (15, 3)), ("opacity", (1,)), ("scaling", (3,)), ("rotation", (4,)))}
+        a = dp.AdamConfig()
+        lrs = dict(xyz=a.lr_xyz, f_dc=a.lr_f_dc, f_rest=a.lr_f_rest, opacity=a.lr_opacity, scaling=a.lr_scaling, rotation=a.lr_rotation)
+        opt = torch.optim.Adam([{"params": [raw[k]], "lr": lrs[k], "name": k} for k in raw], lr=0.0, eps=1e-15)
+        accum, denom, maxr = torch.zeros((P, 1), device=device), torch.zeros((P, 1), device=device), torch.zeros(P, device=device)
+        state = {"rm": 1.0}
+
+        def iteration(i, timed):
+            cam, gt = cams[i % V], gts[i % V]
+            t = [ev()]
+            shs = torch.cat((raw["f_dc"], raw["f_rest"]), dim=1)                    # gaussian_model.py:121-124
+            vsp = torch.zeros_like(raw["xyz"], requires_grad=True)                    # gaussian_renderer:26-30
+            vsp.retain_grad()
+            image, radii, _ = ref_cuda.RefRasterize.apply(raw["xyz"], vsp, shs, torch.sigmoid(raw["opacity"]),
+                                                          torch.exp(raw["scaling"]),
+                                                          torch.nn.functional.normalize(raw["rotation"]), cam, bg, 3)
+            image = image.clamp(0, 1)
+            t.append(ev())
+            l1, ssim = photometric_oracle.photometric_terms(image, gt)               # train.py:128,182-188
+            dwt, patch, _, _ = dwt_oracle.lgdwt_losses(image, gt)                    # train.py:131-180
+            base = 0.8 * l1 + 0.2 * (1.0 - ssim)
+            ratio = (base / (dwt + 1e-8)).item()                                      # train.py:190-196 (host sync)
+            state["rm"] = 0.95 * state["rm"] + 0.05 * ratio
+            loss = base + min(max(state["rm"], 0.1), 10.0) * dwt + 0.1 * patch
+            t.append(ev())
+            loss.backward()
+            t.append(ev())
+            vis = radii > 0                                                           # train.py:268-269
+            maxr[vis] = torch.max(maxr[vis], radii[vis].float())
+            accum[vis] += torch.norm(vsp.grad[vis, :2], dim=-1, keepdim=True)
+            denom[vis] += 1
+            t.append(ev())
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            t.append(ev())
+            if timed:
+                marks.append(t)
+
+    for i in range(warm):
+        iteration(i, False)
+    ms_total = timed_loop(lambda i: iteration(warm + i, True), iters, 1, device)
+    br = {name: round(float(np.mean([m[k].elapsed_time(m[k + 1]) for m in marks])), 4) for k, name in enumerate(phases)}
+    out = {"workload": "config 3: one training iteration, 500k-Gaussian slab scene, 1008x756, 3 cameras, L1 + SSIM + "
+                       "global/patch DWT loss, densification statistics, Adam", "ms_per_iteration": round(ms_total / iters, 4),
+           "iterations_per_s": round(iters / (ms_total / 1e3), 2), "breakdown_ms": br}
+    if impl == "ours":
+        a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        P0 = g.P
+        saved = (g.data.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone(), stats.xyz_gradient_accum.clone(),
+                 stats.denom.clone())
+        for rep in range(3):   # two warm calls (lazy module load, allocator), the third one timed
+            g.replace(P0, saved[0].clone(), saved[1].clone(), saved[2].clone())
+            stats.__init__(P0, device)
+            stats.xyz_gradient_accum.copy_(saved[3])
+            stats.denom.copy_(saved[4])
+            torch.cuda.synchronize(device)
+            a0.record()
+            counts = densify.densify_and_prune(g, stats, 0.0002, 0.005, 6.0, None, generator=gen)
+            b0.record()
+            torch.cuda.synchronize(device)
+        out["densify_and_prune"] = {"ms": round(a0.elapsed_time(b0), 3), "P_before": P0, "P_after": g.P,
+                                    "cloned": counts["cloned"], "split": counts["split_parents"],
+                                    "algorithmic_bytes": 36 * P0 + 2 * 3 * 4 * g.floats * g.P,
+                                    "note": "plan + one host read-back of the counts + gather of parameters and both Adam moments"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-iteration", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     W = max(args.warmup, 3)
@@ -415,6 +540,8 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sc, cams[0])
             line["image_loss"] = image_loss_section(device, hbm_peak)
+        if rank == 0 and world == 1 and not args.no_train_iteration:
+            line["train_iteration"] = train_iteration_section("ours", device)
     else:
         line["impl"] = "reference"
         line["gpu_launches"] = None
@@ -423,6 +550,8 @@ def main():
         line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": ref_kind,
                                 "sample": "the reference has no CPU implementation of this path; this arm times its "
                                           "own CUDA implementation on the same GPU (cores = 0 host threads)"}
+        if not args.no_train_iteration:
+            line["train_iteration"] = train_iteration_section("reference", device)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

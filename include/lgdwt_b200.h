@@ -263,13 +263,16 @@ int lg_adam_step_split(float* param, const float* grad, float* exp_avg, float* e
  *   eps (2*S, 3) ~ N(0,1) (torch.normal's samples, :421-423) from a generator shared by all ranks.
  * lg_densify_apply: one gather pass per field writes the P_new-row parameter buffer and both Adam moments (moments of
  *   new rows zero, cat_tensors_to_optimizer :376-378).  Output order = the reference's (see csrc/densify.cu).
+ *   Slab k of a buffer starts at (floats of the fields before it) * stride; stride >= rows lets the caller pad P to a
+ *   multiple of 4 so that every slab is 16-byte aligned (the rasterizer reads rotations as float4).
  * The statistics of the new set are zeros of length P_new (densification_postfix :404-409): the caller re-allocates. */
 size_t lg_densify_scratch_bytes(int P);
 int lg_densify_plan(int P, const float* scaling, const float* opacity, const float* grad_accum, const float* denom,
                     float max_grad, float min_opacity, float extent, float percent_dense, float max_screen_size,
                     uint32_t* src_index, uint32_t* eps_row, int* totals, void* scratch, size_t scratch_bytes,
                     void* stream);
-int lg_densify_apply(int P, int P_new, int sh_floats, const float* data, const float* exp_avg,
+int lg_densify_apply(int P, int P_stride, int P_new, int P_new_stride, int sh_floats, const float* data,
+                     const float* exp_avg,
                      const float* exp_avg_sq, float* data_new, float* exp_avg_new, float* exp_avg_sq_new,
                      const uint32_t* src_index, const uint32_t* eps_row, const float* eps, int eps_rows, void* stream);
 /* visible = radii > 0:  grad_accum += |grad2D.xy|, denom += 1, max_radii2D = max(max_radii2D, radii) */

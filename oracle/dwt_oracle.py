@@ -102,7 +102,7 @@ def compute_patch_dwt_loss(pred, gt, elf_map, patch_size=128, percentile=0.2, lh
     L = pp.shape[2]
     mask, _, _ = patch_selection(elf_map, patch_size, percentile)
     if mask.sum() == 0:
-        return torch.tensor(0.0)
+        return torch.tensor(0.0, device=pred.device)
     pp = pp.view(N, C, patch_size, patch_size, L).permute(0, 4, 1, 2, 3)
     gp = gp.view(N, C, patch_size, patch_size, L).permute(0, 4, 1, 2, 3)
     pb, gb = get_dwt_subbands(pp[mask]), get_dwt_subbands(gp[mask])
@@ -125,7 +125,7 @@ def lgdwt_losses(pred, gt, band_weights=(1, 1, 1, 0, 0, 0, 0, 0), patch_size=128
     for n, w in zip(BAND_NAMES, band_weights):
         if w != 0.0:
             total = total + w * band_l1[n]
-    patch_loss, mask = torch.tensor(0.0), None
+    patch_loss, mask = torch.tensor(0.0, device=pb.device), None
     if patch_enable:
         elf = compute_elf_map(gb)
         patch_loss = compute_patch_dwt_loss(pb, gb, elf, patch_size, percentile, w_lh, w_hl)

@@ -30,7 +30,7 @@ def ssim(img1, img2, window_size=11):
     """loss_utils._ssim (:67-86) with size_average=True; img: (C,H,W) or (N,C,H,W)"""
     C = img1.size(-3)
     _, w2 = gaussian_window(window_size)
-    window = w2.to(img1.dtype).expand(C, 1, window_size, window_size).contiguous()
+    window = w2.to(img1.dtype).to(img1.device).expand(C, 1, window_size, window_size).contiguous()
     pad = window_size // 2
     x = img1 if img1.dim() == 4 else img1.unsqueeze(0)
     y = img2 if img2.dim() == 4 else img2.unsqueeze(0)

@@ -301,13 +301,14 @@ extern "C" int lg_densify_plan(int P, const float* scaling, const float* opacity
     return LG_OK;
 }
 
-extern "C" int lg_densify_apply(int P, int P_new, int sh_floats, const float* data, const float* exp_avg,
+extern "C" int lg_densify_apply(int P, int P_stride, int P_new, int P_new_stride, int sh_floats, const float* data,
+                                const float* exp_avg,
                                 const float* exp_avg_sq, float* data_new, float* exp_avg_new, float* exp_avg_sq_new,
                                 const uint32_t* src_index, const uint32_t* eps_row, const float* eps, int eps_rows,
                                 void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
-    if (P < 0 || P_new < 0 || sh_floats < 0 || P_new > 2 * (long long)P) {
-        set_error("lg_densify_apply: invalid sizes (P_new <= 2 P)");
+    if (P < 0 || P_new < 0 || sh_floats < 0 || P_new > 2 * (long long)P || P_stride < P || P_new_stride < P_new) {
+        set_error("lg_densify_apply: invalid sizes (P_new <= 2 P, strides >= row counts)");
         return LG_ERR_INVALID_ARGUMENT;
     }
     if (P_new == 0) return LG_OK;
@@ -317,14 +318,14 @@ extern "C" int lg_densify_apply(int P, int P_new, int sh_floats, const float* da
         return LG_ERR_INVALID_ARGUMENT;
     }
     const int widths[5] = {3, sh_floats, 1, 3, 4};
-    const size_t sP = (size_t)P, dP = (size_t)P_new;
+    const size_t sP = (size_t)P_stride, dP = (size_t)P_new_stride;  // slab k starts at (floats before it) * stride
     size_t off = 0;
     const float* in_scaling = data + (size_t)(3 + sh_floats + 1) * sP;
     const float* in_rotation = in_scaling + 3 * sP;
     for (int f = 0; f < 5; f++) {
         const int w = widths[f];
         if (w == 0) continue;
-        const long long n_out = (long long)dP * w;
+        const long long n_out = (long long)P_new * w;
         const int blocks = (int)((n_out + 255) / 256 < (long long)LG_NUM_SMS * 32 ? (n_out + 255) / 256
                                                                                    : (long long)LG_NUM_SMS * 32);
 #define DN_ARGS n_out, w, src_index, eps_row, eps, data + off * sP, exp_avg + off * sP, exp_avg_sq + off * sP, \

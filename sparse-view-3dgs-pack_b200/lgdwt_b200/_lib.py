@@ -87,7 +87,7 @@ def _load():
     lib.lg_densify_plan.restype = i
     lib.lg_densify_plan.argtypes = [i, _P, _P, _P, _P, f, f, f, f, f, _P, _P, _P, _P, ctypes.c_size_t, _P]
     lib.lg_densify_apply.restype = i
-    lib.lg_densify_apply.argtypes = [i, i, i] + [_P] * 9 + [i, _P]
+    lib.lg_densify_apply.argtypes = [i, i, i, i, i] + [_P] * 9 + [i, _P]
     lib.lg_densify_stats.restype = i
     lib.lg_densify_stats.argtypes = [i] + [_P] * 6
     lib.lg_reset_opacity.restype = i

@@ -77,9 +77,10 @@ def densify_and_prune(g, stats, max_grad, min_opacity, extent, max_screen_size, 
     eps = eps.contiguous()
     if eps.dtype != torch.float32 or eps.numel() != 6 * split_parents or eps.device != g.data.device:
         raise RuntimeError("densify_and_prune: eps must be a (2*%d, 3) fp32 tensor on %s" % (split_parents, dev))
-    new = [torch.empty(g.floats * P_new, dtype=torch.float32, device=dev) for _ in range(3)]
+    stride_new = g.padded(P_new)
+    new = [torch.zeros(g.floats * stride_new, dtype=torch.float32, device=dev) for _ in range(3)]
     with torch.cuda.device(dev):
-        rc = _lib.lib.lg_densify_apply(P, P_new, 3 * g.M, _lib.ptr(g.data), _lib.ptr(g.exp_avg), _lib.ptr(g.exp_avg_sq),
+        rc = _lib.lib.lg_densify_apply(P, g.stride, P_new, stride_new, 3 * g.M, _lib.ptr(g.data), _lib.ptr(g.exp_avg), _lib.ptr(g.exp_avg_sq),
                                        _lib.ptr(new[0]), _lib.ptr(new[1]), _lib.ptr(new[2]), _lib.ptr(src_index),
                                        _lib.ptr(eps_row), _lib.ptr(eps), 2 * split_parents, _lib.stream_ptr(dev))
     _lib.check(rc, RuntimeError)

@@ -75,26 +75,33 @@ class FlatGaussians:
         self.floats = sum(w for _, w in self.fields)
         self.M = (sh_degree + 1) ** 2
         self.step_count = 0
-        self._install(int(P), *(torch.zeros(self.floats * int(P), dtype=torch.float32, device=device) for _ in range(3)))
+        n = self.floats * self.padded(int(P))
+        self._install(int(P), *(torch.zeros(n, dtype=torch.float32, device=device) for _ in range(3)))
+
+    @staticmethod
+    def padded(P):
+        """row stride of the slabs: P rounded up to a multiple of 4, so that every slab starts 16-byte aligned (the
+        rasterizer reads rotations and writes their gradients as float4).  Padding rows stay zero."""
+        return (int(P) + 3) // 4 * 4
 
     def _install(self, P, data, exp_avg, exp_avg_sq):
-        self.P = P
+        self.P, self.stride = P, self.padded(P)
         self.data, self.exp_avg, self.exp_avg_sq = data, exp_avg, exp_avg_sq
         self.grad = torch.zeros_like(data)
         self._slices, off = {}, 0
         for name, w in self.fields:
-            self._slices[name] = (off * P, (off + w) * P, w)
+            self._slices[name] = (off * self.stride, (off + w) * self.stride, w)
             off += w
         self._act = None
 
     def replace(self, P_new, data, exp_avg, exp_avg_sq):
         """install the buffers a densification produced (every per-Gaussian side array is re-created by the caller)"""
-        assert data.numel() == exp_avg.numel() == exp_avg_sq.numel() == self.floats * P_new
+        assert data.numel() == exp_avg.numel() == exp_avg_sq.numel() == self.floats * self.padded(P_new)
         self._install(int(P_new), data, exp_avg, exp_avg_sq)
 
     def slab(self, name, buf=None):
-        a, b, w = self._slices[name]
-        return (self.data if buf is None else buf)[a:b].view(self.P, w)
+        a, _b, w = self._slices[name]
+        return (self.data if buf is None else buf)[a:a + self.P * w].view(self.P, w)
 
     def field(self, name, buf=None):
         """(P, w) view of one of the reference's six parameter groups (f_dc / f_rest are column ranges of the SH slab)"""

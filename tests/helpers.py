@@ -143,7 +143,8 @@ def flat_from_groups(dp, d, device, prefix=""):
     g = dp.FlatGaussians(P, torch.device(device))
     for buf, pre in ((g.data, ""), (g.exp_avg, "exp_avg/"), (g.exp_avg_sq, "exp_avg_sq/")):
         for k in DENSIFY_GROUPS:
-            g.field(k, buf).copy_(torch.as_tensor(d[prefix + pre + k]).reshape(P, -1))
+            dst = g.field(k, buf)
+            dst.copy_(torch.as_tensor(d[prefix + pre + k]).reshape(P, dst.shape[1]))
     return g
 
 
@@ -163,11 +164,11 @@ def oracle_densify_fn(g, stats, cfg, max_screen_size, generator):
                                                            cfg.densify_grad_threshold, cfg.min_opacity,
                                                            cfg.cameras_extent, max_screen_size, cfg.percent_dense)
     P_new = counts["P"]
-    bufs = [torch.zeros(g.floats * P_new) for _ in range(3)]
+    bufs = [torch.zeros(g.floats * g.padded(P_new)) for _ in range(3)]
     g.replace(P_new, *bufs)
     for buf, src in ((g.data, np_), (g.exp_avg, nm), (g.exp_avg_sq, nv)):
         for k in DENSIFY_GROUPS:
-            g.field(k, buf).copy_(src[k].reshape(P_new, -1))
+            g.field(k, buf).copy_(src[k].reshape(P_new, g.field(k, buf).shape[1]))
     return counts
 
 

@@ -178,7 +178,7 @@ def test_trainer_single_gpu_with_density_control():
         losses.append(float(tr.step(cams, gts, bg)))
         sizes.append(g.P)
     assert sizes[0] == sizes[1] == 30_000 and sizes[2] != 30_000 and sizes[5] != sizes[4], sizes
-    assert torch.isfinite(g.data).all() and g.grad.numel() == g.data.numel() == g.floats * g.P
+    assert torch.isfinite(g.data).all() and g.grad.numel() == g.data.numel() == g.floats * g.stride
     assert tr.stats.denom.numel() == g.P
     assert np.isfinite(losses).all()
     # after the reset at iteration 7 no opacity exceeds sigmoid^-1(0.01) by more than two Adam steps' worth
