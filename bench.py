@@ -110,7 +110,16 @@ class Stepper:
         self.copy_done = [torch.cuda.Event() for _ in range(VIEWS_PER_RANK)]
         self.dev_gt = [torch.empty((3, HEIGHT, WIDTH), device=device) for _ in range(VIEWS_PER_RANK)]
         # the flat gradient bucket (what a data-parallel step all-reduces): means3D 3 | shs 48 | opacity 1 | scales 3 | rot 4
-        self.bucket = torch.zeros(59 * P, device=device)
+        self.peer, self.peer_unavailable = None, ""
+        if impl == "ours" and world > 1:
+            # the exchange step over NVLink peer memory (csrc/peer.cu); NCCL all-reduce when the ranks cannot map
+            # each other's memory (LGDWT_EXCHANGE=nccl forces it)
+            if os.environ.get("LGDWT_EXCHANGE", "peer") == "peer":
+                from lgdwt_b200.peer import PeerExchange
+                self.peer, self.peer_unavailable = PeerExchange.create(59 * P, device)
+            else:
+                self.peer_unavailable = "LGDWT_EXCHANGE=nccl"
+        self.bucket = self.peer.grad if self.peer is not None else torch.zeros(59 * P, device=device)
         self.fields = (("means3D", 3), ("shs", 48), ("opacities", 1), ("scales", 3), ("rotations", 4))
         views, off = {}, 0
         for k, w in self.fields:
@@ -150,7 +159,10 @@ class Stepper:
         if self.impl != "ours":
             for k, _ in self.fields:
                 self.views[k].copy_(self.p[k].grad)
-        dist.all_reduce(self.bucket)
+        if self.peer is not None:
+            self.peer.allreduce(1.0)
+        else:
+            dist.all_reduce(self.bucket)
 
     def step_resident(self, cams):
         self.begin_step()
@@ -199,6 +211,49 @@ def timed_loop(fn, steps, world, device):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
+
+
+def exchange_section(stepper, device, world):
+    """The exchange step of one data-parallel training step on the benchmark's bucket (236 B per Gaussian), timed
+    alone: NCCL all-reduce vs the peer-memory all-reduce the timed step uses, and — with the optimizer — NCCL
+    all-reduce + the fused Adam pass on every rank vs ONE fused reduce-scatter + Adam + all-gather kernel."""
+    from lgdwt_b200 import dp
+    out = {"step_uses": "peer all-reduce (csrc/peer.cu)" if stepper.peer is not None else "nccl all-reduce",
+           "bucket_bytes": int(stepper.bucket.numel() * 4)}
+    if stepper.peer is None:
+        out["peer_unavailable"] = stepper.peer_unavailable
+
+    def t(fn, reps=10):
+        for _ in range(3):
+            fn()
+        return timed_loop(lambda i: fn(), reps, world, device) / reps
+
+    scratch = torch.zeros_like(stepper.bucket)
+    out["nccl_allreduce_ms"] = round(t(lambda: dist.all_reduce(scratch)), 4)
+    del scratch
+    if stepper.peer is not None:
+        ex = stepper.peer
+        out["peer_allreduce_ms"] = round(t(lambda: ex.allreduce(1.0)), 4)
+        g = dp.FlatGaussians(stepper.P, device)
+        cfg = dp.AdamConfig()
+        moments = (g.exp_avg, g.exp_avg_sq)
+        g.data, g.grad = ex.param, ex.grad   # time on the shared block itself
+
+        def nccl_adam():
+            dist.all_reduce(g.grad)
+            g.adam_step(cfg)
+
+        def fused():
+            g.step_count += 1
+            ex.reduce_adam(moments[0], moments[1], g.adam_segments(cfg), cfg, g.step_count, 1.0)
+
+        out["nccl_allreduce_plus_adam_ms"] = round(t(nccl_adam), 4)
+        out["peer_fused_reduce_adam_gather_ms"] = round(t(fused), 4)
+        ex.check()
+        n = stepper.bucket.numel() * 4
+        out["nvlink_bytes_per_rank_each_way"] = int(n * (world - 1) / world)
+        out["peer_fused_GBps_each_way"] = round(n * (world - 1) / world / (out["peer_fused_reduce_adam_gather_ms"] * 1e-3) / 1e9, 1)
+    return out
 
 
 def cpu_baseline(sc, cam):
@@ -502,6 +557,11 @@ def main():
                          "MEASURED_PEAKS.json)",
                          "work_terms": {"num_rendered": R, "n_eval_fwd": n_eval, "n_trav": n_trav, "n_hit": n_hit}})
 
+    # ---- the exchange step alone (N > 1): NCCL vs the peer-memory kernels, with and without the optimizer
+    exchange = None
+    if impl == "ours" and world > 1:
+        exchange = exchange_section(stepper, device, world)
+
     # ---- e2e: host inputs every step + loss read-back
     host_cams = []
     for c in cams:
@@ -529,12 +589,15 @@ def main():
         "config": {"workload": "1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, %d views per "
                                "rank per step (global view batch %d), rasterize forward+backward with the gradients "
                                "of the rank's views accumulated in one flat bucket" % (V, V * world) +
-                               (" + one NCCL all-reduce of the 236 B/Gaussian bucket per step" if world > 1 else ""),
+                               (" + one all-reduce of the 236 B/Gaussian bucket per step (%s)" %
+                                ("peer-memory kernel over NVLink" if stepper.peer is not None else "NCCL") if world > 1 else ""),
                    "views_per_rank_per_step": V, "global_view_batch": V * world, "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                    "cameras": N_CAMERAS, "parallelism": "view-parallel dp%d" % world,
                    "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 43 MB of sort keys per step)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
+    if exchange is not None:
+        line["exchange"] = exchange
     if impl == "ours":
         line["roofline"], line["stages"] = roofline, stages
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -247,6 +247,33 @@ int lg_adam_step_split(float* param, const float* grad, float* exp_avg, float* e
                        const int* row_width, const int* row_split, float beta1, float beta2, float eps, int step,
                        float grad_scale, void* stream);
 
+/* The data-parallel exchange step over NVLink peer memory (no counterpart in the reference, which is single-GPU;
+ * SURVEY.md §8e): gradient reduce-scatter + Adam + parameter all-gather as ONE kernel per rank (csrc/peer.cu).
+ * Buffers are cudaMalloc allocations shared between the per-GPU processes with CUDA IPC:
+ *   lg_peer_alloc/free     zero-filled device buffer that can be exported
+ *   lg_peer_export         64-byte IPC handle of such a buffer (exchange it with any host-side all-gather)
+ *   lg_peer_open/close     map a peer's buffer into this process (peer access enabled lazily)
+ *   lg_peer_barrier        flag exchange between the `world` ranks on `stream` (flag_ptrs[q] = rank q's array of 16
+ *                          u32 words (world <= 8), mapped here; `epoch` must grow by one per call); orders every rank's earlier
+ *                          work on its stream before every rank's later work
+ *   lg_peer_check          host-side: LG_ERR_CUDA if a barrier timed out (~2 s) since the last check
+ *   lg_peer_reduce_adam    rank's shard = float4 range [n/4*rank/world, n/4*(rank+1)/world): g = sum_r grad_r (rank
+ *                          order), Adam (lg_adam_step_split semantics; moments touched by the owner only), new
+ *                          parameters stored into all ranks' parameter buffers.  Call between two lg_peer_barrier.
+ *   lg_peer_allreduce      the reduce + broadcast alone (sum * grad_scale lands in every rank's gradient buffer) */
+int lg_peer_alloc(size_t bytes, void** dev_ptr);
+int lg_peer_free(void* dev_ptr);
+int lg_peer_export(void* dev_ptr, unsigned char* handle64);
+int lg_peer_open(const unsigned char* handle64, void** mapped);
+int lg_peer_close(void* mapped);
+int lg_peer_barrier(int rank, int world, void* const* flag_ptrs, unsigned epoch, void* stream);
+int lg_peer_check(void* stream);
+int lg_peer_reduce_adam(int rank, int world, void* const* grad_ptrs, void* const* param_ptrs, float* exp_avg,
+                        float* exp_avg_sq, long long n, int num_segments, const long long* segment_ends,
+                        const float* lrs, const float* lrs_b, const int* row_width, const int* row_split, float beta1,
+                        float beta2, float eps, int step, float grad_scale, void* stream);
+int lg_peer_allreduce(int rank, int world, void* const* grad_ptrs, long long n, float grad_scale, void* stream);
+
 /* Adaptive density control on the flat field-major parameter buffer of the view-parallel trainer
  * (F = 11 + sh_floats floats per Gaussian: xyz 3 | SH (M,3) = f_dc then f_rest | opacity 1 | scaling 3 | rotation 4,
  * every field a contiguous (P, w) slab; the same buffer lg_adam_step updates).  Replaces the boolean-index + torch.cat

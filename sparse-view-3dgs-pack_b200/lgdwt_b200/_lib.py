@@ -92,6 +92,26 @@ def _load():
     lib.lg_densify_stats.argtypes = [i] + [_P] * 6
     lib.lg_reset_opacity.restype = i
     lib.lg_reset_opacity.argtypes = [i] + [_P] * 4
+    lib.lg_peer_alloc.restype = i
+    lib.lg_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    lib.lg_peer_free.restype = i
+    lib.lg_peer_free.argtypes = [_P]
+    lib.lg_peer_export.restype = i
+    lib.lg_peer_export.argtypes = [_P, ctypes.c_char_p]
+    lib.lg_peer_open.restype = i
+    lib.lg_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.lg_peer_close.restype = i
+    lib.lg_peer_close.argtypes = [_P]
+    lib.lg_peer_barrier.restype = i
+    lib.lg_peer_barrier.argtypes = [i, i, ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint, _P]
+    lib.lg_peer_check.restype = i
+    lib.lg_peer_check.argtypes = [_P]
+    lib.lg_peer_reduce_adam.restype = i
+    lib.lg_peer_reduce_adam.argtypes = [i, i, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _P, _P,
+                                        ctypes.c_longlong, i, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(f),
+                                        ctypes.POINTER(f), ctypes.POINTER(i), ctypes.POINTER(i), f, f, f, i, f, _P]
+    lib.lg_peer_allreduce.restype = i
+    lib.lg_peer_allreduce.argtypes = [i, i, ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong, f, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

@@ -169,6 +169,29 @@ class FlatGaussians:
         return GradSinks(s("xyz"), s("shs").view(self.P, self.M, 3), s("opacity"), s("scaling"), s("rotation"),
                          accumulate=accumulate, raw_rot_norm=rot_norm)
 
+    def adopt(self, data_storage, grad_storage):
+        """move the parameters and the gradient bucket into caller-provided storage of the same size (the IPC-shared
+        block of a PeerExchange); views handed out earlier become stale"""
+        assert data_storage.numel() == grad_storage.numel() == self.data.numel()
+        data_storage.copy_(self.data)
+        grad_storage.copy_(self.grad)
+        self.data, self.grad = data_storage, grad_storage
+        self._act = None
+
+    def adam_segments(self, cfg: AdamConfig):
+        """(ends, lr_a, lr_b, row_width, row_split) ctypes arrays for lg_adam_step_split / lg_peer_reduce_adam: one
+        segment per slab, the SH slab split at column 3 into the f_dc and f_rest learning rates"""
+        lrs = dict(xyz=cfg.lr_xyz, f_dc=cfg.lr_f_dc, f_rest=cfg.lr_f_rest, opacity=cfg.lr_opacity,
+                   scaling=cfg.lr_scaling, rotation=cfg.lr_rotation)
+        n_seg = len(self.fields)
+        names = [name for name, _ in self.fields]
+        ends = (ctypes.c_longlong * n_seg)(*[self._slices[n][1] for n in names])
+        lr_a = (ctypes.c_float * n_seg)(*[float(lrs["f_dc" if n == "shs" else n]) for n in names])
+        lr_b = (ctypes.c_float * n_seg)(*[float(lrs["f_rest" if n == "shs" else n]) for n in names])
+        width = (ctypes.c_int * n_seg)(*[self._slices[n][2] if n == "shs" else 1 for n in names])
+        split = (ctypes.c_int * n_seg)(*[3 if n == "shs" else 0 for n in names])
+        return ends, lr_a, lr_b, width, split
+
     def adam_step(self, cfg: AdamConfig, grad_scale: float = 1.0):
         """torch.optim.Adam semantics (bias-corrected, eps outside the sqrt), the reference's six learning rates;
         identical on every rank because the reduced gradient bucket is identical.  CUDA buffers take ONE fused
@@ -182,18 +205,12 @@ class FlatGaussians:
             return
         if self.data.is_cuda:
             from . import _lib
-            n_seg = len(self.fields)
-            names = [name for name, _ in self.fields]
-            ends = (ctypes.c_longlong * n_seg)(*[self._slices[n][1] for n in names])
-            lr_a = (ctypes.c_float * n_seg)(*[float(lrs["f_dc" if n == "shs" else n]) for n in names])
-            lr_b = (ctypes.c_float * n_seg)(*[float(lrs["f_rest" if n == "shs" else n]) for n in names])
-            width = (ctypes.c_int * n_seg)(*[self._slices[n][2] if n == "shs" else 1 for n in names])
-            split = (ctypes.c_int * n_seg)(*[3 if n == "shs" else 0 for n in names])
+            ends, lr_a, lr_b, width, split = self.adam_segments(cfg)
             with torch.cuda.device(self.data.device):
                 rc = _lib.lib.lg_adam_step_split(self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                                 self.exp_avg_sq.data_ptr(), self.data.numel(), n_seg, ends, lr_a, lr_b,
-                                                 width, split, b1, b2, cfg.eps, self.step_count, float(grad_scale),
-                                                 _lib.stream_ptr(self.data.device))
+                                                 self.exp_avg_sq.data_ptr(), self.data.numel(), len(ends), ends, lr_a,
+                                                 lr_b, width, split, b1, b2, cfg.eps, self.step_count,
+                                                 float(grad_scale), _lib.stream_ptr(self.data.device))
             _lib.check(rc, RuntimeError)
             return
         bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
@@ -268,9 +285,12 @@ class ViewParallelTrainer:
                  render_fn: Optional[Callable] = None, loss_fn: Callable = default_loss,
                  group: Optional[dist.ProcessGroup] = None, densify: Optional[DensifyConfig] = None,
                  densify_fn: Optional[Callable] = None, stats_fn: Optional[Callable] = None,
-                 reset_opacity_fn: Optional[Callable] = None, seed: int = 0):
+                 reset_opacity_fn: Optional[Callable] = None, seed: int = 0, exchange: str = "nccl"):
         """render_fn=None selects the fused CUDA path (`fused_render`); a custom render_fn(act, cam, bg) ->
-        (image, radii[, viewspace_points]) runs through autograd leaves.  densify=None disables density control."""
+        (image, radii[, viewspace_points]) runs through autograd leaves.  densify=None disables density control.
+        exchange="nccl": all-reduce of the bucket + the same full Adam pass on every rank; exchange="peer": the
+        fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (lgdwt_b200.peer), falling back to
+        "nccl" (with `peer_unavailable` saying why) when the ranks cannot map each other's memory."""
         self.g, self.adam, self.render_fn, self.loss_fn, self.group = gaussians, adam, render_fn, loss_fn, group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -284,6 +304,31 @@ class ViewParallelTrainer:
         self.generator = torch.Generator(device=gaussians.device).manual_seed(seed)
         if densify is not None:
             self._new_stats()
+        self.peer, self.peer_unavailable, self._want_peer = None, "", exchange == "peer"
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self._make_peer()
+
+    def _make_peer(self):
+        """(re)create the IPC-shared parameter / gradient block for the current buffer size — collective"""
+        self.peer = None
+        if not (self._want_peer and self.distributed and self.world > 1 and self.g.data.is_cuda and self.g.P > 0):
+            return
+        from .peer import PeerExchange
+        self.peer, self.peer_unavailable = PeerExchange.create(self.g.data.numel(), self.g.device, self.group)
+        if self.peer is not None:
+            self.g.adopt(self.peer.param, self.peer.grad)
+
+    def _collect_moments(self):
+        """peer exchange keeps every Adam moment only on its owner rank; a densification needs them everywhere"""
+        if self.peer is None:
+            return
+        n4 = self.g.data.numel() // 4
+        lo, hi = 4 * (n4 * self.rank // self.world), 4 * (n4 * (self.rank + 1) // self.world)
+        for buf in (self.g.exp_avg, self.g.exp_avg_sq):
+            buf[:lo].zero_()
+            buf[hi:].zero_()
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
 
     def _new_stats(self):
         from .densify import DensifyStats
@@ -346,9 +391,11 @@ class ViewParallelTrainer:
         rebuilt = False
         if it > c.densify_from_iter and it % c.densification_interval == 0:
             self.reduce_stats()
+            self._collect_moments()
             mss = c.size_threshold if it > c.opacity_reset_interval else None
             self.densify_fn(self.g, self.stats, c, mss, self.generator)
             self._new_stats()
+            self._make_peer()
             rebuilt = True
         if it % c.opacity_reset_interval == 0:
             if self.reset_opacity_fn is not None:
@@ -362,10 +409,19 @@ class ViewParallelTrainer:
         self.iteration += 1
         loss = self.accumulate_views(cams, gts, bg)
         if not self.maybe_densify():
-            self.reduce_gradients()
             scale = 1.0 / len(cams) if (num_views_scale and len(cams) > 1) else 1.0  # mean over the view batch
-            self.g.adam_step(self.adam, grad_scale=scale)
+            self.exchange_and_update(scale)
         return loss
+
+    def exchange_and_update(self, grad_scale=1.0):
+        """the exchange step + optimizer: NCCL all-reduce then Adam everywhere, or the fused peer-memory kernel"""
+        if self.peer is not None:
+            self.g.step_count += 1
+            self.peer.reduce_adam(self.g.exp_avg, self.g.exp_avg_sq, self.g.adam_segments(self.adam), self.adam,
+                                  self.g.step_count, grad_scale)
+        else:
+            self.reduce_gradients()
+            self.g.adam_step(self.adam, grad_scale=grad_scale)
 
     def replicas_in_sync(self):
         """parameter count and checksum min == max over ranks"""

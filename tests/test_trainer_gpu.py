@@ -183,3 +183,14 @@ def test_trainer_single_gpu_with_density_control():
     assert np.isfinite(losses).all()
     # after the reset at iteration 7 no opacity exceeds sigmoid^-1(0.01) by more than two Adam steps' worth
     assert float(torch.sigmoid(g.slab("opacity")).max()) < 0.05
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink / PCIe peer access")
+def test_peer_exchange_two_gpus():
+    """fused reduce-scatter + Adam + all-gather over peer memory == NCCL all-reduce + local Adam (tests/peer_worker.py)"""
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29641", os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_KERNELS_OK" in r.stdout and "PEER_TRAINER_OK" in r.stdout, r.stdout + r.stderr
