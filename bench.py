@@ -53,7 +53,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
+
+    def mark(self):
+        """start of the window whose samples are reported (the sampler itself is started earlier: nvidia-smi needs
+        ~0.2 s before its first line, longer than a short timed region)"""
+        self.t_mark = time.monotonic()
 
     def start(self):
         try:
@@ -66,19 +71,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.monotonic()
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        window = "timed regions (value + e2e)"
+        rows = [r for t, r in self.rows if self.t_mark is None or self.t_mark <= t <= t_end + 0.05]
+        if not rows:  # region shorter than one sampling period: fall back to the samples of the whole loaded run
+            rows, window = [r for _, r in self.rows], "whole run incl. warm-up (timed regions shorter than one sample)"
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def make_workload(device):
@@ -218,7 +228,8 @@ def exchange_section(stepper, device, world):
     alone: NCCL all-reduce vs the peer-memory all-reduce the timed step uses, and — with the optimizer — NCCL
     all-reduce + the fused Adam pass on every rank vs ONE fused reduce-scatter + Adam + all-gather kernel."""
     from lgdwt_b200 import dp
-    out = {"step_uses": "peer all-reduce (csrc/peer.cu)" if stepper.peer is not None else "nccl all-reduce",
+    out = {"step_uses": ("peer all-reduce (csrc/peer.cu, %s)" % stepper.peer.backend) if stepper.peer is not None
+           else "nccl all-reduce",
            "bucket_bytes": int(stepper.bucket.numel() * 4)}
     if stepper.peer is None:
         out["peer_unavailable"] = stepper.peer_unavailable
@@ -479,16 +490,16 @@ def main():
     pick = lambda i: [cam_devs[((i * world + rank) * V + v) % len(cam_devs)] for v in range(V)]
 
     from lgdwt_b200 import _lib
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- value: inputs resident in HBM
     for i in range(W):
         stepper.step_resident(pick(i))
     launches0 = _lib.lib.lg_launch_count()
     if impl == "ours":
         _lib.stage_timing(min(K * V, 256))
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     ms_total = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device)
-    clocks = sampler.stop()
     launches = _lib.lib.lg_launch_count() - launches0
     ms_step = ms_total / K
     value = world * K * V / (ms_total / 1e3)
@@ -576,6 +587,7 @@ def main():
     for i in range(W):
         e2e_fn(i)
     ms_e2e = timed_loop(e2e_fn, K, world, device)
+    clocks = sampler.stop()
     e2e_value = world * K * V / (ms_e2e / 1e3)
     h2d = V * (3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4)
     e2e = {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_step": round(ms_e2e / K, 4),

@@ -273,6 +273,16 @@ int lg_peer_reduce_adam(int rank, int world, void* const* grad_ptrs, void* const
                         const float* lrs, const float* lrs_b, const int* row_width, const int* row_split, float beta1,
                         float beta2, float eps, int step, float grad_scale, void* stream);
 int lg_peer_allreduce(int rank, int world, void* const* grad_ptrs, long long n, float grad_scale, void* stream);
+/* NVLS variants for buffers that are also mapped through an NVSwitch multicast object (mc_* = the multicast
+ * addresses of the gradient / parameter regions, e.g. torch symmetric memory's multicast_ptr + offset): the sum over
+ * ranks is one multimem.ld_reduce (added inside the switch), the delivery one multimem.st.  Same contract otherwise;
+ * local_param = this rank's own (unicast) parameter region. */
+int lg_peer_reduce_adam_mc(int rank, int world, const void* mc_grad, void* mc_param, const float* local_param,
+                           float* exp_avg, float* exp_avg_sq, long long n, int num_segments,
+                           const long long* segment_ends, const float* lrs, const float* lrs_b, const int* row_width,
+                           const int* row_split, float beta1, float beta2, float eps, int step, float grad_scale,
+                           void* stream);
+int lg_peer_allreduce_mc(int rank, int world, void* mc_grad, long long n, float grad_scale, void* stream);
 
 /* Adaptive density control on the flat field-major parameter buffer of the view-parallel trainer
  * (F = 11 + sh_floats floats per Gaussian: xyz 3 | SH (M,3) = f_dc then f_rest | opacity 1 | scaling 3 | rotation 4,

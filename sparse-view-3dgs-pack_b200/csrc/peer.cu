@@ -174,6 +174,76 @@ __global__ void __launch_bounds__(256, 2) peer_allreduce_kernel(PeerPtrs grads, 
     }
 }
 
+// ---- NVLS variants: the buffers are additionally mapped through a multicast object (NVSwitch), so ONE
+// multimem.ld_reduce returns the sum over all ranks (added inside the switch) and ONE multimem.st delivers the result
+// to all ranks.  Per rank and direction the links then carry about one bucket per step instead of 2 (N-1)/N buckets.
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float4* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#ifndef MC_UNROLL
+#define MC_UNROLL 4  // multimem.ld_reduce round trips through the switch: keep several in flight per thread
+#endif
+__global__ void __launch_bounds__(256, 2) peer_reduce_adam_mc_kernel(const float4* __restrict__ mc_grad,
+                                                                     float4* __restrict__ mc_param,
+                                                                     const float4* __restrict__ local_param,
+                                                                     float4* __restrict__ exp_avg,
+                                                                     float4* __restrict__ exp_avg_sq, long long lo4,
+                                                                     long long hi4, PeerAdam a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < hi4; q0 += MC_UNROLL * stride) {
+        float4 s[MC_UNROLL], m[MC_UNROLL], v[MC_UNROLL], p[MC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MC_UNROLL; u++) {
+            const long long q = q0 + u * stride;
+            if (q < hi4) {
+                s[u] = mc_ld_reduce_add(mc_grad + q);
+                m[u] = exp_avg[q];
+                v[u] = exp_avg_sq[q];
+                p[u] = local_param[q];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MC_UNROLL; u++) {
+            const long long q = q0 + u * stride;
+            if (q >= hi4) break;
+            float4 pn;
+            pn.x = peer_adam_one(s[u].x, m[u].x, v[u].x, p[u].x, 4 * q + 0, a);
+            pn.y = peer_adam_one(s[u].y, m[u].y, v[u].y, p[u].y, 4 * q + 1, a);
+            pn.z = peer_adam_one(s[u].z, m[u].z, v[u].z, p[u].z, 4 * q + 2, a);
+            pn.w = peer_adam_one(s[u].w, m[u].w, v[u].w, p[u].w, 4 * q + 3, a);
+            exp_avg[q] = m[u];
+            exp_avg_sq[q] = v[u];
+            mc_st(mc_param + q, pn);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) peer_allreduce_mc_kernel(float4* __restrict__ mc_grad, long long lo4,
+                                                                   long long hi4, float grad_scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < hi4; q0 += MC_UNROLL * stride) {
+        float4 s[MC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MC_UNROLL; u++)
+            if (q0 + u * stride < hi4) s[u] = mc_ld_reduce_add(mc_grad + q0 + u * stride);
+#pragma unroll
+        for (int u = 0; u < MC_UNROLL; u++) {
+            const long long q = q0 + u * stride;
+            if (q >= hi4) break;
+            s[u].x *= grad_scale; s[u].y *= grad_scale; s[u].z *= grad_scale; s[u].w *= grad_scale;
+            mc_st(mc_grad + q, s[u]);
+        }
+    }
+}
+
 static unsigned* g_peer_status = nullptr;  // device word set by a timed-out barrier
 
 static int peer_status_word(unsigned** out) {
@@ -343,6 +413,65 @@ extern "C" int lg_peer_allreduce(int rank, int world, void* const* grad_ptrs, lo
         default: set_error("lg_peer_allreduce: world sizes 1..8 are built (one NVSwitch node)"); return LG_ERR_UNSUPPORTED;
     }
 #undef PEER_LAUNCH
+    LG_LAUNCH_CHECK(false, stream);
+    return LG_OK;
+}
+
+static int peer_fill_adam(PeerAdam& a, long long n, int num_segments, const long long* segment_ends, const float* lrs,
+                          const float* lrs_b, const int* row_width, const int* row_split, float beta1, float beta2,
+                          float eps, int step, float grad_scale) {
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.count = num_segments;
+    for (int s = 0; s < num_segments; s++) {
+        a.end[s] = segment_ends[s];
+        a.step_a[s] = (float)((double)lrs[s] / bc1);
+        a.step_b[s] = (float)((double)(lrs_b ? lrs_b[s] : lrs[s]) / bc1);
+        a.width[s] = row_width ? row_width[s] : 1;
+        a.split[s] = row_split ? row_split[s] : 0;
+    }
+    if (a.end[num_segments - 1] != n) {
+        set_error("peer Adam: the last segment must end at n");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.grad_scale = grad_scale;
+    return LG_OK;
+}
+
+extern "C" int lg_peer_reduce_adam_mc(int rank, int world, const void* mc_grad, void* mc_param, const float* local_param,
+                                      float* exp_avg, float* exp_avg_sq, long long n, int num_segments,
+                                      const long long* segment_ends, const float* lrs, const float* lrs_b,
+                                      const int* row_width, const int* row_split, float beta1, float beta2, float eps,
+                                      int step, float grad_scale, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (world < 1 || rank < 0 || rank >= world || !mc_grad || !mc_param || !local_param || !exp_avg || !exp_avg_sq ||
+        n < 0 || (n & 3) || num_segments < 1 || num_segments > PEER_MAX_SEGMENTS || !segment_ends || !lrs || step < 1) {
+        set_error("lg_peer_reduce_adam_mc: invalid arguments (n must be a multiple of 4)");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return LG_OK;
+    PeerAdam a;
+    int rc = peer_fill_adam(a, n, num_segments, segment_ends, lrs, lrs_b, row_width, row_split, beta1, beta2, eps, step,
+                            grad_scale);
+    if (rc != LG_OK) return rc;
+    long long lo4, hi4;
+    shard_of(n / 4, rank, world, &lo4, &hi4);
+    peer_reduce_adam_mc_kernel<<<peer_grid(hi4 - lo4), 256, 0, stream>>>((const float4*)mc_grad, (float4*)mc_param,
+                                                                        (const float4*)local_param, (float4*)exp_avg,
+                                                                        (float4*)exp_avg_sq, lo4, hi4, a);
+    LG_LAUNCH_CHECK(false, stream);
+    return LG_OK;
+}
+
+extern "C" int lg_peer_allreduce_mc(int rank, int world, void* mc_grad, long long n, float grad_scale, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (world < 1 || rank < 0 || rank >= world || !mc_grad || n < 0 || (n & 3)) {
+        set_error("lg_peer_allreduce_mc: invalid arguments (n must be a multiple of 4)");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return LG_OK;
+    long long lo4, hi4;
+    shard_of(n / 4, rank, world, &lo4, &hi4);
+    peer_allreduce_mc_kernel<<<peer_grid(hi4 - lo4), 256, 0, stream>>>((float4*)mc_grad, lo4, hi4, grad_scale);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }

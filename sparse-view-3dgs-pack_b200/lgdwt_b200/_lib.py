@@ -112,6 +112,12 @@ def _load():
                                         ctypes.POINTER(f), ctypes.POINTER(i), ctypes.POINTER(i), f, f, f, i, f, _P]
     lib.lg_peer_allreduce.restype = i
     lib.lg_peer_allreduce.argtypes = [i, i, ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong, f, _P]
+    lib.lg_peer_reduce_adam_mc.restype = i
+    lib.lg_peer_reduce_adam_mc.argtypes = [i, i, _P, _P, _P, _P, _P, ctypes.c_longlong, i,
+                                           ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(f), ctypes.POINTER(f),
+                                           ctypes.POINTER(i), ctypes.POINTER(i), f, f, f, i, f, _P]
+    lib.lg_peer_allreduce_mc.restype = i
+    lib.lg_peer_allreduce_mc.argtypes = [i, i, _P, ctypes.c_longlong, f, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

@@ -1,8 +1,11 @@
 """The data-parallel exchange step over NVLink peer memory (host side of csrc/peer.cu).
 
-One process per GPU.  Every rank allocates one cudaMalloc block [flags | gradient bucket | parameters], exports it
-with CUDA IPC, and maps the blocks of all other ranks of the node; `PeerExchange.reduce_adam` then runs the fused
-reduce-scatter + Adam + all-gather kernel between two flag barriers.  The NCCL all-reduce + local Adam path of
+One process per GPU.  Every rank owns one block [flags | gradient bucket | parameters] that all other ranks of the
+node map; `PeerExchange.reduce_adam` runs the fused reduce-scatter + Adam + all-gather kernel between two flag
+barriers.  Two ways to share the block, tried in this order:
+  "nvls"  torch symmetric memory (VMM allocation + NVSwitch multicast object; torch.distributed is plumbing here): the
+          kernels sum with multimem.ld_reduce inside the switch and deliver with multimem.st;
+  "ipc"   a cudaMalloc block exported with CUDA IPC: the kernels use plain 16-byte peer loads / stores.  The NCCL all-reduce + local Adam path of
 `dp.ViewParallelTrainer` stays available (`exchange="nccl"`) and is what runs when peer mapping is impossible
 (different nodes, IPC disabled) — `PeerExchange.create` then returns None and says why.
 """
@@ -42,22 +45,53 @@ class _Block:
 
 
 class PeerExchange:
-    def __init__(self, n_floats, device, group=None):
+    def __init__(self, n_floats, device, group=None, backend="nvls"):
         if n_floats % 4:
             raise ValueError("PeerExchange: the flat buffer must hold a multiple of 4 floats")
-        self.n, self.device, self.group = int(n_floats), device, group
+        self.n, self.device, self.group, self.backend = int(n_floats), device, group, backend
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerExchange: one NVSwitch node (world <= 8)")
         self.epoch = 0
+        self.mc_base = None
+        if backend == "nvls":
+            bases = self._init_symmetric()
+        elif backend == "ipc":
+            bases = self._init_ipc()
+        else:
+            raise ValueError("backend must be 'nvls' or 'ipc'")
+        arr = lambda vals: (ctypes.c_void_p * self.world)(*vals)
+        self._flags = arr(bases)
+        self._grads = arr([b + _FLAG_BYTES for b in bases])
+        self._params = arr([b + _FLAG_BYTES + 4 * self.n for b in bases])
+        dist.barrier(group=group)  # every rank has mapped every block before anyone uses (or frees) one
+
+    def _init_symmetric(self):
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else dist.group.WORLD
+        total = _FLAG_BYTES // 4 + 2 * self.n
+        self._symm_tensor = symm.empty(total, dtype=torch.float32, device=self.device)
+        self._symm_tensor.zero_()
+        torch.cuda.synchronize(self.device)
+        h = self._symm_handle = symm.rendezvous(self._symm_tensor, grp.group_name)
+        if not h.multicast_ptr:
+            raise RuntimeError("symmetric memory has no multicast mapping on this system")
+        self.mc_base = int(h.multicast_ptr)
+        self.grad = self._symm_tensor[_FLAG_BYTES // 4:_FLAG_BYTES // 4 + self.n]
+        self.param = self._symm_tensor[_FLAG_BYTES // 4 + self.n:]
+        return [int(p) for p in h.buffer_ptrs]
+
+    def _init_ipc(self):
         blk = self._blk = _Block()
         nbytes = _FLAG_BYTES + 2 * 4 * self.n
         base = ctypes.c_void_p()
-        with torch.cuda.device(device):
+        with torch.cuda.device(self.device):
             _lib.check(_lib.lib.lg_peer_alloc(nbytes, ctypes.byref(base)), RuntimeError)
             blk.base = base.value
             handle = ctypes.create_string_buffer(64)
             _lib.check(_lib.lib.lg_peer_export(blk.base, handle), RuntimeError)
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
             bases = []
             for r, h in enumerate(handles):
                 if r == self.rank:
@@ -67,28 +101,32 @@ class PeerExchange:
                 _lib.check(_lib.lib.lg_peer_open(h, ctypes.byref(m)), RuntimeError)
                 blk.mapped.append(m.value)
                 bases.append(m.value)
-        arr = lambda vals: (ctypes.c_void_p * self.world)(*vals)
-        self._flags = arr(bases)
-        self._grads = arr([b + _FLAG_BYTES for b in bases])
-        self._params = arr([b + _FLAG_BYTES + 4 * self.n for b in bases])
-        self.grad = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES, self.n, blk), device=device)
-        self.param = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES + 4 * self.n, self.n, blk), device=device)
-        dist.barrier(group=group)  # every rank has mapped every block before anyone uses (or frees) one
+        self.grad = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES, self.n, blk), device=self.device)
+        self.param = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES + 4 * self.n, self.n, blk), device=self.device)
+        return bases
 
     @classmethod
-    def create(cls, n_floats, device, group=None):
+    def create(cls, n_floats, device, group=None, backends=None):
         """-> (exchange or None, reason).  Collective: every rank of the group must call it; all ranks agree on the
-        outcome (a rank that cannot map its peers makes everyone fall back)."""
-        ex, why = None, ""
-        try:
-            ex = cls(n_floats, device, group)
-        except Exception as e:  # IPC unavailable / no peer access: all ranks then take the NCCL path
-            why = "%s: %s" % (type(e).__name__, e)
-        ok = torch.tensor([1 if ex is not None else 0], device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
-            return None, why or "a peer rank could not map the shared buffers"
-        return ex, ""
+        outcome (a rank that cannot map its peers makes everyone move on to the next backend, then to NCCL).
+        Default order (measured on 8 x B200, 236 MB bucket, fused kernel): N = 2: ipc 0.40 ms, nvls 0.63 ms;
+        N = 8: nvls 0.56 ms, ipc 0.68 ms (NCCL all-reduce + Adam: 0.86 / 1.02 ms) -> peer loads up to 4 ranks,
+        in-switch reduction above."""
+        if backends is None:
+            backends = ("ipc", "nvls") if dist.get_world_size(group) <= 4 else ("nvls", "ipc")
+        whys = []
+        for backend in backends:
+            ex, why = None, ""
+            try:
+                ex = cls(n_floats, device, group, backend)
+            except Exception as e:  # mapping unavailable: all ranks then try the next way
+                why = "%s: %s: %s" % (backend, type(e).__name__, e)
+            ok = torch.tensor([1 if ex is not None else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                return ex, ""
+            whys.append(why or "%s: a peer rank could not map the shared buffers" % backend)
+        return None, " | ".join(whys)
 
     def barrier(self):
         self.epoch += 1
@@ -107,10 +145,17 @@ class PeerExchange:
         ends, lr_a, lr_b, width, split = segments
         self.barrier()
         with torch.cuda.device(self.device):
-            rc = _lib.lib.lg_peer_reduce_adam(self.rank, self.world, self._grads, self._params, exp_avg.data_ptr(),
-                                              exp_avg_sq.data_ptr(), self.n, len(ends), ends, lr_a, lr_b, width, split,
-                                              cfg.beta1, cfg.beta2, cfg.eps, int(step), float(grad_scale),
-                                              _lib.stream_ptr(self.device))
+            if self.mc_base is not None:
+                rc = _lib.lib.lg_peer_reduce_adam_mc(self.rank, self.world, self.mc_base + _FLAG_BYTES,
+                                                     self.mc_base + _FLAG_BYTES + 4 * self.n, self.param.data_ptr(),
+                                                     exp_avg.data_ptr(), exp_avg_sq.data_ptr(), self.n, len(ends), ends,
+                                                     lr_a, lr_b, width, split, cfg.beta1, cfg.beta2, cfg.eps, int(step),
+                                                     float(grad_scale), _lib.stream_ptr(self.device))
+            else:
+                rc = _lib.lib.lg_peer_reduce_adam(self.rank, self.world, self._grads, self._params, exp_avg.data_ptr(),
+                                                  exp_avg_sq.data_ptr(), self.n, len(ends), ends, lr_a, lr_b, width,
+                                                  split, cfg.beta1, cfg.beta2, cfg.eps, int(step), float(grad_scale),
+                                                  _lib.stream_ptr(self.device))
         _lib.check(rc, RuntimeError)
         self.barrier()
 
@@ -118,7 +163,11 @@ class PeerExchange:
         """barrier | every rank sums its shard over all ranks and stores it into every gradient buffer | barrier"""
         self.barrier()
         with torch.cuda.device(self.device):
-            rc = _lib.lib.lg_peer_allreduce(self.rank, self.world, self._grads, self.n, float(grad_scale),
-                                            _lib.stream_ptr(self.device))
+            if self.mc_base is not None:
+                rc = _lib.lib.lg_peer_allreduce_mc(self.rank, self.world, self.mc_base + _FLAG_BYTES, self.n,
+                                                   float(grad_scale), _lib.stream_ptr(self.device))
+            else:
+                rc = _lib.lib.lg_peer_allreduce(self.rank, self.world, self._grads, self.n, float(grad_scale),
+                                                _lib.stream_ptr(self.device))
         _lib.check(rc, RuntimeError)
         self.barrier()

@@ -23,39 +23,43 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     say = (lambda *a: print(*a, flush=True)) if rank == 0 else (lambda *a: None)
 
-    # ---- kernel level: all-reduce and reduce+Adam+gather vs NCCL + local Adam
+    # ---- kernel level: all-reduce and reduce+Adam+gather vs NCCL + local Adam, both ways of sharing the block
     P = 10_001
-    g_ref, g_peer = dp.FlatGaussians(P, dev), dp.FlatGaussians(P, dev)
-    init = torch.randn(g_ref.data.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
-    g_ref.data.copy_(init)
-    g_peer.data.copy_(init)
-    ex, why = PeerExchange.create(g_peer.data.numel(), dev)
-    assert ex is not None, "peer exchange unavailable: " + why
-    g_peer.adopt(ex.param, ex.grad)
     cfg = dp.AdamConfig()
-    for step in range(1, 4):
-        grad = torch.randn(init.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
-        # all-reduce alone
-        ex.grad.copy_(grad)
-        ex.allreduce(0.5)
-        want = grad.clone()
-        dist.all_reduce(want)
-        torch.testing.assert_close(ex.grad, want * 0.5, rtol=1e-6, atol=1e-6)
-        # fused exchange + optimizer
-        g_ref.grad.copy_(grad)
-        dist.all_reduce(g_ref.grad)
-        g_ref.adam_step(cfg, grad_scale=0.25)
-        ex.grad.copy_(grad)
-        g_peer.step_count += 1
-        ex.reduce_adam(g_peer.exp_avg, g_peer.exp_avg_sq, g_peer.adam_segments(cfg), cfg, g_peer.step_count, 0.25)
-        ex.check()
-        torch.testing.assert_close(g_peer.data, g_ref.data, rtol=1e-6, atol=1e-7)
-    # every replica holds bit-identical parameters (each element is computed by exactly one rank)
-    lo, hi = g_peer.data.clone(), g_peer.data.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    assert torch.equal(lo, hi)
-    say("PEER_KERNELS_OK world", world)
+    for backend in ("nvls", "ipc"):
+      g_ref, g_peer = dp.FlatGaussians(P, dev), dp.FlatGaussians(P, dev)
+      init = torch.randn(g_ref.data.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+      g_ref.data.copy_(init)
+      g_peer.data.copy_(init)
+      ex, why = PeerExchange.create(g_peer.data.numel(), dev, backends=(backend,))
+      if ex is None:
+          say("PEER_BACKEND_UNAVAILABLE", why)
+          assert backend == "nvls", why   # NVLS needs an NVSwitch; plain IPC must work wherever there is peer access
+          continue
+      g_peer.adopt(ex.param, ex.grad)
+      for step in range(1, 4):
+          grad = torch.randn(init.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
+          # all-reduce alone
+          ex.grad.copy_(grad)
+          ex.allreduce(0.5)
+          want = grad.clone()
+          dist.all_reduce(want)
+          torch.testing.assert_close(ex.grad, want * 0.5, rtol=1e-6, atol=1e-6)
+          # fused exchange + optimizer
+          g_ref.grad.copy_(grad)
+          dist.all_reduce(g_ref.grad)
+          g_ref.adam_step(cfg, grad_scale=0.25)
+          ex.grad.copy_(grad)
+          g_peer.step_count += 1
+          ex.reduce_adam(g_peer.exp_avg, g_peer.exp_avg_sq, g_peer.adam_segments(cfg), cfg, g_peer.step_count, 0.25)
+          ex.check()
+          torch.testing.assert_close(g_peer.data, g_ref.data, rtol=1e-6, atol=1e-7)
+      # every replica holds bit-identical parameters (each element is computed by exactly one rank)
+      lo, hi = g_peer.data.clone(), g_peer.data.clone()
+      dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+      dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+      assert torch.equal(lo, hi)
+      say("PEER_KERNELS_OK world", world, "backend", ex.backend)
 
     # ---- trainer level: nccl vs peer exchange on the same views, with a densification in between
     sc = scenes.trained_like_scene(20_000, seed=5, log_scale_mean=np.log(0.02))
@@ -81,11 +85,14 @@ def main():
     say("PEER_TRAINER_OK P", out["peer"][0], "max |param diff| nccl vs peer", err)
 
     if "--time" in sys.argv:
-        n = 59 * 1_000_000
+      n = 59 * 1_000_000
+      bucket = torch.randn(n, device=dev)
+      for backend in ("nvls", "ipc"):
         g = dp.FlatGaussians(1_000_000, dev)
-        ex, _ = PeerExchange.create(g.data.numel(), dev)
+        ex, why = PeerExchange.create(g.data.numel(), dev, backends=(backend,))
+        if ex is None:
+            continue
         g.adopt(ex.param, ex.grad)
-        bucket = torch.randn(n, device=dev)
 
         def timeit(fn, reps=20):
             for _ in range(3):
@@ -126,8 +133,8 @@ def main():
         t_nccl = timeit(nccl_path)
         t_peer = timeit(peer_path)
         ex.check()
-        say("PEER_TIMING world %d bucket %.0f MB: nccl all-reduce %.3f ms | peer all-reduce %.3f ms | nccl all-reduce + "
-            "Adam %.3f ms | fused peer reduce+Adam+gather %.3f ms" % (world, n * 4 / 1e6, t_ar, t_par, t_nccl, t_peer))
+        say("PEER_TIMING %s world %d bucket %.0f MB: nccl all-reduce %.3f ms | peer all-reduce %.3f ms | nccl all-reduce + "
+            "Adam %.3f ms | fused peer reduce+Adam+gather %.3f ms" % (backend, world, n * 4 / 1e6, t_ar, t_par, t_nccl, t_peer))
     dist.barrier()
     dist.destroy_process_group()
 
