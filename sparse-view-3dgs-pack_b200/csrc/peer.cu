@@ -64,18 +64,31 @@ struct PeerAdam {
     float beta1, beta2, eps, inv_sqrt_bc2, grad_scale;
 };
 
-__device__ __forceinline__ float peer_adam_one(float g, float& m, float& v, float p, long long i, const PeerAdam& a) {
+// Adam on the four elements of float4 number q (segment boundaries and split-row widths are multiples of 4, so the
+// four share their segment and row: one segment search per float4)
+__device__ __forceinline__ float4 peer_adam4(float4 g, float4& m, float4& v, float4 p, long long q, const PeerAdam& a) {
+    const long long i = 4 * q;
     int s = 0;
     while (s + 1 < a.count && i >= a.end[s]) s++;
-    float step = a.step_a[s];
+    float st[4] = {a.step_a[s], a.step_a[s], a.step_a[s], a.step_a[s]};
     if (a.width[s] > 1) {
-        const long long local = i - (s ? a.end[s - 1] : 0);
-        if ((int)(local % a.width[s]) >= a.split[s]) step = a.step_b[s];
+        const int col = (int)((i - (s ? a.end[s - 1] : 0)) % a.width[s]);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (col + k >= a.split[s]) st[k] = a.step_b[s];
     }
-    g *= a.grad_scale;
-    m = a.beta1 * m + (1.0f - a.beta1) * g;
-    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
-    return p - step * (m / (sqrtf(v) * a.inv_sqrt_bc2 + a.eps));
+    float gv[4] = {g.x, g.y, g.z, g.w}, mv[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float gs = gv[k] * a.grad_scale;
+        mv[k] = a.beta1 * mv[k] + (1.0f - a.beta1) * gs;
+        vv[k] = a.beta2 * vv[k] + (1.0f - a.beta2) * gs * gs;
+        pv[k] = pv[k] - st[k] * (mv[k] / (sqrtf(vv[k]) * a.inv_sqrt_bc2 + a.eps));
+    }
+    m = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    return make_float4(pv[0], pv[1], pv[2], pv[3]);
 }
 
 // lo4 .. hi4: this rank's shard in float4 units.  WORLD and UNROLL are template parameters so that the
@@ -124,11 +137,7 @@ __global__ void __launch_bounds__(256, 2) peer_reduce_adam_kernel(PeerPtrs grads
             float4 s = g[u][0];
 #pragma unroll
             for (int r = 1; r < WORLD; r++) { s.x += g[u][r].x; s.y += g[u][r].y; s.z += g[u][r].z; s.w += g[u][r].w; }
-            float4 pn;
-            pn.x = peer_adam_one(s.x, m[u].x, v[u].x, p[u].x, 4 * q + 0, a);
-            pn.y = peer_adam_one(s.y, m[u].y, v[u].y, p[u].y, 4 * q + 1, a);
-            pn.z = peer_adam_one(s.z, m[u].z, v[u].z, p[u].z, 4 * q + 2, a);
-            pn.w = peer_adam_one(s.w, m[u].w, v[u].w, p[u].w, 4 * q + 3, a);
+            const float4 pn = peer_adam4(s, m[u], v[u], p[u], q, a);
             exp_avg[q] = m[u];
             exp_avg_sq[q] = v[u];
 #pragma unroll
@@ -214,11 +223,7 @@ __global__ void __launch_bounds__(256, 2) peer_reduce_adam_mc_kernel(const float
         for (int u = 0; u < MC_UNROLL; u++) {
             const long long q = q0 + u * stride;
             if (q >= hi4) break;
-            float4 pn;
-            pn.x = peer_adam_one(s[u].x, m[u].x, v[u].x, p[u].x, 4 * q + 0, a);
-            pn.y = peer_adam_one(s[u].y, m[u].y, v[u].y, p[u].y, 4 * q + 1, a);
-            pn.z = peer_adam_one(s[u].z, m[u].z, v[u].z, p[u].z, 4 * q + 2, a);
-            pn.w = peer_adam_one(s[u].w, m[u].w, v[u].w, p[u].w, 4 * q + 3, a);
+            const float4 pn = peer_adam4(s[u], m[u], v[u], p[u], q, a);
             exp_avg[q] = m[u];
             exp_avg_sq[q] = v[u];
             mc_st(mc_param + q, pn);
@@ -263,6 +268,10 @@ static void shard_of(long long n4, int rank, int world, long long* lo4, long lon
 }  // namespace lg
 
 using namespace lg;
+
+static int peer_fill_adam(PeerAdam& a, long long n, int num_segments, const long long* segment_ends, const float* lrs,
+                          const float* lrs_b, const int* row_width, const int* row_split, float beta1, float beta2,
+                          float eps, int step, float grad_scale);
 
 extern "C" int lg_peer_alloc(size_t bytes, void** dev_ptr) {
     if (!dev_ptr || bytes == 0) {
@@ -361,21 +370,12 @@ extern "C" int lg_peer_reduce_adam(int rank, int world, void* const* grad_ptrs, 
         return LG_ERR_INVALID_ARGUMENT;
     }
     if (n == 0) return LG_OK;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     PeerAdam a;
-    a.count = num_segments;
-    for (int s = 0; s < num_segments; s++) {
-        a.end[s] = segment_ends[s];
-        a.step_a[s] = (float)((double)lrs[s] / bc1);
-        a.step_b[s] = (float)((double)(lrs_b ? lrs_b[s] : lrs[s]) / bc1);
-        a.width[s] = row_width ? row_width[s] : 1;
-        a.split[s] = row_split ? row_split[s] : 0;
+    {
+        int rc = peer_fill_adam(a, n, num_segments, segment_ends, lrs, lrs_b, row_width, row_split, beta1, beta2, eps,
+                                step, grad_scale);
+        if (rc != LG_OK) return rc;
     }
-    if (a.end[num_segments - 1] != n) {
-        set_error("lg_peer_reduce_adam: the last segment must end at n");
-        return LG_ERR_INVALID_ARGUMENT;
-    }
-    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.grad_scale = grad_scale;
     PeerPtrs g, p;
     for (int r = 0; r < world; r++) { g.p[r] = grad_ptrs[r]; p.p[r] = param_ptrs[r]; }
     long long lo4, hi4;
@@ -433,6 +433,11 @@ static int peer_fill_adam(PeerAdam& a, long long n, int num_segments, const long
         set_error("peer Adam: the last segment must end at n");
         return LG_ERR_INVALID_ARGUMENT;
     }
+    for (int s = 0; s < num_segments; s++)
+        if (a.end[s] % 4 != 0 || (a.width[s] > 1 && a.width[s] % 4 != 0)) {
+            set_error("peer Adam: segment ends and split-row widths must be multiples of 4 elements");
+            return LG_ERR_INVALID_ARGUMENT;
+        }
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.grad_scale = grad_scale;
     return LG_OK;
 }

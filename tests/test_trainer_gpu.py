@@ -194,3 +194,24 @@ def test_peer_exchange_two_gpus():
            "127.0.0.1", "--master-port", "29641", os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PEER_KERNELS_OK" in r.stdout and "PEER_TRAINER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_adam_scalar_fallback_for_unaligned_buffers():
+    """lg_adam_step on a buffer whose size / segment ends are not multiples of 4 (the float4 kernel cannot be used)"""
+    import ctypes
+    from lgdwt_b200 import _lib
+    n, cut = 1003, 501
+    gen = torch.Generator().manual_seed(4)
+    p0, g0 = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    ref_a, ref_b = p0[:cut].clone().requires_grad_(True), p0[cut:].clone().requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [ref_a], "lr": 0.01}, {"params": [ref_b], "lr": 0.002}], lr=0.0, eps=1e-15)
+    p, m, v = p0.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    ends = (ctypes.c_longlong * 2)(cut, n)
+    lrs = (ctypes.c_float * 2)(0.01, 0.002)
+    for step in range(1, 4):
+        g = (g0 * step).to(dev)
+        ref_a.grad, ref_b.grad = (g0 * step)[:cut].clone(), (g0 * step)[cut:].clone()
+        opt.step()
+        _lib.check(_lib.lib.lg_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2, ends, lrs, 0.9,
+                                         0.999, 1e-15, step, 1.0, _lib.stream_ptr(torch.device(dev))))
+    torch.testing.assert_close(p.cpu(), torch.cat([ref_a.detach(), ref_b.detach()]), rtol=2e-5, atol=1e-7)
