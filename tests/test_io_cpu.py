@@ -1,0 +1,138 @@
+"""CPU tier for the file formats either side of the path.  When /root/reference is mounted (the
+build container) the reference's OWN writer / reader functions are executed against this repo's readers / writers
+through the `plyfile` stand-in; on the GPU box only the self-consistency half runs."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lgdwt_b200 import dp, io, scenes
+
+REF_LG = "/root/reference/fs3dgs_benchmark/LGDWT-GS"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_LG), reason="reference sources not mounted")
+
+
+def _flat(P=257, seed=3):
+    g = dp.FlatGaussians(P, torch.device("cpu"))
+    g.data.copy_(torch.randn(g.data.shape, generator=torch.Generator().manual_seed(seed)))
+    return g
+
+
+def test_gaussian_ply_round_trip_and_property_order(tmp_path):
+    g = _flat()
+    path = str(tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply")
+    io.save_gaussians_ply(path, g)
+    v = io.PlyData.read(path).elements[0]
+    names = [p.name for p in v.properties]
+    assert names == io.gaussian_ply_attributes(3) and len(names) == 62 and names[6:9] == ["f_dc_0", "f_dc_1", "f_dc_2"]
+    # f_rest is channel-major in the file: f_rest_0..14 = red coefficients 1..15
+    shs = g.slab("shs").view(g.P, 16, 3)
+    np.testing.assert_array_equal(np.asarray(v["f_rest_1"]), shs[:, 2, 0].numpy())
+    np.testing.assert_array_equal(np.asarray(v["f_rest_15"]), shs[:, 1, 1].numpy())
+    g2 = io.load_gaussians_ply(path, torch.device("cpu"))
+    for name, _ in g.fields:
+        assert torch.equal(g.slab(name), g2.slab(name)), name
+
+
+def test_blender_dataset_layout_and_camera_inverse(tmp_path):
+    cams = scenes.orbit_cameras(9, 32, 24)
+    imgs = [np.full((3, 24, 32), 0.1 * k, np.float32) for k in range(9)]
+    xyz = np.random.default_rng(0).normal(size=(50, 3)).astype(np.float32)
+    counts = io.write_blender_dataset(str(tmp_path), cams, imgs, split_test_every=8,
+                                      points=(xyz, np.full((50, 3), 128, np.uint8)))
+    assert counts == {"train": 8, "test": 1}
+    tr = json.load(open(tmp_path / "transforms_train.json"))
+    assert abs(tr["camera_angle_x"] - 2 * np.arctan(cams[0].tanfovx)) < 1e-12 and len(tr["frames"]) == 8
+    # what readCamerasFromTransforms does with a frame (dataset_readers.py:342-350) gives back the camera
+    c2w = np.array(tr["frames"][3]["transform_matrix"])
+    c2w[:3, 1:3] *= -1
+    w2c = np.linalg.inv(c2w)
+    np.testing.assert_allclose(w2c.T, cams[3].viewmatrix, atol=1e-6)
+    from PIL import Image
+    im = np.array(Image.open(tmp_path / "train" / "r_3.png"))
+    assert im.shape == (24, 32, 4) and im[0, 0, 3] == 255 and abs(int(im[0, 0, 0]) - round(0.3 * 255)) <= 1
+    pc = io.PlyData.read(str(tmp_path / "points3d.ply"))["vertex"]
+    np.testing.assert_array_equal(np.asarray(pc["x"]), xyz[:, 0])
+    assert np.asarray(pc["red"]).dtype == np.uint8
+
+
+def test_cfg_args_is_evaluable(tmp_path):
+    from argparse import Namespace  # noqa: F401  (the reference evals the file with Namespace in scope)
+    io.write_cfg_args(str(tmp_path), source_path="/data/scene", sh_degree=3)
+    ns = eval(open(tmp_path / "cfg_args").read())
+    assert ns.source_path == "/data/scene" and ns.sh_degree == 3 and ns.white_background is False
+
+
+def test_ascii_and_big_endian_ply_are_readable(tmp_path):
+    p = tmp_path / "a.ply"
+    p.write_text("ply\nformat ascii 1.0\ncomment hi\nelement vertex 2\nproperty float x\nproperty uchar red\nend_header\n"
+                 "1.5 7\n-2 255\n")
+    v = io.PlyData.read(str(p))["vertex"]
+    np.testing.assert_array_equal(np.asarray(v["x"]), np.array([1.5, -2], np.float32))
+    np.testing.assert_array_equal(np.asarray(v["red"]), np.array([7, 255], np.uint8))
+    q = tmp_path / "b.ply"
+    with open(q, "wb") as f:
+        f.write(b"ply\nformat binary_big_endian 1.0\nelement vertex 1\nproperty float x\nproperty int k\nend_header\n")
+        f.write(np.array([3.25], ">f4").tobytes() + np.array([-9], ">i4").tobytes())
+    w = io.PlyData.read(str(q))["vertex"]
+    assert float(w["x"][0]) == 3.25 and int(w["k"][0]) == -9
+
+
+def _import_reference():
+    """the reference modules with `plyfile` resolved to the stand-in and the CUDA-only simple_knn stubbed"""
+    import plyfile  # noqa: F401  (compat/plyfile.py via lgdwt_b200.io's sys.path entry, or the real package)
+    knn, knn_c = types.ModuleType("simple_knn"), types.ModuleType("simple_knn._C")
+    knn_c.distCUDA2 = lambda pts: None
+    knn._C = knn_c
+    sys.modules.setdefault("simple_knn", knn)
+    sys.modules.setdefault("simple_knn._C", knn_c)
+    if REF_LG not in sys.path:
+        sys.path.insert(0, REF_LG)
+    from scene import dataset_readers, gaussian_model
+    return dataset_readers, gaussian_model
+
+
+@needs_ref
+def test_reference_readers_and_writers_interoperate(tmp_path):
+    dr, gm = _import_reference()
+    # our point cloud -> the reference's fetchPly; the reference's storePly -> our reader
+    xyz = np.random.default_rng(1).normal(size=(40, 3)).astype(np.float32)
+    rgb = np.random.default_rng(2).integers(0, 256, (40, 3)).astype(np.uint8)
+    io.store_point_cloud_ply(str(tmp_path / "ours.ply"), xyz, rgb)
+    pcd = dr.fetchPly(str(tmp_path / "ours.ply"))
+    np.testing.assert_array_equal(pcd.points, xyz)
+    np.testing.assert_allclose(pcd.colors, rgb / 255.0)
+    dr.storePly(str(tmp_path / "ref.ply"), xyz, rgb)
+    assert open(tmp_path / "ref.ply", "rb").read() == open(tmp_path / "ours.ply", "rb").read()
+    # our Gaussian PLY has the property list the reference model constructs, and the reference's save_ply output
+    # (same parameters) is byte-identical to ours
+    g = _flat(P=33)
+    model = gm.GaussianModel(3)
+    shs = g.slab("shs").view(g.P, 16, 3)
+    model._xyz, model._opacity = g.slab("xyz").clone(), g.slab("opacity").clone()
+    model._features_dc, model._features_rest = shs[:, :1, :].clone(), shs[:, 1:, :].clone()
+    model._scaling, model._rotation = g.slab("scaling").clone(), g.slab("rotation").clone()
+    assert model.construct_list_of_attributes() == io.gaussian_ply_attributes(3)
+    model.save_ply(str(tmp_path / "m" / "ref_model.ply"))
+    io.save_gaussians_ply(str(tmp_path / "m" / "our_model.ply"), g)
+    assert open(tmp_path / "m" / "ref_model.ply", "rb").read() == open(tmp_path / "m" / "our_model.ply", "rb").read()
+    # the reference's Blender reader opens the dataset this repo writes
+    cams = scenes.orbit_cameras(3, 16, 12)
+    io.write_blender_dataset(str(tmp_path / "ds"), cams, [np.zeros((3, 12, 16), np.float32)] * 3, split_test_every=0)
+    try:
+        infos = dr.readCamerasFromTransforms(str(tmp_path / "ds"), "transforms_train.json", "", False, False)
+    except TypeError as e:
+        # the reference builds its RGB image from an int8 array (dataset_readers.py:362), which Pillow >= 10 rejects
+        # before any of this repo's data is judged; the camera inverse is covered by the layout test above
+        assert "Cannot handle this data type" in str(e)
+        return
+    assert len(infos) == 3 and infos[0].width == 16 and infos[0].height == 12
+    # CameraInfo.R is the transpose of w2c's rotation, T its translation (:349-350)
+    w2c = np.asarray(cams[1].viewmatrix, np.float64).T
+    np.testing.assert_allclose(infos[1].R, w2c[:3, :3].T, atol=1e-6)
+    np.testing.assert_allclose(infos[1].T, w2c[:3, 3], atol=1e-6)
+    np.testing.assert_allclose(infos[1].FovX, 2 * np.arctan(cams[1].tanfovx), atol=1e-9)
