@@ -59,6 +59,9 @@ ImageState ImageState::from_chunk(char*& chunk, size_t W, size_t H) {
     carve(chunk, s.accum_alpha, W * H);
     carve(chunk, s.n_contrib, W * H);
     carve(chunk, s.ranges, T);
+    carve(chunk, s.tile_order, T);
+    carve(chunk, s.tile_neff, T);
+    carve(chunk, s.tile_order_bwd, T);
     return s;
 }
 size_t image_state_bytes(size_t W, size_t H) {

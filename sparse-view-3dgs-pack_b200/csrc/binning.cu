@@ -199,6 +199,65 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const uint
     }
 }
 
+// Tile launch order for the blend kernels: one block buckets the T tiles by key (1024 buckets scaled to the largest
+// key) and lists them heaviest bucket first.  keys[t * key_stride + key_offset] with (stride 2, offset: y - x computed
+// here) for ranges, (stride 1) for tile_neff.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint32_t* __restrict__ keys, int key_stride,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_cnt[1024];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    s_cnt[tid] = 0;
+    if (tid == 0) s_max = 1;
+    __syncthreads();
+    auto key_of = [&](int t) -> uint32_t {
+        return key_stride == 2 ? keys[2 * t + 1] - keys[2 * t] : keys[t];
+    };
+    uint32_t m = 0;
+    for (int t = tid; t < T; t += 1024) m = max(m, key_of(t));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const float scale = 1023.0f / (float)s_max;
+    // bucket 0 = heaviest
+    for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)key_of(t) * scale), 1023)], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 bucket counts
+    const uint32_t c = s_cnt[tid];
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], z = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+            if ((int)lane >= o) z += y;
+        }
+        s_warp[lane] = z - w;
+    }
+    __syncthreads();
+    s_cnt[tid] = x - c + s_warp[warp];
+    __syncthreads();
+    for (int t = tid; t < T; t += 1024) {
+        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)key_of(t) * scale), 1023)], 1u);
+        order[pos] = (uint32_t)t;
+    }
+}
+
+int launch_tile_order(int T, const uint32_t* keys, int key_stride, uint32_t* order, cudaStream_t stream) {
+    tile_order_kernel<<<1, 1024, 0, stream>>>(T, keys, key_stride, order);
+    LG_LAUNCH_CHECK(false, stream);
+    return LG_OK;
+}
+
 // inspection only (lg_state_read "point_list_keys"): the reference's sorted 64-bit keys
 __global__ void __launch_bounds__(256) rebuild_keys_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
                                                            const uint32_t* __restrict__ point_list,
@@ -229,7 +288,7 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
     const int gx = num_tiles_x(W), gy = num_tiles_y(H);
     const int T = gx * gy;
     LG_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, stream));
-    if (R <= 0) return LG_OK;
+    if (R <= 0) return launch_tile_order(T, reinterpret_cast<const uint32_t*>(img.ranges), 2, img.tile_order, stream);
     const int end_bit = higher_msb((uint32_t)T);
     const int passes = radix_sort_num_passes(0, end_bit);
     // ping-pong so that the sorted list ends in tile_keys / point_list
@@ -260,7 +319,7 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
     if (rc != LG_OK) return rc;
     tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);
     LG_LAUNCH_CHECK(debug, stream);
-    return LG_OK;
+    return launch_tile_order(T, reinterpret_cast<const uint32_t*>(img.ranges), 2, img.tile_order, stream);
 }
 
 int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-    const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec) {
+    const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec,
+    const uint32_t* __restrict__ tile_order) {
     constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
     constexpr int VC = 6 + (INVD ? 1 : 0);      // first colour slot among the reduced values
     // one staged entry = three float4: (mean.x, mean.y, Gaussian id, 1/depth) (conic a, b, c, opacity) (colours, C <= 4),
@@ -77,14 +78,15 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     __shared__ uint32_t s_max;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t tile = tile_order[blockIdx.x];  // deepest tiles first
+    const uint32_t tile_x = tile % (uint32_t)grid_x, tile_y = tile / (uint32_t)grid_x;
     const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
     const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
-    const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
+    const uint2 range = ranges[tile];
 
     const float T_final = inside ? final_Ts[pix_id] : 0.0f;
     float T = T_final;
@@ -231,11 +233,14 @@ int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, co
                           const float* dL_dpix, const float* dL_dinvdepth_pix, float* grad_scratch, bool debug,
                           cudaStream_t stream) {
     LG_CUDA(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * LG_REC * (size_t)P, stream));
-    const dim3 grid(num_tiles_x(W), num_tiles_y(H), 1), block(LG_TILE_PIX, 1, 1);
+    const int gx = num_tiles_x(W), T = gx * num_tiles_y(H);
+    int rc = launch_tile_order(T, img.tile_neff, 1, img.tile_order_bwd, stream);
+    if (rc != LG_OK) return rc;
+    const dim3 grid(T, 1, 1), block(LG_TILE_PIX, 1, 1);
 #define LG_LAUNCH_BWD(CH, INVD)                                                                                    \
     blend_backward_kernel<CH, INVD><<<grid, block, 0, stream>>>(                                                     \
-        img.ranges, b.point_list, W, H, (int)grid.x, background, g.means2D, g.conic_opacity, features, g.depths,     \
-        img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch)
+        img.ranges, b.point_list, W, H, gx, background, g.means2D, g.conic_opacity, features, g.depths,              \
+        img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch, img.tile_order_bwd)
     const bool invd = dL_dinvdepth_pix != nullptr;
     switch (C) {
         case 1: if (invd) LG_LAUNCH_BWD(1, true); else LG_LAUNCH_BWD(1, false); break;

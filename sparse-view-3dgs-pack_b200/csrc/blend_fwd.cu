@@ -30,15 +30,19 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth) {
+    const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth,
+    const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff) {
     // one staged entry = three float4: (mean.x, mean.y, -, 1/depth) (conic a, b, c, opacity) (colours, C <= 4), read
     // as warp-wide broadcasts from a single base address
     __shared__ float4 s_ent[BLEND_BATCH * 3];
     __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
     __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
+    __shared__ uint32_t s_neff;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t tile = tile_order[blockIdx.x];  // heaviest tiles first
+    const uint32_t tile_x = tile % (uint32_t)grid_x, tile_y = tile / (uint32_t)grid_x;
+    if (tid == 0) s_neff = 0;
     const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
     const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
 
-    const uint2 range = ranges[tile_y * (uint32_t)grid_x + tile_x];
+    const uint2 range = ranges[tile];
     const int rounds = (int)((range.y - range.x + BLEND_BATCH - 1) / BLEND_BATCH);
     int to_do = (int)(range.y - range.x);
 
@@ -130,6 +134,12 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
         }
     }
 
+    // the backward's launch order key: how deep into the list this tile's pixels reached
+    const uint32_t warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
+    __syncthreads();  // s_neff initialised (every thread passes here: the loop above has no early return)
+    if (lane == 0 && warp_max) atomicMax(&s_neff, warp_max);
+    __syncthreads();
+    if (tid == 0) tile_neff[tile] = s_neff;
     if (inside) {
         final_T[pix_id] = T;
         n_contrib[pix_id] = last_contributor;
@@ -197,11 +207,13 @@ int launch_blend_count(int W, int H, const GeometryState& g, const BinningState&
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream) {
-    const dim3 grid(num_tiles_x(W), num_tiles_y(H), 1), block(LG_TILE_PIX, 1, 1);
+    const int gx = num_tiles_x(W);
+    const dim3 grid(gx * num_tiles_y(H), 1, 1), block(LG_TILE_PIX, 1, 1);
 #define LG_LAUNCH_FWD(CH)                                                                                          \
-    blend_forward_kernel<CH><<<grid, block, 0, stream>>>(img.ranges, b.point_list, W, H, (int)grid.x, g.means2D,     \
+    blend_forward_kernel<CH><<<grid, block, 0, stream>>>(img.ranges, b.point_list, W, H, gx, g.means2D,              \
                                                          features, g.conic_opacity, g.depths, img.accum_alpha,       \
-                                                         img.n_contrib, background, out_color, out_invdepth)
+                                                         img.n_contrib, background, out_color, out_invdepth,         \
+                                                         img.tile_order, img.tile_neff)
     switch (C) {
         case 1: LG_LAUNCH_FWD(1); break;
         case 2: LG_LAUNCH_FWD(2); break;

@@ -76,6 +76,11 @@ struct ImageState {
     float* accum_alpha;   // W*H final transmittance
     uint32_t* n_contrib;  // W*H
     uint2* ranges;        // T
+    // launch order of the tiles in the blend kernels, heaviest first (longest-processing-time-first scheduling: the
+    // hardware hands out blocks in blockIdx order, so the long tiles of the image centre no longer form the tail)
+    uint32_t* tile_order;      // T: forward, by list length
+    uint32_t* tile_neff;       // T: entries that reached some pixel of the tile (max n_contrib), written by the forward
+    uint32_t* tile_order_bwd;  // T: backward, by tile_neff
     static ImageState from_chunk(char*& chunk, size_t W, size_t H);
 };
 size_t image_state_bytes(size_t W, size_t H);
@@ -123,6 +128,8 @@ int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int
                    ImageState& img, bool debug, cudaStream_t stream);
 int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,
                         cudaStream_t stream);
+// order[0..T) = tile indices by descending key (bucketed; ties in no particular order) — scheduling only
+int launch_tile_order(int T, const uint32_t* keys, int key_stride, uint32_t* order, cudaStream_t stream);
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream);
