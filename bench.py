@@ -15,7 +15,8 @@ inside the timed step — the path's only exchange step.  ms/view = ms_per_step 
 
 One JSON line on rank 0.  `value`: operator fwd+bwd with all inputs resident in HBM.  `e2e`: the same step through
 the public torch operator with the step's inputs (camera matrices + ground-truth image) copied from pinned host
-memory, an L1 loss against that image, backward, and a device->host read of the loss.  `roofline`: the dominant
+memory, an L1 loss against that image (`lgdwt_b200.fused_l1_loss` here, the stock torch expression in the
+reference arm), backward, and a device->host read of the loss.  `roofline`: the dominant
 kernel against its bound, timed live with CUDA events on the launching stream; `stages`: every stage likewise.
 `cpu_baseline`: the CPU oracle (a port: the reference has no CPU rasterizer) timed on this box's cores.
 """
@@ -139,6 +140,8 @@ class Stepper:
         if impl == "ours":
             from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, GradSinks
             self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
+            from lgdwt_b200 import fused_l1_loss
+            self.l1 = fused_l1_loss
             self.sinks = GradSinks(views["means3D"], views["shs"], views["opacities"], views["scales"],
                                    views["rotations"])
         else:
@@ -198,7 +201,10 @@ class Stepper:
                 self.copy_done[v].record(self.copy_stream)
             color, radii, invd = self.render(cam, v == 0)
             main.wait_event(self.copy_done[v])
-            loss = (color - self.dev_gt[v]).abs().mean()
+            if self.impl == "ours":   # this repo's public loss op; the reference arm keeps the stock torch expression
+                loss = self.l1(color, self.dev_gt[v])
+            else:
+                loss = (color - self.dev_gt[v]).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
             loss.backward()
             total += loss.detach()
         self.exchange()

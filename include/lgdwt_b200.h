@@ -86,8 +86,9 @@ int lg_rasterize_forward(
  * zero them first (the reference requires torch::zeros, rasterize_points.cu:163-172).
  *   dL_dpix (channels,H,W); dL_dinvdepth_pix (1,H,W) or NULL.
  *   dL_dmean2D (P,3) [xy in NDC-scaled units, z = 0]; dL_dconic (P,4) [a,b,unused,c as in the reference];
- *   dL_dopacity (P); dL_dcolor (P,channels); dL_dinvdepth (P) or NULL; dL_dmean3D (P,3); dL_dcov3D (P,6);
- *   dL_dsh (P,M,3) or NULL; dL_dscale (P,3); dL_drot (P,4).  */
+ *   dL_dopacity (P); dL_dcolor (P,channels) — may be NULL unless colors_precomp is given; dL_dinvdepth (P) or NULL;
+ *   dL_dmean3D (P,3); dL_dcov3D (P,6) — may be NULL unless cov3D_precomp is given (intermediate results nobody reads
+ *   are then not written: 36 B/Gaussian at 3 channels); dL_dsh (P,M,3) or NULL; dL_dscale (P,3); dL_drot (P,4).  */
 int lg_rasterize_backward(
     int P, int D, int M, int R, int channels,
     const float* background,
@@ -317,6 +318,11 @@ int lg_densify_stats(int P, const float* grad2D, const int* radii, float* grad_a
                      float* max_radii2D, void* stream);
 /* opacity <- inverse_sigmoid(min(sigmoid(opacity), 0.01)), Adam moments of the opacity slab <- 0 */
 int lg_reset_opacity(int P, float* opacity, float* exp_avg, float* exp_avg_sq, void* stream);
+
+/* l1_loss alone (LG/utils/loss_utils.py:40-41): out_loss[0] = mean |pred - gt| over n elements, one launch;
+ * dL_dpred = g * sign(pred - gt) / n (g: device scalar), one launch.  scratch16: 16 bytes of device scratch. */
+int lg_l1_loss_forward(const float* pred, const float* gt, long long n, float* out_loss, char* scratch16, void* stream);
+int lg_l1_loss_backward(const float* pred, const float* gt, long long n, const float* g, float* dL_dpred, void* stream);
 
 /* Fused photometric terms of the iteration's base loss (LG/train.py:128,182-188): out_losses[0] = mean |pred - gt|
  * (l1_loss, LG/utils/loss_utils.py:40-41), out_losses[1] = mean SSIM map (ssim/_ssim, LG/utils/loss_utils.py:58-86:

@@ -237,8 +237,9 @@ int lg_rasterize_backward_raw(int P, int D, int M, int R, int channels, const fl
         return LG_ERR_INVALID_ARGUMENT;
     }
     if (P == 0) return LG_OK;
-    if (!geometry_state || !binning_state || !image_state || !dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor ||
-        !dL_dmean3D || !dL_dcov3D || !means3D || !opacities || !background || !viewmatrix || !projmatrix || !campos) {
+    if (!geometry_state || !binning_state || !image_state || !dL_dpix || !dL_dmean2D || !dL_dopacity ||
+        !dL_dmean3D || !means3D || !opacities || !background || !viewmatrix || !projmatrix || !campos ||
+        (colors_precomp && !dL_dcolor) || (cov3D_precomp && !dL_dcov3D)) {
         set_error("lg_rasterize_backward: missing required pointer");
         return LG_ERR_INVALID_ARGUMENT;
     }

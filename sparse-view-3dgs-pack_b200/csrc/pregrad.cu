@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
     a.dL_dmean2D[3 * i + 1] = r[1];
     a.dL_dmean2D[3 * i + 2] = 0.0f;
     if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(r[2], r[3], 0.0f, r[4]);
-    for (int c = 0; c < C; c++) a.dL_dcolor[i * C + c] = r[7 + c];
+    if (a.dL_dcolor)  // only a colors_precomp caller needs the per-Gaussian colour gradient in memory
+        for (int c = 0; c < C; c++) a.dL_dcolor[i * C + c] = r[7 + c];
     if (a.dL_dinvdepth) a.dL_dinvdepth[i] = r[6];
 
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -412,7 +413,8 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
     a.dL_dmean3D[3 * i + 1] = dmean[1];
     a.dL_dmean3D[3 * i + 2] = dmean[2];
 #pragma unroll
-    for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * i + k] = dcov[k];
+    if (a.dL_dcov3D)  // only a cov3D_precomp caller needs it in memory
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * i + k] = dcov[k];
     }  // idx < P
 
     if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores

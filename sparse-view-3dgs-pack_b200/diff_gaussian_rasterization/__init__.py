@@ -169,10 +169,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise RuntimeError("grad_sinks.%s must be a contiguous fp32 CUDA tensor of shape %s" % (name, shape))
             dL_dmeans3D, dL_dsh, dL_dopacity = sinks.means3D, sinks.shs, sinks.opacities
             dL_dscales, dL_drotations = sinks.scales, sinks.rotations
-            dL_dmeans2D, dL_dcolors, dL_dcov3D = new(P, 3), new(P, C), new(P, 6)
+            dL_dmeans2D, dL_dcolors, dL_dcov3D = new(P, 3), None, None
         else:
             dL_dmeans3D, dL_dmeans2D = new(P, 3), new(P, 3)
-            dL_dcolors, dL_dopacity, dL_dcov3D = new(P, C), new(P, 1), new(P, 6)
+            dL_dopacity = new(P, 1)
+            # per-Gaussian colour / covariance gradients are intermediates unless the caller supplied those inputs
+            dL_dcolors = new(P, C) if has_colors else None
+            dL_dcov3D = new(P, 6) if has_cov else None
             dL_dsh = new(P, M, 3) if has_sh else None
             dL_dscales = new(P, 3) if has_scales else None
             dL_drotations = new(P, 4) if has_scales else None

@@ -4,4 +4,4 @@ operator surface: the ctypes binding (`_lib`), the fused Haar-DWT loss op (`dwt_
 view-parallel trainer (`dp`)."""
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .dwt_loss import DWTLossConfig, fused_dwt_loss  # noqa: F401
-from .photometric import fused_photometric_loss  # noqa: F401
+from .photometric import fused_l1_loss, fused_photometric_loss  # noqa: F401

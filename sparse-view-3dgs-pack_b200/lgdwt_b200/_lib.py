@@ -118,6 +118,10 @@ def _load():
                                            ctypes.POINTER(i), ctypes.POINTER(i), f, f, f, i, f, _P]
     lib.lg_peer_allreduce_mc.restype = i
     lib.lg_peer_allreduce_mc.argtypes = [i, i, _P, ctypes.c_longlong, f, _P]
+    lib.lg_l1_loss_forward.restype = i
+    lib.lg_l1_loss_forward.argtypes = [_P, _P, ctypes.c_longlong, _P, _P, _P]
+    lib.lg_l1_loss_backward.restype = i
+    lib.lg_l1_loss_backward.argtypes = [_P, _P, ctypes.c_longlong, _P, _P, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

@@ -53,3 +53,41 @@ def fused_photometric_loss(pred, gt):
     The reference's base loss is `(1 - lambda_dssim) * l1 + lambda_dssim * (1 - ssim)` (LG/train.py:188).
     Differentiable w.r.t. `pred` only."""
     return _FusedPhotometric.apply(pred, gt)
+
+
+class _FusedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt):
+        if not pred.is_cuda:
+            raise RuntimeError("fused_l1_loss (B200-native): CUDA tensors only; there is no CPU path")
+        if pred.shape != gt.shape:
+            raise RuntimeError("fused_l1_loss: pred and gt must have the same shape")
+        pred_c, gt_c = pred.contiguous().float(), gt.contiguous().float()
+        dev = pred_c.device
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib.lg_l1_loss_forward(pred_c.data_ptr(), gt_c.data_ptr(), pred_c.numel(), out.data_ptr(),
+                                             scratch.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, RuntimeError)
+        ctx.save_for_backward(pred_c, gt_c)
+        ctx.in_shape = pred.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred_c, gt_c = ctx.saved_tensors
+        dev = pred_c.device
+        g = g.reshape(()).float().contiguous()
+        grad = torch.empty_like(pred_c)
+        with torch.cuda.device(dev):
+            rc = _lib.lib.lg_l1_loss_backward(pred_c.data_ptr(), gt_c.data_ptr(), pred_c.numel(), g.data_ptr(),
+                                              grad.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, RuntimeError)
+        return grad.reshape(ctx.in_shape), None
+
+
+def fused_l1_loss(pred, gt):
+    """mean |pred - gt| (l1_loss, LG/utils/loss_utils.py:40-41) in one launch forward and one backward;
+    differentiable w.r.t. `pred` only."""
+    return _FusedL1.apply(pred, gt)

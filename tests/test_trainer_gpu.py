@@ -215,3 +215,18 @@ def test_adam_scalar_fallback_for_unaligned_buffers():
         _lib.check(_lib.lib.lg_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2, ends, lrs, 0.9,
                                          0.999, 1e-15, step, 1.0, _lib.stream_ptr(torch.device(dev))))
     torch.testing.assert_close(p.cpu(), torch.cat([ref_a.detach(), ref_b.detach()]), rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(3, 800, 800), (3, 37, 53), (1, 4, 64, 64), (7,)])
+def test_fused_l1_loss_matches_torch(shape):
+    from lgdwt_b200 import fused_l1_loss
+    gen = torch.Generator(device=dev).manual_seed(sum(shape))
+    gt = torch.rand(shape, device=dev, generator=gen)
+    pred = (gt + 0.1 * torch.randn(shape, device=dev, generator=gen)).requires_grad_(True)
+    with torch.no_grad():
+        pred[..., :2] = gt[..., :2]          # exact ties: sign(0) = 0 in both
+    ref = pred.detach().clone().requires_grad_(True)
+    (3.0 * fused_l1_loss(pred, gt)).backward()
+    (3.0 * (ref - gt).abs().mean()).backward()
+    torch.testing.assert_close(fused_l1_loss(pred, gt), (ref - gt).abs().mean(), rtol=2e-6, atol=1e-8)
+    torch.testing.assert_close(pred.grad, ref.grad, rtol=1e-6, atol=0)
