@@ -64,18 +64,31 @@ class PeerExchange:
         self._flags = arr(bases)
         self._grads = arr([b + _FLAG_BYTES for b in bases])
         self._params = arr([b + _FLAG_BYTES + 4 * self.n for b in bases])
-        dist.barrier(group=group)  # every rank has mapped every block before anyone uses (or frees) one
+        # both set-up paths end in a collective (_agree / rendezvous): every rank has mapped every block before anyone
+        # uses (or frees) one
+
+    def _agree(self, ok, what):
+        """collective AND over the ranks: a rank that failed locally must not leave the others waiting inside the
+        next collective (rendezvous / handle exchange), so every step that can fail is followed by one of these"""
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            raise RuntimeError("%s failed on %s" % (what, "this rank" if not ok else "a peer rank"))
 
     def _init_symmetric(self):
-        import torch.distributed._symmetric_memory as symm
-        grp = self.group if self.group is not None else dist.group.WORLD
-        total = _FLAG_BYTES // 4 + 2 * self.n
-        self._symm_tensor = symm.empty(total, dtype=torch.float32, device=self.device)
-        self._symm_tensor.zero_()
-        torch.cuda.synchronize(self.device)
+        err = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            total = _FLAG_BYTES // 4 + 2 * self.n
+            self._symm_tensor = symm.empty(total, dtype=torch.float32, device=self.device)
+            self._symm_tensor.zero_()
+            torch.cuda.synchronize(self.device)
+        except Exception as e:
+            err = e
+        self._agree(err is None, "symmetric-memory allocation (%s)" % err)
         h = self._symm_handle = symm.rendezvous(self._symm_tensor, grp.group_name)
-        if not h.multicast_ptr:
-            raise RuntimeError("symmetric memory has no multicast mapping on this system")
+        self._agree(bool(h.multicast_ptr), "NVSwitch multicast mapping")
         self.mc_base = int(h.multicast_ptr)
         self.grad = self._symm_tensor[_FLAG_BYTES // 4:_FLAG_BYTES // 4 + self.n]
         self.param = self._symm_tensor[_FLAG_BYTES // 4 + self.n:]
@@ -85,22 +98,34 @@ class PeerExchange:
         blk = self._blk = _Block()
         nbytes = _FLAG_BYTES + 2 * 4 * self.n
         base = ctypes.c_void_p()
+        handle, err = None, None
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib.lg_peer_alloc(nbytes, ctypes.byref(base)), RuntimeError)
-            blk.base = base.value
-            handle = ctypes.create_string_buffer(64)
-            _lib.check(_lib.lib.lg_peer_export(blk.base, handle), RuntimeError)
+            try:
+                _lib.check(_lib.lib.lg_peer_alloc(nbytes, ctypes.byref(base)), RuntimeError)
+                blk.base = base.value
+                buf = ctypes.create_string_buffer(64)
+                _lib.check(_lib.lib.lg_peer_export(blk.base, buf), RuntimeError)
+                handle = bytes(buf.raw)
+            except Exception as e:
+                err = e
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            dist.all_gather_object(handles, handle, group=self.group)   # every rank takes part, failed or not
+            if any(h is None for h in handles):
+                raise RuntimeError("CUDA IPC export failed on rank(s) %s (%s)" %
+                                   ([r for r, h in enumerate(handles) if h is None], err))
             bases = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    bases.append(blk.base)
-                    continue
-                m = ctypes.c_void_p()
-                _lib.check(_lib.lib.lg_peer_open(h, ctypes.byref(m)), RuntimeError)
-                blk.mapped.append(m.value)
-                bases.append(m.value)
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        bases.append(blk.base)
+                        continue
+                    m = ctypes.c_void_p()
+                    _lib.check(_lib.lib.lg_peer_open(h, ctypes.byref(m)), RuntimeError)
+                    blk.mapped.append(m.value)
+                    bases.append(m.value)
+            except Exception as e:
+                err = e
+            self._agree(err is None, "mapping a peer's block (%s)" % err)
         self.grad = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES, self.n, blk), device=self.device)
         self.param = torch.as_tensor(_DeviceArray(blk.base + _FLAG_BYTES + 4 * self.n, self.n, blk), device=self.device)
         return bases
