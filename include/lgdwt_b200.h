@@ -257,7 +257,7 @@ int lg_adam_step_split(float* param, const float* grad, float* exp_avg, float* e
  *   lg_peer_barrier        flag exchange between the `world` ranks on `stream` (flag_ptrs[q] = rank q's array of 16
  *                          u32 words (world <= 8), mapped here; `epoch` must grow by one per call); orders every rank's earlier
  *                          work on its stream before every rank's later work
- *   lg_peer_check          host-side: LG_ERR_CUDA if a barrier timed out (~2 s) since the last check
+ *   lg_peer_check          host-side: LG_ERR_CUDA if a barrier timed out (~30 s) since the last check
  *   lg_peer_reduce_adam    rank's shard = float4 range [n/4*rank/world, n/4*(rank+1)/world): g = sum_r grad_r (rank
  *                          order), Adam (lg_adam_step_split semantics; moments touched by the owner only), new
  *                          parameters stored into all ranks' parameter buffers.  Call between two lg_peer_barrier.

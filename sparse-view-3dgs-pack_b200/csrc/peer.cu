@@ -16,7 +16,7 @@
 // release/acquire before (all buckets complete) and after (all parameter shards delivered) the kernel.
 //
 // Buffers live in cudaMalloc memory exported with CUDA IPC (lg_peer_alloc/export/open) — one process per GPU, no
-// NVSHMEM in this image.  A barrier that does not complete within ~2 s raises LG_ERR_CUDA on the host side at the
+// NVSHMEM in this image.  A barrier that does not complete within ~30 s raises LG_ERR_CUDA on the host side at the
 // next lg_peer_check instead of hanging the GPU.
 #include "common.cuh"
 
@@ -46,7 +46,7 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int rank, int world, unsigne
     const unsigned* mine = (const unsigned*)flags.p[rank] + t;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s at 1.9 GHz: a peer died or never arrived
+        if (clock64() - t0 > 60000000000ll) {  // ~30 s at 1.9 GHz: a peer died or never arrived
             atomicExch(status, 1u);
             break;
         }

@@ -173,3 +173,54 @@ def test_flat_gaussians_adam_matches_torch_optim():
         g.adam_step(cfg)
     for n in dp.GROUPS:
         torch.testing.assert_close(g.field(n), ref_params[n].detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_flat_gaussians_layout_padding_and_group_views():
+    """slabs start at (floats before) x stride with stride = P rounded up to 4; f_dc / f_rest are column ranges of the
+    SH slab whose rows are the rasterizer's (M, 3) layout; Adam segments follow the slabs"""
+    from lgdwt_b200 import dp
+    g = dp.FlatGaussians(10, torch.device("cpu"))
+    assert g.stride == 12 and g.floats == 59 and g.data.numel() == 59 * 12 == g.grad.numel()
+    offs = {n: g._slices[n][0] for n, _ in g.fields}
+    assert offs == {"xyz": 0, "shs": 3 * 12, "opacity": 51 * 12, "scaling": 52 * 12, "rotation": 55 * 12}
+    assert all(o % 4 == 0 for o in offs.values())
+    g.slab("shs").copy_(torch.arange(10 * 48, dtype=torch.float32).view(10, 48))
+    shs = g.slab("shs").view(10, 16, 3)
+    assert torch.equal(g.field("f_dc"), shs[:, 0, :]) and torch.equal(g.field("f_rest"), shs[:, 1:, :].reshape(10, 45))
+    g.field("f_dc").add_(1000.0)           # group views write through to the flat buffer
+    assert float(g.data[offs["shs"]]) == 1000.0
+    assert not g.data[offs["shs"] + 10 * 48: offs["opacity"]].any()   # padding rows untouched
+    ends, lr_a, lr_b, width, split = g.adam_segments(dp.AdamConfig())
+    assert list(ends) == [3 * 12, 51 * 12, 52 * 12, 55 * 12, 59 * 12]
+    assert list(width) == [1, 48, 1, 1, 1] and list(split) == [0, 3, 0, 0, 0]
+    assert abs(lr_a[1] - 0.0025) < 1e-9 and abs(lr_b[1] - 0.0025 / 20) < 1e-9 and lr_a[0] == lr_b[0]
+    for P in (0, 1, 4, 5):
+        h = dp.FlatGaussians(P, torch.device("cpu"))
+        assert h.stride == (P + 3) // 4 * 4 and h.slab("rotation").shape == (P, 4)
+    g2 = dp.FlatGaussians(7, torch.device("cpu"), sh_degree=1)
+    assert g2.floats == 11 + 12 and g2.M == 4 and g2.slab("shs").shape == (7, 12)
+
+
+def test_density_control_schedule_follows_train_py():
+    """which iterations densify / reset opacity / use the size threshold (LG/train.py:265-276), and that the Adam
+    update of a densification iteration is dropped"""
+    from lgdwt_b200 import dp
+    g = dp.FlatGaussians(8, torch.device("cpu"))
+    calls = []
+    cfg = dp.DensifyConfig(densify_from_iter=4, densify_until_iter=13, densification_interval=3, opacity_reset_interval=6)
+
+    def render(act, cam, bg):
+        return (act["means3D"].sum() + act["opacities"].sum()).view(1, 1, 1), torch.ones(8, dtype=torch.int32)
+
+    tr = dp.ViewParallelTrainer(g, render_fn=render, loss_fn=lambda img, gt: img.sum(), densify=cfg,
+                                densify_fn=lambda g_, st, c, mss, gen: calls.append(("densify", tr.iteration, mss)),
+                                stats_fn=lambda *a: None, reset_opacity_fn=lambda g_: calls.append(("reset", tr.iteration)))
+    steps_before = []
+    for _ in range(15):
+        before = g.step_count
+        tr.step([{}], [None], None)
+        steps_before.append(g.step_count - before)
+    assert [c for c in calls if c[0] == "densify"] == [("densify", 6, None), ("densify", 9, 20.0), ("densify", 12, 20.0)]
+    assert [c for c in calls if c[0] == "reset"] == [("reset", 6), ("reset", 12)]
+    # iterations 6, 9 and 12 rebuilt the set: no optimizer step there (the reference's new Parameters have no .grad)
+    assert [i + 1 for i, s in enumerate(steps_before) if s == 0] == [6, 9, 12]
