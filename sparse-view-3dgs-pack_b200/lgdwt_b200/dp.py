@@ -323,6 +323,7 @@ class ViewParallelTrainer:
         """peer exchange keeps every Adam moment only on its owner rank; a densification needs them everywhere"""
         if self.peer is None:
             return
+        self.peer.check()  # a sync point anyway: surface a timed-out flag barrier before the set is rebuilt
         n4 = self.g.data.numel() // 4
         lo, hi = 4 * (n4 * self.rank // self.world), 4 * (n4 * (self.rank + 1) // self.world)
         for buf in (self.g.exp_avg, self.g.exp_avg_sq):
@@ -424,7 +425,10 @@ class ViewParallelTrainer:
             self.g.adam_step(self.adam, grad_scale=grad_scale)
 
     def replicas_in_sync(self):
-        """parameter count and checksum min == max over ranks"""
+        """parameter count and checksum min == max over ranks; also raises if a peer-exchange barrier
+        timed out since the last check"""
+        if self.peer is not None:
+            self.peer.check()
         c = torch.stack([self.g.checksum(), torch.tensor(float(self.g.P), dtype=torch.float64, device=self.g.device)])
         if not (self.distributed and self.world > 1):
             return True
