@@ -289,8 +289,8 @@ def cpu_baseline(sc, cam):
     oracle.rasterize_backward(f, dL_dpix=dL, **kw)
     t2 = time.perf_counter()
     return {"value": 1.0 / (t2 - t0), "unit": "views/s", "cores": oracle.num_threads(), "kind": "port",
-            "sample": "1 view fwd+bwd of the same 1M-Gaussian 800x800 scene (fwd %.2f s, bwd %.2f s; blend backward "
-                      "is single-threaded)" % (t1 - t0, t2 - t1)}
+            "sample": "1 view fwd+bwd of the same 1M-Gaussian 800x800 scene (fwd %.2f s, bwd %.2f s; OpenMP over "
+                      "Gaussians / tiles, the radix sort is single-threaded)" % (t1 - t0, t2 - t1)}
 
 
 def image_loss_section(device, hbm_peak):
