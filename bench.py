@@ -5,8 +5,9 @@ Metric (BASELINE.json): rasterize forward+backward per view at 1 M Gaussians, 80
 whole-job views/s.  A step is a batch of VIEWS_PER_RANK = 4 views per rank (8 ranks x 4 = the 32-view batch of
 BASELINE config 5; per-rank work is the same at every N: weak scaling by camera view): every view is rendered and
 back-propagated, the parameter gradients (59 floats = 236 B per Gaussian) of the rank's views are accumulated in one
-flat bucket by the backward kernel itself, and at N > 1 the bucket is summed over ranks with ONE NCCL all-reduce
-inside the timed step — the path's only exchange step.  ms/view = ms_per_step / 4 (also printed as ms_per_view).
+flat bucket by the backward kernel itself, and at N > 1 the bucket is summed over ranks with ONE all-reduce inside
+the timed step — the path's only exchange step (this repo's peer-memory kernel over NVLink, csrc/peer.cu; NCCL when the
+ranks cannot map each other's memory or with LGDWT_EXCHANGE=nccl).  ms/view = ms_per_step / 4 (also printed as ms_per_view).
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
