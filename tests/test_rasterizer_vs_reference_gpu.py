@@ -173,3 +173,43 @@ def test_mark_visible_matches_reference():
     lib.ref_mark_visible(pts.shape[0], pts.data_ptr(), c["viewmatrix"].data_ptr(), c["projmatrix"].data_ptr(), ref.data_ptr())
     torch.cuda.synchronize()
     assert bool((mine == ref).all()) and 0 < int(mine.sum()) < pts.shape[0]
+
+
+@pytest.mark.parametrize("sh_degree,scale_modifier,debug", [(0, 1.0, False), (1, 1.0, False), (2, 1.0, True),
+                                                            (3, 0.6, False), (1, 1.7, True)])
+def test_active_sh_degree_scale_modifier_and_debug(sh_degree, scale_modifier, debug):
+    """the states a real training run goes through before it reaches degree 3 (active_sh_degree grows every 1000
+    iterations, LG/train.py:105-107, with all 16 coefficients allocated), the viewer's scale_modifier, and the debug
+    flag: forward state bit-exact, image and gradients within the bars"""
+    _need_ref()
+    sc = scenes.trained_like_scene(30_000, seed=9, log_scale_mean=np.log(0.02))
+    cam = scenes.look_at_camera(320, 208, 0.6911, 0.6911 * 208 / 320, (0.3, -0.2, -4.03))
+    t, c = helpers.scene_to_torch(sc), helpers.cam_to_torch(cam)
+    bg = torch.tensor([0.2, 0.1, 0.9], device="cuda")
+    kw = dict(sh_degree=sh_degree, scale_modifier=scale_modifier, debug=debug)
+    ours = helpers.run_ours(t, c, cam, bg, **kw)
+    ref = helpers.run_ref(t, c, cam, bg, **kw)
+    assert ours["num_rendered"] == ref["num_rendered"] > 0
+    vis = ref["radii"] > 0
+    _assert_bit_equal("radii", ours["radii"], ref["radii"])
+    _assert_bit_equal("rgb", ours["rgb"].view(-1, 3), ref["rgb"].view(-1, 3), vis)
+    _assert_bit_equal("clamped", ours["clamped"].view(-1, 3), ref["clamped"].view(-1, 3), vis)
+    _assert_bit_equal("conic_opacity", ours["conic_opacity"].view(-1, 4), ref["conic_opacity"].view(-1, 4), vis)
+    _assert_bit_equal("point_list_keys", ours["point_list_keys"], ref["point_list_keys"])
+    _assert_bit_equal("point_list", ours["point_list"], ref["point_list"])
+    _assert_bit_equal("n_contrib", ours["n_contrib"], ref["n_contrib"])
+    _assert_bit_equal("final_T", ours["final_T"], ref["final_T"])
+    assert float((ours["color"] - ref["color"]).abs().max()) <= IMG_ATOL
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    dL_dpix = torch.randn((3, cam.image_height, cam.image_width), device="cuda", generator=gen)
+    mine = helpers.backward_ours(t, c, cam, bg, ours, dL_dpix, None, **kw)
+    refs = [helpers.backward_ref(t, c, cam, bg, ref, dL_dpix, None, **kw) for _ in range(3)]
+    for name in ("dL_dmean2D", "dL_dopacity", "dL_dmean3D", "dL_dsh", "dL_dscale", "dL_drot"):
+        r = torch.stack([x[name] for x in refs]).double().mean(0)
+        e = float((mine[name].double() - r).abs().max() / max(float(r.abs().max()), 1e-12))
+        assert e <= GRAD_RTOL, "%s relative error %g (degree %d)" % (name, e, sh_degree)
+    # coefficients above the active degree receive exactly zero gradient on both sides
+    used = (sh_degree + 1) ** 2
+    if used < 16:
+        assert not mine["dL_dsh"].view(-1, 16, 3)[:, used:, :].any()
+        assert not refs[0]["dL_dsh"].view(-1, 16, 3)[:, used:, :].any()
