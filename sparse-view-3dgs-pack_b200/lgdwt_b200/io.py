@@ -1,6 +1,6 @@
 """File formats either side of the training path: Gaussian point-cloud PLY in the reference's exact
-property order, the Blender-format ("NeRF synthetic") dataset layout its loader reads, the initial point cloud
-`points3d.ply`, and the `cfg_args` file `render.py` looks for — so that a trained `dp.FlatGaussians` can be opened by
+property order, the Blender-format ("NeRF synthetic") and COLMAP-format dataset layouts its loaders read, the initial
+point cloud `points3d.ply`, and the `cfg_args` file `render.py` looks for — so that a trained `dp.FlatGaussians` can be opened by
 the reference's viewer / render.py and a synthetic dataset can drive the reference's train.py on a box without data.
 
 Mirrors: GaussianModel.save_ply / load_ply / construct_list_of_attributes (LG/scene/gaussian_model.py:225-314),
@@ -131,3 +131,63 @@ def write_cfg_args(model_path, **kwargs):
     base.update(kwargs)
     with open(os.path.join(model_path, "cfg_args"), "w") as f:
         f.write(str(Namespace(**base)))
+
+
+# ---------------------------------------------------------------- COLMAP sparse model (LLFF / Mip-NeRF360 style scenes)
+def _rotmat_to_qvec(R):
+    """COLMAP quaternion (w, x, y, z) of a rotation matrix — the inverse of qvec2rotmat (LG/scene/colmap_loader.py:43-53),
+    largest-component branch for numerical stability"""
+    R = np.asarray(R, np.float64)
+    t = np.trace(R)
+    if t > 0:
+        s = math.sqrt(t + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = math.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+        q = [(R[2, 1] - R[1, 2]) / s, 0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s]
+    elif R[1, 1] > R[2, 2]:
+        s = math.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+        q = [(R[0, 2] - R[2, 0]) / s, (R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s]
+    else:
+        s = math.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+        q = [(R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s]
+    q = np.array(q)
+    return q if q[0] >= 0 else -q
+
+
+def write_colmap_dataset(root, cameras, images, points, image_dir="images"):
+    """COLMAP-format scene as readColmapSceneInfo expects it (LG/scene/dataset_readers.py:188-260): images/*.png and
+    sparse/0/{cameras,images,points3D}.bin in COLMAP's binary layout (LG/scene/colmap_loader.py:113-142,167-229): one
+    PINHOLE camera per view (fx, fy, cx, cy), world-to-camera (qvec, tvec) per image with no 2-D observations, points
+    with empty tracks.  cameras: lgdwt_b200.scenes.Camera; images: (3, H, W) floats in [0, 1]; points: (xyz, rgb_u8)."""
+    import struct
+    from PIL import Image
+    sparse = os.path.join(root, "sparse", "0")
+    os.makedirs(sparse, exist_ok=True)
+    os.makedirs(os.path.join(root, image_dir), exist_ok=True)
+    with open(os.path.join(sparse, "cameras.bin"), "wb") as f:
+        f.write(struct.pack("<Q", len(cameras)))
+        for k, cam in enumerate(cameras):
+            W, H = cam.image_width, cam.image_height
+            fx, fy = W / (2.0 * cam.tanfovx), H / (2.0 * cam.tanfovy)
+            f.write(struct.pack("<iiQQ", k + 1, 1, W, H))                 # model 1 = PINHOLE
+            f.write(struct.pack("<dddd", fx, fy, W / 2.0, H / 2.0))
+    with open(os.path.join(sparse, "images.bin"), "wb") as f:
+        f.write(struct.pack("<Q", len(cameras)))
+        for k, (cam, img) in enumerate(zip(cameras, images)):
+            w2c = np.asarray(cam.viewmatrix, np.float64).T                # column-vector world-to-camera
+            q, t = _rotmat_to_qvec(w2c[:3, :3]), w2c[:3, 3]
+            name = "view_%04d.png" % k
+            f.write(struct.pack("<idddddddi", k + 1, q[0], q[1], q[2], q[3], t[0], t[1], t[2], k + 1))
+            f.write(name.encode("utf-8") + b"\x00")
+            f.write(struct.pack("<Q", 0))
+            a = np.clip(np.asarray(img, np.float32), 0, 1)[:3]
+            Image.fromarray((a.transpose(1, 2, 0) * 255.0 + 0.5).astype(np.uint8), "RGB").save(os.path.join(root, image_dir, name))
+    xyz, rgb = np.asarray(points[0], np.float64), np.asarray(points[1]).astype(np.uint8)
+    with open(os.path.join(sparse, "points3D.bin"), "wb") as f:
+        f.write(struct.pack("<Q", xyz.shape[0]))
+        for i in range(xyz.shape[0]):
+            f.write(struct.pack("<QdddBBBd", i + 1, xyz[i, 0], xyz[i, 1], xyz[i, 2], int(rgb[i, 0]), int(rgb[i, 1]),
+                                int(rgb[i, 2]), 0.0))
+            f.write(struct.pack("<Q", 0))
+    return len(cameras)

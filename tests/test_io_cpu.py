@@ -136,3 +136,51 @@ def test_reference_readers_and_writers_interoperate(tmp_path):
     np.testing.assert_allclose(infos[1].R, w2c[:3, :3].T, atol=1e-6)
     np.testing.assert_allclose(infos[1].T, w2c[:3, 3], atol=1e-6)
     np.testing.assert_allclose(infos[1].FovX, 2 * np.arctan(cams[1].tanfovx), atol=1e-9)
+
+
+def test_colmap_dataset_self_consistency(tmp_path):
+    import struct
+    cams = scenes.orbit_cameras(4, 40, 24)
+    xyz = np.random.default_rng(4).normal(size=(30, 3))
+    rgb = np.random.default_rng(5).integers(0, 256, (30, 3)).astype(np.uint8)
+    io.write_colmap_dataset(str(tmp_path), cams, [np.full((3, 24, 40), 0.5, np.float32)] * 4, (xyz, rgb))
+    raw = open(tmp_path / "sparse" / "0" / "cameras.bin", "rb").read()
+    assert struct.unpack("<Q", raw[:8])[0] == 4 and len(raw) == 8 + 4 * (24 + 32)
+    cid, model, W, H = struct.unpack("<iiQQ", raw[8:32])
+    fx, fy, cx, cy = struct.unpack("<dddd", raw[32:64])
+    assert (cid, model, W, H) == (1, 1, 40, 24) and abs(fx - 40 / (2 * cams[0].tanfovx)) < 1e-9 and (cx, cy) == (20.0, 12.0)
+    for k, cam in enumerate(cams):   # quaternion round trip through the documented qvec2rotmat formula
+        w2c = np.asarray(cam.viewmatrix, np.float64).T
+        q = io._rotmat_to_qvec(w2c[:3, :3])
+        R = np.array([[1 - 2 * q[2] ** 2 - 2 * q[3] ** 2, 2 * q[1] * q[2] - 2 * q[0] * q[3], 2 * q[3] * q[1] + 2 * q[0] * q[2]],
+                      [2 * q[1] * q[2] + 2 * q[0] * q[3], 1 - 2 * q[1] ** 2 - 2 * q[3] ** 2, 2 * q[2] * q[3] - 2 * q[0] * q[1]],
+                      [2 * q[3] * q[1] - 2 * q[0] * q[2], 2 * q[2] * q[3] + 2 * q[0] * q[1], 1 - 2 * q[1] ** 2 - 2 * q[2] ** 2]])
+        np.testing.assert_allclose(R, w2c[:3, :3], atol=1e-6)
+    assert (tmp_path / "images" / "view_0003.png").exists()
+
+
+@needs_ref
+def test_reference_colmap_readers_open_our_dataset(tmp_path):
+    _import_reference()
+    from scene import colmap_loader as cl
+    from utils.graphics_utils import focal2fov
+    cams = scenes.orbit_cameras(5, 48, 32)
+    xyz = np.random.default_rng(6).normal(size=(64, 3))
+    rgb = np.random.default_rng(7).integers(0, 256, (64, 3)).astype(np.uint8)
+    io.write_colmap_dataset(str(tmp_path), cams, [np.zeros((3, 32, 48), np.float32)] * 5, (xyz, rgb))
+    sp = tmp_path / "sparse" / "0"
+    extr = cl.read_extrinsics_binary(str(sp / "images.bin"))
+    intr = cl.read_intrinsics_binary(str(sp / "cameras.bin"))
+    pts, cols, errs = cl.read_points3D_binary(str(sp / "points3D.bin"))
+    assert len(extr) == len(intr) == 5
+    np.testing.assert_allclose(pts, xyz, atol=0)
+    np.testing.assert_array_equal(cols, rgb)
+    for k, cam in enumerate(cams):
+        e, i = extr[k + 1], intr[extr[k + 1].camera_id]
+        assert e.name == "view_%04d.png" % k and i.model == "PINHOLE" and (i.width, i.height) == (48, 32)
+        w2c = np.asarray(cam.viewmatrix, np.float64).T
+        # what readColmapCameras derives (dataset_readers.py:85-96): R = qvec2rotmat(q)^T, T = tvec, FoV from the focals
+        np.testing.assert_allclose(np.transpose(cl.qvec2rotmat(e.qvec)), w2c[:3, :3].T, atol=1e-6)
+        np.testing.assert_allclose(e.tvec, w2c[:3, 3], atol=1e-9)
+        np.testing.assert_allclose(focal2fov(i.params[0], i.width), 2 * np.arctan(cam.tanfovx), atol=1e-9)
+        np.testing.assert_allclose(focal2fov(i.params[1], i.height), 2 * np.arctan(cam.tanfovy), atol=1e-9)
