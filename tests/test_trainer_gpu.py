@@ -230,3 +230,24 @@ def test_fused_l1_loss_matches_torch(shape):
     (3.0 * (ref - gt).abs().mean()).backward()
     torch.testing.assert_close(fused_l1_loss(pred, gt), (ref - gt).abs().mean(), rtol=2e-6, atol=1e-8)
     torch.testing.assert_close(pred.grad, ref.grad, rtol=1e-6, atol=0)
+
+
+def test_fused_ssim_dropin_matches_pytorch_ssim():
+    """the optional `fused_ssim` import of LG/train.py:36-40 resolved to this repo: value and gradient equal the
+    reference's PyTorch ssim (restated in oracle/photometric_oracle.py, pinned on loss_utils.ssim)"""
+    from fused_ssim import fused_ssim
+    from oracle import photometric_oracle
+    pred_np, gt_np = golden_inputs.photometric_case_inputs("smooth_odd", 3, 67, 131)
+    gt = T(gt_np).unsqueeze(0)
+    a = T(pred_np).unsqueeze(0).requires_grad_(True)
+    b = T(pred_np).unsqueeze(0).requires_grad_(True)
+    v = fused_ssim(a, gt)
+    r = photometric_oracle.ssim(b, gt)
+    torch.testing.assert_close(v, r, rtol=1e-5, atol=1e-7)
+    (1.0 - v).backward()
+    (1.0 - r).backward()
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-4, atol=1e-8)
+    two = fused_ssim(torch.cat([a.detach(), gt]), torch.cat([gt, gt]), train=False)
+    torch.testing.assert_close(two, 0.5 * (v.detach() + 1.0), rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        fused_ssim(a, gt, padding="valid")
