@@ -86,7 +86,7 @@ def _ref_check(lib, rc):
 
 
 def run_ref(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
-            scale_modifier=1.0, debug=False, want_state=True):
+            scale_modifier=1.0, debug=False, want_state=True, prefiltered=False):
     lib = load_ref()
     dev = t["means3D"].device
     P = t["means3D"].shape[0]
@@ -104,8 +104,8 @@ def run_ref(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None,
     rc = lib.ref_rasterize_forward(
         geom.cb, None, binning.cb, None, img.cb, None, P, sh_degree, M, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs),
         _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp),
-        _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, 0, _ptr(color),
-        _ptr(invd), int(antialiasing), _ptr(radii), int(debug), ctypes.byref(R))
+        _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, int(prefiltered),
+        _ptr(color), _ptr(invd), int(antialiasing), _ptr(radii), int(debug), ctypes.byref(R))
     _ref_check(lib, rc)
     torch.cuda.synchronize()
     out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,

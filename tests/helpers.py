@@ -52,7 +52,7 @@ class _Buf:
 
 
 def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
-             scale_modifier=1.0, debug=False, want_state=True, with_invdepth=True):
+             scale_modifier=1.0, debug=False, want_state=True, with_invdepth=True, prefiltered=False):
     """Low-level call through the C ABI (no autograd).  Returns dict of outputs, state tensors and raw buffers."""
     from lgdwt_b200 import _lib
     dev = t["means3D"].device
@@ -72,7 +72,7 @@ def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None
         geom.callback, None, binning.callback, None, img.callback, None, P, sh_degree, M, C, _ptr(bg), W, H,
         _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier,
         _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]),
-        cam.tanfovx, cam.tanfovy, 0, _ptr(color), _ptr(invd) if with_invdepth else None, int(antialiasing),
+        cam.tanfovx, cam.tanfovy, int(prefiltered), _ptr(color), _ptr(invd) if with_invdepth else None, int(antialiasing),
         _ptr(radii), int(debug), _lib.stream_ptr(dev), ctypes.byref(R))
     _lib.check(rc)
     out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,
@@ -131,6 +131,36 @@ def rel_err(a, b):
     """max |a-b| / max(|b|_inf, eps): the per-tensor relative error of SURVEY §8c."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+# ---------------------------------------------------------------- gradient bars (tests/test_configs_gpu.py docstring)
+TENSOR_RTOL = 2e-4
+ELEM_RTOL, ELEM_ATOL_FRAC, ELEM_QUANTILE = 1e-3, 2e-6, 0.999
+HARD_RTOL, HARD_ATOL_FRAC = 1e-2, 2e-4
+
+
+def grad_stats(mine, ref):
+    """the three gradient measures of this file, as numbers (shared with test_rasterizer_vs_reference_gpu.py)"""
+    mine, ref = mine.double().reshape(-1), ref.double().reshape(-1)
+    scale = max(float(ref.abs().max()), 1e-30)
+    d = (mine - ref).abs()
+    soft = d <= ELEM_RTOL * ref.abs() + ELEM_ATOL_FRAC * scale
+    hard = d <= HARD_RTOL * ref.abs() + HARD_ATOL_FRAC * scale
+    return {"tensor_rel": float(d.max()) / scale, "elem_ok_frac": float(soft.double().mean()),
+            "hard_violations": int((~hard).sum()), "scale": scale}
+
+
+def assert_grad_close(name, mine, ref, floor=0.0):
+    s = grad_stats(mine, ref)
+    if s["scale"] <= floor:      # analytically zero tensor: both sides hold rounding noise
+        assert float((mine.double() - ref.double()).abs().max()) <= TENSOR_RTOL * floor, name
+        return s
+    assert s["tensor_rel"] <= TENSOR_RTOL, "%s: per-tensor relative error %.3g" % (name, s["tensor_rel"])
+    assert s["elem_ok_frac"] >= ELEM_QUANTILE, "%s: only %.5f of the elements within rtol %.0e" % (
+        name, s["elem_ok_frac"], ELEM_RTOL)
+    assert s["hard_violations"] == 0, "%s: %d elements off by more than 1 %%" % (name, s["hard_violations"])
+    return s
+
 
 
 # ---------------------------------------------------------------- flat Gaussian buffer <-> reference-shaped groups

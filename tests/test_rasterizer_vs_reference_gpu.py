@@ -125,8 +125,8 @@ def test_backward_gradients(case, with_invdepth):
             # identity rotations with isotropic scales (the Blender-style init) make dL/dq analytically zero: both
             # sides then hold rounding noise of magnitude ~ulp(|dL/dscale| * |scale|), which is the right yardstick
             floor = float(refs[0]["dL_dscale"].abs().max() * t["scales"].abs().max())
-        e = float((mine.double() - ref).abs().max() / max(float(ref.abs().max()), floor, 1e-12))
-        assert e <= GRAD_RTOL, "%s relative error %g" % (name, e)
+        # per tensor 2e-4, per element rtol 1e-3 (99.9 %) / 1e-2 (all): tests/helpers.py, tests/test_configs_gpu.py
+        helpers.assert_grad_close("%s [%s]" % (name, case), mine, ref, floor=floor)
 
 
 def test_colors_precomp_and_cov3d_precomp_paths():

@@ -15,17 +15,7 @@ from lgdwt_b200 import scenes  # noqa: E402
 from bringup import timeit  # noqa: E402
 
 
-def cfg(name):
-    if name == "cfg2":   # Blender-style init, 100k Gaussians, 800x800 (the reference's quoted small case)
-        return scenes.blender_init_scene(100_000, seed=0), scenes.metric_camera(800, 800)
-    if name == "cfg3":   # LLFF-style: 1008x756, ~500k Gaussians, forward-facing slab
-        return scenes.slab_scene(500_000, seed=2), scenes.look_at_camera(1008, 756, 1.05, 2 * math.atan(math.tan(0.525) * 756 / 1008), (0.0, 0.0, 0.0), target=(0.0, 0.0, 5.0))
-    if name == "cfg4":   # RGB+NIR scale: 1296x964, 1M Gaussians
-        return scenes.trained_like_scene(1_000_000, seed=4), scenes.look_at_camera(1296, 964, 0.8, 2 * math.atan(math.tan(0.4) * 964 / 1296), (0.0, 0.0, -4.03))
-    if name == "cfg5":   # Mip-NeRF360 scale: 1920x1080, 6M Gaussians
-        sc = scenes.trained_like_scene(6_000_000, seed=5, sigma_xyz=1.2, clip=3.0, log_scale_mean=math.log(0.006))
-        return sc, scenes.look_at_camera(1920, 1080, 1.0, 2 * math.atan(math.tan(0.5) * 1080 / 1920), (0.0, 0.0, -5.0))
-    raise SystemExit("unknown config " + name)
+cfg = scenes.baseline_config
 
 
 def main():

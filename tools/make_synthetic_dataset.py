@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--size", default="400x300")
     ap.add_argument("--gaussians", type=int, default=50_000)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--nir", action="store_true", help="also write nir/<name>.png (grey-scale near-infrared stand-in: a "
+                    "fixed mix of the rendered channels), where MS/utils/camera_utils.py:65-84 looks for it")
     args = ap.parse_args()
     W, H = (int(v) for v in args.size.lower().split("x"))
     dev = torch.device("cuda", 0)
@@ -52,6 +54,14 @@ def main():
         counts = io.write_blender_dataset(args.out, cams, images, split_test_every=8, points=(xyz, rgb))
     else:
         counts = {"images": io.write_colmap_dataset(args.out, cams, images, (xyz, rgb))}
+    if args.nir:
+        from PIL import Image
+        os.makedirs(os.path.join(args.out, "nir"), exist_ok=True)
+        names = (["view_%04d.png" % k for k in range(len(images))] if args.format == "colmap" else
+                 ["r_%d.png" % k for k in range(len(images))])
+        for name, im in zip(names, images):
+            nir = np.clip(0.6 * im[0] + 0.1 * im[1] + 0.3 * (1.0 - im[2]) * im[1], 0, 1)
+            Image.fromarray((nir * 255.0 + 0.5).astype(np.uint8), "L").save(os.path.join(args.out, "nir", name))
     print("wrote %s dataset to %s: %s, %dx%d, %d initial points, mean image %.3f" %
           (args.format, args.out, counts, W, H, pick.size, float(np.mean([im.mean() for im in images]))))
 
