@@ -195,6 +195,11 @@ int lg_blend_work_count(int P, int channels, int width, int height, int R, const
                         void* stream);
 #define LG_NUM_STAGES 5
 unsigned long long lg_launch_count(void);
+/* On-box SIMT peaks the blend kernels are measured against (no counterpart in the reference; SURVEY.md §8d asks for
+ * measured FFMA / MUFU / shared-memory ceilings).  Runs six short microbenchmarks on `stream`, best of 5 each:
+ * peaks_out[0] FFMA TFLOP/s, [1] MUFU.EX2 G lane-ops/s, [2] MUFU.RCP G lane-ops/s, [3] broadcast LDS.128
+ * G warp-instructions/s, [4] SHFL.BFLY G warp-instructions/s, [5] integer ALU (add / logic) G warp-instructions/s. */
+int lg_simt_peaks(float* peaks_out, int n, void* stream);
 int lg_stage_timing_enable(int slots);
 int lg_stage_timing_read(int slot, float* ms_out, int n);
 

@@ -133,6 +133,8 @@ def _load():
     lib.lg_stage_timing_enable.argtypes = [i]
     lib.lg_stage_timing_read.restype = i
     lib.lg_stage_timing_read.argtypes = [i, ctypes.POINTER(f), i]
+    lib.lg_simt_peaks.restype = i
+    lib.lg_simt_peaks.argtypes = [ctypes.POINTER(f), i, _P]
     if lib.lg_abi_version() != 1:
         raise ImportError("liblgdwt_b200.so has ABI version %d, expected 1" % lib.lg_abi_version())
     return lib
@@ -172,6 +174,18 @@ def read_stage_times(slot):
     buf = (ctypes.c_float * len(STAGES))()
     check(lib.lg_stage_timing_read(int(slot), buf, len(STAGES)))
     return {name: float(buf[k]) for k, name in enumerate(STAGES)}
+
+
+SIMT_PEAKS = ("ffma_tflops", "mufu_ex2_gops", "mufu_rcp_gops", "lds128_broadcast_gwarpinst", "shfl_gwarpinst",
+              "alu_gwarpinst")
+
+
+def simt_peaks(device=None):
+    """on-box FFMA / MUFU / LDS / SHFL / issue ceilings (csrc/microbench.cu), a few milliseconds"""
+    buf = (ctypes.c_float * len(SIMT_PEAKS))()
+    with torch.cuda.device(device):
+        check(lib.lg_simt_peaks(buf, len(SIMT_PEAKS), stream_ptr(device)))
+    return {name: float(buf[k]) for k, name in enumerate(SIMT_PEAKS)}
 
 
 class ResizableBuffer:
