@@ -24,7 +24,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // ---------------------------------------------------------------- opaque state layouts
 GeometryState GeometryState::from_chunk(char*& chunk, size_t P, int channels) {
     GeometryState g;
-    const size_t blocks = (P + 255) / 256;
     carve(chunk, g.depths, P);
     carve(chunk, g.clamped, P * 3);
     carve(chunk, g.internal_radii, P);
@@ -33,18 +32,8 @@ GeometryState GeometryState::from_chunk(char*& chunk, size_t P, int channels) {
     carve(chunk, g.conic_opacity, P);
     carve(chunk, g.rgb, P * (size_t)channels);
     carve(chunk, g.tiles_touched, P);
-    carve(chunk, g.point_offsets, P);
-    carve(chunk, g.scan_state, blocks + 1);
-    carve(chunk, g.counters, 8);
-    carve(chunk, g.grad_scratch, P * 12);
-    for (int k = 0; k < 2; k++) {
-        carve(chunk, g.depth_keys[k], P);
-        carve(chunk, g.depth_ids[k], P);
-    }
     carve(chunk, g.rect_packed, P);
-    carve(chunk, g.emit_scan_state, blocks + 1);
-    g.sort_temp_bytes = radix_sort_temp_bytes(P, 4);
-    carve(chunk, g.sort_temp, g.sort_temp_bytes);
+    carve(chunk, g.grad_scratch, P * 12);
     return g;
 }
 size_t geometry_state_bytes(size_t P, int channels) {
@@ -62,6 +51,8 @@ ImageState ImageState::from_chunk(char*& chunk, size_t W, size_t H) {
     carve(chunk, s.tile_order, T);
     carve(chunk, s.tile_neff, T);
     carve(chunk, s.tile_order_bwd, T);
+    carve(chunk, s.counters, LG_CTR_STRIDE + T * LG_CTR_STRIDE);  // one allocation: one memset clears both
+    s.tile_ctr = s.counters + LG_CTR_STRIDE;
     return s;
 }
 size_t image_state_bytes(size_t W, size_t H) {
@@ -72,12 +63,9 @@ size_t image_state_bytes(size_t W, size_t H) {
 
 BinningState BinningState::from_chunk(char*& chunk, size_t R) {
     BinningState b;
+    carve(chunk, b.pairs, R);
+    carve(chunk, b.pairs_alt, R);
     carve(chunk, b.point_list, R);
-    carve(chunk, b.point_list_unsorted, R);
-    carve(chunk, b.tile_keys, R);
-    carve(chunk, b.tile_keys_unsorted, R);
-    b.sort_temp_bytes = radix_sort_temp_bytes(R, 4);
-    carve(chunk, b.sort_temp, b.sort_temp_bytes);
     return b;
 }
 size_t binning_state_bytes(size_t R) {
@@ -186,19 +174,17 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
     f.prefiltered = prefiltered != 0; f.antialiasing = antialiasing != 0; f.debug = debug != 0;
 
     stage_begin(ST_PREPROCESS, stream);
-    int rc = launch_preprocess(f, g, radii, stream);
+    int rc = launch_preprocess(f, g, img, radii, stream);
     if (rc != LG_OK) return rc;
     stage_end(ST_PREPROCESS, stream);
 
-    // The depth ordering of the Gaussians needs nothing from the host, so it is queued before the read-back below and
-    // runs while the host waits for num_rendered.
     stage_begin(ST_BINNING, stream);
-    rc = launch_depth_order(P, g, f.debug, stream);
+    rc = launch_tile_scan(width, height, img, f.debug, stream);
     if (rc != LG_OK) return rc;
 
     // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288)
     if (!g_pinned_word) LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
-    LG_CUDA(cudaMemcpyAsync(g_pinned_word, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LG_CUDA(cudaMemcpyAsync(g_pinned_word, img.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     LG_CUDA(cudaStreamSynchronize(stream));
     const int R = (int)*g_pinned_word;
     *num_rendered = R;
@@ -415,15 +401,21 @@ int lg_state_read(const char* name, int P, int channels, int width, int height, 
         BinningState b = BinningState::from_chunk(p, (size_t)R);
         if (!strcmp(name, "point_list")) { src = b.point_list; bytes = 4 * (size_t)R; }
         else if (!strcmp(name, "point_list_keys")) {
-            // the 64-bit (tile | depth) keys of the reference are never materialised by the two-level sort; rebuild
-            // them from the sorted tile ids and the depths for inspection
+            // the 64-bit (tile | depth) keys of the reference are never materialised (binning.cu); rebuild them from
+            // the tile ranges and the depths for inspection
             if (!geometry_state || dst_bytes < 8 * (size_t)R) {
                 set_error("lg_state_read: 'point_list_keys' needs the geometry state and %zu bytes", 8 * (size_t)R);
                 return LG_ERR_INVALID_ARGUMENT;
             }
             char* gp = const_cast<char*>(geometry_state);
             GeometryState g = GeometryState::from_chunk(gp, (size_t)P, channels);
-            return launch_rebuild_keys(R, g, b, (unsigned long long*)dst, stream);
+            if (!image_state) {
+                set_error("lg_state_read: 'point_list_keys' needs the image state (tile ranges)");
+                return LG_ERR_INVALID_ARGUMENT;
+            }
+            char* ip2 = const_cast<char*>(image_state);
+            ImageState s2 = ImageState::from_chunk(ip2, (size_t)width, (size_t)height);
+            return launch_rebuild_keys(width, height, g, b, s2, (unsigned long long*)dst, stream);
         }
     }
     if (!src) {

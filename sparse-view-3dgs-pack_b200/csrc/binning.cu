@@ -2,229 +2,81 @@
 // identifyTileRanges produce in the reference (DGR/cuda_rasterizer/rasterizer_impl.cu:70-138, 292-321): the list of
 // Gaussian ids ordered by (tile, depth bits, Gaussian id) and the [begin, end) range of every tile.
 //
-// The reference sorts R = sum(tiles_touched) 64-bit (tile | depth) keys.  The same total order is reached with far
-// less traffic by a two-level LSD scheme:
-//   1. order the P Gaussians by their 32 depth bits (stable, so equal depths stay in ascending-id order);
-//   2. emit one (tile id, Gaussian id) pair per overlap while walking the Gaussians in that order, so that inside
-//      every tile the pairs already appear in (depth, id) order;
-//   3. stable-sort the R pairs by the tile id alone (ceil(log2 T) = 12..13 bits: two 8-bit passes).
-// Stable LSD sorting by the minor key first and the major key second is exactly a sort by (tile, depth, id) — the
-// order the reference's stable 44..45-bit sort yields (a Gaussian appears at most once per tile, so the order is
-// total and every correct sort reproduces the reference list bit for bit).  P-sized passes replace four of the six
-// R-sized passes and the R-sized passes move 8 bytes per pair instead of 12.
+// The reference sorts R = sum(tiles_touched) 64-bit (tile | depth) keys globally (6 passes over 12-byte pairs).
+// The major key only has T <= a few thousand values, so here it is never sorted at all:
+//   1. COUNT    the preprocess kernel adds 1 to tile_count[t] for every tile t of a Gaussian's rectangle;
+//   2. SCAN     one block turns the counts into the tile ranges (the reference's identifyTileRanges output), the
+//               per-tile write cursors, the total R and the longest-list-first launch order of the tiles;
+//   3. SCATTER  every (Gaussian, tile) overlap takes a slot of its tile's range with one atomic on the tile cursor and
+//               stores (depth bits, Gaussian id) there — the tile's entries are now contiguous, in arbitrary order;
+//   4. SORT     one block per tile sorts its own entries by (depth bits, id) in shared memory (LSD radix over the
+//               depth digits that actually vary inside the tile; equal depths are put in ascending-id order) and writes
+//               the tile's slice of the id list.
+// (tile, depth bits, id) is a total order — a Gaussian appears at most once per tile — so the list is the
+// reference's bit for bit whatever order the atomics of step 3 resolved in.  Per-overlap traffic: 8 B written + 8 B
+// read + 4 B written, all L2-resident, against 8 + 6 x 24 B in the reference; no P-sized or R-sized global sort pass
+// is left.
 #include "common.cuh"
 
 namespace lg {
 
-// bits needed for the tile id: the reference's getHigherMsb (rasterizer_impl.cu:35-50) == 32 - clz(n) for n >= 1
-// (tests/test_host_logic.py checks the equality against a line-by-line restatement).
+// bits needed to hold values < n (>= 1)
 int higher_msb(uint32_t n) {
     int b = 0;
     while (n) { b++; n >>= 1; }
     return b < 1 ? 1 : b;
 }
 
-#define EMIT_BLOCK 256
-#define EMIT_IPT 4   // Gaussians per thread
-#define EMIT_TILE (EMIT_BLOCK * EMIT_IPT)
-#define EMIT_CAP 5120 // pairs staged in shared memory per round (40 KB)
-#define EMIT_COOP 8  // rectangles of more tiles than this are written by the whole warp (coalesced stores)
-
-// Walks the Gaussians in depth order.  A thread takes EMIT_IPT consecutive entries of `order`, learns where their
-// pairs start from a fused exclusive scan of the tile counts in that order (block scan + decoupled look-back over
-// blocks taken in ticket order), and writes one (tile, id) pair per tile of each rectangle, row-major as the
-// reference's double loop (rasterizer_impl.cu:93-108; the order inside one Gaussian is irrelevant to the result,
-// its tiles being distinct).  The block also accumulates the digit histograms of the tile ids it writes, which the
-// tile-id sort that follows would otherwise need a pass of its own for.
-__global__ void __launch_bounds__(EMIT_BLOCK) emit_pairs_kernel(int P, const uint32_t* __restrict__ order,
-                                                                const uint32_t* __restrict__ tiles_touched,
-                                                                const uint32_t* __restrict__ rect_packed,
-                                                                const float2* __restrict__ xy,
-                                                                const int* __restrict__ radii,
-                                                                uint32_t* __restrict__ tile_keys,
-                                                                uint32_t* __restrict__ ids, int grid_x, int grid_y,
-                                                                unsigned long long* scan_state, uint32_t* ticket,
-                                                                uint32_t* tile_hist, uint32_t mask0, uint32_t mask1) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp_sums[EMIT_BLOCK / 32];
-    __shared__ uint32_t s_block_prefix, s_block_total;
-    __shared__ uint32_t s_keys[EMIT_CAP], s_ids[EMIT_CAP];  // the block's pairs at their block-local offsets
-    __shared__ uint32_t s_hist[2 * 256];  // digit histograms of the tile ids emitted by this block (two 8-bit places)
-    s_hist[threadIdx.x] = 0;
-    s_hist[256 + threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int i0 = (int)(tile * EMIT_TILE + threadIdx.x * EMIT_IPT);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
-    // per item: Gaussian id and its tile rectangle packed as xs = x0 | x1 << 16, ys = y0 | y1 << 16
-    uint32_t id[EMIT_IPT], xs[EMIT_IPT], ys[EMIT_IPT];
-#pragma unroll
-    for (int u = 0; u < EMIT_IPT; u++) id[u] = (i0 + u < P) ? order[i0 + u] : 0u;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int u = 0; u < EMIT_IPT; u++) {
-        xs[u] = ys[u] = 0;
-        if (i0 + u < P) {
-            if (rect_packed) {  // one 4-byte gather gives both the count and the rectangle
-                const uint32_t r = rect_packed[id[u]];
-                xs[u] = (r & 255u) | (((r >> 16) & 255u) << 16);
-                ys[u] = ((r >> 8) & 255u) | ((r >> 24) << 16);
-            } else if (tiles_touched[id[u]] > 0) {
-                const float2 p = xy[id[u]];
-                uint32_t x0, y0, x1, y1;
-                lg_get_rect(p.x, p.y, radii[id[u]], grid_x, grid_y, x0, y0, x1, y1);
-                xs[u] = x0 | (x1 << 16);
-                ys[u] = y0 | (y1 << 16);
-            }
-        }
-        mine += ((xs[u] >> 16) - (xs[u] & 0xffffu)) * ((ys[u] >> 16) - (ys[u] & 0xffffu));
-    }
-    // ---- exclusive scan of the tile counts over the depth-ordered Gaussians
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += t;
-    }
-    if (lane == 31) s_warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t ws = lane < EMIT_BLOCK / 32 ? s_warp_sums[lane] : 0u;
-        uint32_t wincl = ws;
-#pragma unroll
-        for (int o = 1; o < EMIT_BLOCK / 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
-            if (lane >= (unsigned)o) wincl += t;
-        }
-        if (lane < EMIT_BLOCK / 32) s_warp_sums[lane] = wincl - ws;  // exclusive warp offsets
-        const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, EMIT_BLOCK / 32 - 1);
-        const uint32_t exclusive = lg_lookback_exclusive(scan_state, tile, block_total, lane);
-        if (lane == 0) {
-            s_block_prefix = exclusive;
-            s_block_total = block_total;
-        }
-    }
-    __syncthreads();
-    // ---- emission.  Every thread owns a run of consecutive output slots, but runs are short (3.6 pairs per Gaussian
-    // on the benchmark scene), so writing them straight to global memory touches ~11 sectors per store instruction.
-    // The block's pairs are instead laid out in shared memory at their block-local offsets and streamed out with
-    // fully coalesced stores, EMIT_CAP pairs per round (one round for all but the densest blocks).
-    const uint32_t block_base = s_block_prefix;
-    const uint32_t block_total = s_block_total;
-    const uint32_t my_first = s_warp_sums[warp] + incl - mine;  // block-local offset of this thread's first pair
-    for (uint32_t chunk = 0; chunk < block_total; chunk += EMIT_CAP) {
-        uint32_t off = my_first;
-#pragma unroll
-        for (int u = 0; u < EMIT_IPT; u++) {
-            const uint32_t x0 = xs[u] & 0xffffu, x1 = xs[u] >> 16, y0 = ys[u] & 0xffffu, y1 = ys[u] >> 16;
-            const uint32_t nu = (x1 - x0) * (y1 - y0);
-            const bool touches = nu > 0 && off < chunk + EMIT_CAP && off + nu > chunk;
-            if (touches && nu <= EMIT_COOP) {
-                uint32_t o = off;
-                for (uint32_t y = y0; y < y1; y++)
-                    for (uint32_t x = x0; x < x1; x++, o++) {
-                        const uint32_t q = o - chunk;  // wraps for o < chunk
-                        if (q < EMIT_CAP) {
-                            s_keys[q] = y * (uint32_t)grid_x + x;
-                            s_ids[q] = id[u];
-                        }
-                    }
-            }
-            unsigned big = __ballot_sync(0xffffffffu, touches && nu > EMIT_COOP);
-            while (big) {
-                const int src = __ffs(big) - 1;
-                big &= big - 1;
-                const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-                const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
-                const uint32_t bn = __shfl_sync(0xffffffffu, nu, src), boff = __shfl_sync(0xffffffffu, off, src);
-                const uint32_t bid = __shfl_sync(0xffffffffu, id[u], src);
-                for (uint32_t k = lane; k < bn; k += 32) {
-                    const uint32_t q = boff + k - chunk;
-                    if (q < EMIT_CAP) {
-                        s_keys[q] = (by0 + k / bw) * (uint32_t)grid_x + bx0 + k % bw;
-                        s_ids[q] = bid;
-                    }
-                }
-            }
-            off += nu;
-        }
-        __syncthreads();
-        const uint32_t count = min((uint32_t)EMIT_CAP, block_total - chunk);
-        for (uint32_t q = threadIdx.x; q < count; q += EMIT_BLOCK) {
-            const uint32_t t = s_keys[q];
-            tile_keys[block_base + chunk + q] = t;
-            ids[block_base + chunk + q] = s_ids[q];
-            atomicAdd(&s_hist[t & mask0], 1u);
-            atomicAdd(&s_hist[256 + ((t >> 8) & mask1)], 1u);
-        }
-        __syncthreads();
-    }
-    {
-        const uint32_t c0 = s_hist[threadIdx.x], c1 = s_hist[256 + threadIdx.x];
-        if (c0) atomicAdd(tile_hist + threadIdx.x, c0);
-        if (c1) atomicAdd(tile_hist + 256 + threadIdx.x, c1);
-    }
-}
-
-// identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted tile ids; tiles with no entries keep (0,0).
-// Four consecutive ids per thread (one 16-byte load + the id before them).
-__global__ void __launch_bounds__(256) tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
-                                                          uint2* __restrict__ ranges) {
-    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (base >= L) return;
-    uint32_t k[4];
-    if (base + 4u <= L) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + base);
-        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) k[i] = base + i < L ? tile_keys[base + i] : 0u;
-    }
-    uint32_t prev = base == 0 ? 0u : tile_keys[base - 1];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t idx = base + i;
-        if (idx < L) {
-            const uint32_t cur = k[i];
-            if (idx == 0) ranges[cur].x = 0;
-            else if (cur != prev) {
-                ranges[prev].y = idx;
-                ranges[cur].x = idx;
-            }
-            if (idx == L - 1) ranges[cur].y = L;
-            prev = cur;
-        }
-    }
-}
-
-// Tile launch order for the blend kernels: one block buckets the T tiles by key (1024 buckets scaled to the largest
-// key) and lists them heaviest bucket first.  keys[t * key_stride + key_offset] with (stride 2, offset: y - x computed
-// here) for ranges, (stride 1) for tile_neff.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint32_t* __restrict__ keys, int key_stride,
-                                                          uint32_t* __restrict__ order) {
+// ------------------------------------------------------------------------------------------------ 2. SCAN
+// One block: exclusive scan of the per-tile counts -> ranges / cursors / total, then the tile launch order (1024
+// buckets scaled to the longest list, heaviest first: the hardware hands out blocks in blockIdx order, so the long
+// lists of the image centre are started first and do not form the tail).  Tiles with no entries keep (begin, begin),
+// which the blend kernels treat like the reference's (0, 0): an empty range.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int T, uint32_t* __restrict__ tile_ctr,
+                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                         uint32_t* __restrict__ counters) {
     __shared__ uint32_t s_cnt[1024];
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_max;
+    __shared__ uint32_t s_running, s_max;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) { s_running = 0; s_max = 1; }
     s_cnt[tid] = 0;
-    if (tid == 0) s_max = 1;
     __syncthreads();
-    auto key_of = [&](int t) -> uint32_t {
-        return key_stride == 2 ? keys[2 * t + 1] - keys[2 * t] : keys[t];
-    };
     uint32_t m = 0;
-    for (int t = tid; t < T; t += 1024) m = max(m, key_of(t));
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        const uint32_t v = t < T ? tile_ctr[(size_t)t * LG_CTR_STRIDE] : 0u;
+        m = max(m, v);
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_running;
+        for (unsigned w = 0; w < warp; w++) before += s_warp[w];
+        if (t < T) {
+            const uint32_t begin = before + incl - v;
+            ranges[t] = v ? make_uint2(begin, begin + v) : make_uint2(0u, 0u);  // empty tiles as in the reference
+            tile_ctr[(size_t)t * LG_CTR_STRIDE + 1] = begin;  // write cursor of the scatter step
+        }
+        __syncthreads();
+        if (tid == 1023) s_running = before + incl;
+        __syncthreads();
+    }
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0) atomicMax(&s_max, m);
+    if (tid == 0) {
+        counters[1] = s_running;  // num_rendered
+        counters[4] = 0;          // tile-sort overflow / error word
+    }
     __syncthreads();
     const float scale = 1023.0f / (float)s_max;
-    // bucket 0 = heaviest
-    for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)key_of(t) * scale), 1023)], 1u);
+    for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)(ranges[t].y - ranges[t].x) * scale), 1023)], 1u);
     __syncthreads();
-    // exclusive scan of the 1024 bucket counts
     const uint32_t c = s_cnt[tid];
     uint32_t x = c;
 #pragma unroll
@@ -247,85 +99,629 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint32_t*
     s_cnt[tid] = x - c + s_warp[warp];
     __syncthreads();
     for (int t = tid; t < T; t += 1024) {
-        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)key_of(t) * scale), 1023)], 1u);
+        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)(ranges[t].y - ranges[t].x) * scale), 1023)], 1u);
         order[pos] = (uint32_t)t;
     }
 }
 
-int launch_tile_order(int T, const uint32_t* keys, int key_stride, uint32_t* order, cudaStream_t stream) {
-    tile_order_kernel<<<1, 1024, 0, stream>>>(T, keys, key_stride, order);
+// Tile launch order from an arbitrary per-tile key (used by the backward pass on tile_neff): same bucketing.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint32_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_cnt[1024];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    s_cnt[tid] = 0;
+    if (tid == 0) s_max = 1;
+    __syncthreads();
+    uint32_t m = 0;
+    for (int t = tid; t < T; t += 1024) m = max(m, keys[t]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const float scale = 1023.0f / (float)s_max;
+    for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
+    __syncthreads();
+    const uint32_t c = s_cnt[tid];
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], z = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+            if ((int)lane >= o) z += y;
+        }
+        s_warp[lane] = z - w;
+    }
+    __syncthreads();
+    s_cnt[tid] = x - c + s_warp[warp];
+    __syncthreads();
+    for (int t = tid; t < T; t += 1024) {
+        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
+        order[pos] = (uint32_t)t;
+    }
+}
+
+int launch_tile_order(int T, const uint32_t* keys, uint32_t* order, cudaStream_t stream) {
+    tile_order_kernel<<<1, 1024, 0, stream>>>(T, keys, order);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
 
-// inspection only (lg_state_read "point_list_keys"): the reference's sorted 64-bit keys
-__global__ void __launch_bounds__(256) rebuild_keys_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys,
+// ------------------------------------------------------------------------------------------------ 3. SCATTER
+#define SCATTER_BLOCK 256
+#define SCATTER_COOP 8  // rectangles of more tiles than this are written by the whole warp
+
+// One thread per Gaussian; a slot of the tile's range per overlap (rasterizer_impl.cu:93-108 writes the same pairs at
+// scan offsets; the order inside a tile is settled by the sort that follows).  Does nothing when the capacity the
+// caller's binning buffer was sized for turned out too small (the host then re-runs this step with a larger buffer).
+__global__ void __launch_bounds__(SCATTER_BLOCK) scatter_pairs_kernel(int P, const uint32_t* __restrict__ tiles_touched,
+                                                                      const uint32_t* __restrict__ rect_packed,
+                                                                      const float2* __restrict__ xy,
+                                                                      const int* __restrict__ radii,
+                                                                      const float* __restrict__ depths,
+                                                                      uint32_t* __restrict__ tile_ctr,
+                                                                      uint2* __restrict__ pairs, int grid_x, int grid_y,
+                                                                      const uint32_t* __restrict__ counters,
+                                                                      uint32_t capacity) {
+    if (counters[1] > capacity) return;
+    const int idx = blockIdx.x * SCATTER_BLOCK + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0, key = 0;
+    if (idx < P) {
+        if (rect_packed) {  // 0 for a Gaussian that emits nothing
+            const uint32_t r = rect_packed[idx];
+            x0 = r & 255u; y0 = (r >> 8) & 255u; x1 = (r >> 16) & 255u; y1 = r >> 24;
+        } else if (tiles_touched[idx] > 0) {
+            const float2 p = xy[idx];
+            lg_get_rect(p.x, p.y, radii[idx], grid_x, grid_y, x0, y0, x1, y1);
+        }
+    }
+    const uint32_t n = (x1 - x0) * (y1 - y0);
+    if (n > 0) key = __float_as_uint(depths[idx]);
+    if (n > 0 && n <= SCATTER_COOP) {
+        for (uint32_t y = y0; y < y1; y++)
+            for (uint32_t x = x0; x < x1; x++) {
+                const uint32_t slot = atomicAdd(&tile_ctr[(size_t)(y * (uint32_t)grid_x + x) * LG_CTR_STRIDE + 1], 1u);
+                pairs[slot] = make_uint2(key, (uint32_t)idx);
+            }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, n > SCATTER_COOP);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
+        const uint32_t bn = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t bkey = __shfl_sync(0xffffffffu, key, src);
+        const uint32_t bid = (uint32_t)(idx - (int)lane + src);
+        for (uint32_t k = lane; k < bn; k += 32) {
+            const uint32_t slot = atomicAdd(&tile_ctr[(size_t)((by0 + k / bw) * (uint32_t)grid_x + bx0 + k % bw) * LG_CTR_STRIDE + 1], 1u);
+            pairs[slot] = make_uint2(bkey, bid);
+        }
+    }
+}
+
+// The same step with the block's overlaps first counted per tile in shared memory: one global atomic per (block, tile)
+// reserves a run of slots for all of the block's entries of that tile (a 4096-Gaussian block holds ~6 entries per tile
+// on the benchmark scene, so six times fewer global atomics than above), and the entries then take consecutive slots
+// of their run with shared-memory atomics.  Needs 8 bytes of shared memory per tile.
+#ifndef SCATTER_AGGREGATE
+#define SCATTER_AGGREGATE 1
+#endif
+#define SCATTER_AGG_BLOCK 1024
+#define SCATTER_AGG_IPT 4
+template <bool PLACE>
+__device__ __forceinline__ void scatter_walk(uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, uint32_t n, uint32_t key,
+                                             uint32_t id, int grid_x, unsigned lane, uint32_t* s_cnt,
+                                             const uint32_t* s_base, uint2* __restrict__ pairs) {
+    if (n > 0 && n <= SCATTER_COOP) {
+        for (uint32_t y = y0; y < y1; y++)
+            for (uint32_t x = x0; x < x1; x++) {
+                const uint32_t t = y * (uint32_t)grid_x + x;
+                const uint32_t r = atomicAdd(&s_cnt[t], 1u);
+                if (PLACE) pairs[s_base[t] + r] = make_uint2(key, id);
+            }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, n > SCATTER_COOP);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
+        const uint32_t bn = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t bkey = __shfl_sync(0xffffffffu, key, src), bid = __shfl_sync(0xffffffffu, id, src);
+        for (uint32_t k = lane; k < bn; k += 32) {
+            const uint32_t t = (by0 + k / bw) * (uint32_t)grid_x + bx0 + k % bw;
+            const uint32_t r = atomicAdd(&s_cnt[t], 1u);
+            if (PLACE) pairs[s_base[t] + r] = make_uint2(bkey, bid);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SCATTER_AGG_BLOCK) scatter_pairs_agg_kernel(
+    int P, int T, const uint32_t* __restrict__ rect_packed, const float* __restrict__ depths,
+    uint32_t* __restrict__ tile_ctr, uint2* __restrict__ pairs, int grid_x, const uint32_t* __restrict__ counters,
+    uint32_t capacity) {
+    extern __shared__ uint32_t s_scatter[];
+    if (counters[1] > capacity) return;
+    uint32_t* s_cnt = s_scatter;
+    uint32_t* s_base = s_scatter + T;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    for (int t = tid; t < T; t += SCATTER_AGG_BLOCK) s_cnt[t] = 0;
+    uint32_t x0[SCATTER_AGG_IPT], y0[SCATTER_AGG_IPT], x1[SCATTER_AGG_IPT], y1[SCATTER_AGG_IPT], key[SCATTER_AGG_IPT];
+    const int first = blockIdx.x * (SCATTER_AGG_BLOCK * SCATTER_AGG_IPT) + (int)tid;
+#pragma unroll
+    for (int u = 0; u < SCATTER_AGG_IPT; u++) {
+        const int idx = first + u * SCATTER_AGG_BLOCK;
+        const uint32_t r = idx < P ? rect_packed[idx] : 0u;
+        x0[u] = r & 255u; y0[u] = (r >> 8) & 255u; x1[u] = (r >> 16) & 255u; y1[u] = r >> 24;
+        key[u] = (x1[u] - x0[u]) * (y1[u] - y0[u]) > 0 ? __float_as_uint(depths[idx]) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < SCATTER_AGG_IPT; u++)
+        scatter_walk<false>(x0[u], y0[u], x1[u], y1[u], (x1[u] - x0[u]) * (y1[u] - y0[u]), key[u],
+                            (uint32_t)(first + u * SCATTER_AGG_BLOCK), grid_x, lane, s_cnt, s_base, pairs);
+    __syncthreads();
+    for (int t = tid; t < T; t += SCATTER_AGG_BLOCK) {
+        const uint32_t c = s_cnt[t];
+        if (c) s_base[t] = atomicAdd(&tile_ctr[(size_t)t * LG_CTR_STRIDE + 1], c);
+        s_cnt[t] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < SCATTER_AGG_IPT; u++)
+        scatter_walk<true>(x0[u], y0[u], x1[u], y1[u], (x1[u] - x0[u]) * (y1[u] - y0[u]), key[u],
+                           (uint32_t)(first + u * SCATTER_AGG_BLOCK), grid_x, lane, s_cnt, s_base, pairs);
+}
+
+// ------------------------------------------------------------------------------------------------ 4. SORT
+#ifndef TS_MIN_BLOCKS
+#define TS_MIN_BLOCKS 3
+#endif
+constexpr int TS_RADIX = 256;
+constexpr int TS_MAX_IPT = 16;
+constexpr int TS_MAX_GROUPS = 256;     // groups of 3+ entries queued per tile for the warps to rank
+constexpr int TS_MAX_GROUP_LEN = 128;  // longest group ranked that way (4 entries per lane)
+
+template <int THREADS>
+struct TsSmem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int MAXIPT = THREADS >= 1024 ? 8 : TS_MAX_IPT;  // entries per thread held in registers
+    static constexpr int CAP = THREADS * MAXIPT;
+    uint32_t warp_hist[WARPS][TS_RADIX];  // per warp and digit: running count, then exclusive prefix over warps
+    uint32_t excl[TS_RADIX];              // per digit: first slot inside the chunk
+    uint32_t base[TS_RADIX];              // multi-chunk passes: running global offset of every digit
+    uint32_t warp_sums[32];
+    uint32_t red[8];                      // [0] OR, [1] AND of the keys, [2] full-sort fallback, [3] min, [4] max, [5] #groups
+    uint32_t grp_start[TS_MAX_GROUPS];    // long groups left to the whole block (ts_fix_groups)
+    uint32_t grp_len[TS_MAX_GROUPS];
+    uint2 items[CAP];
+};
+
+template <int SEL>
+__device__ __forceinline__ uint32_t ts_key(const uint2& v) { return SEL == 0 ? v.x : v.y; }
+
+// Stable ranking of the block's chunk by one 8-bit digit.  Items are held warp-striped: warp w owns elements
+// [w * 32 * IPT, (w + 1) * 32 * IPT) of the chunk and item i of a lane is element w * 32 * IPT + i * 32 + lane, so
+// (warp, i, lane) order is element order.  On return rank[i] is the item's position among the warp's items of the same
+// digit, s.warp_hist[w][d] the number of such items in earlier warps, and (threads < 256) the return value the
+// chunk's count of digit `tid`.  The lanes sharing a digit are found with one ballot per digit bit (independent of
+// each other, so they pipeline; MATCH.ANY is far slower on sm_100a).
+template <int THREADS, int IPT, int SEL>
+__device__ __forceinline__ uint32_t ts_rank(TsSmem<THREADS>& s, const uint2 (&it)[IPT], uint32_t n, int shift,
+                                            uint32_t (&rank)[IPT], uint32_t sub = 0u) {
+    constexpr int WARPS = THREADS / 32;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t warp_base = warp * 32u * IPT;
+    for (int k = tid; k < WARPS * TS_RADIX; k += THREADS) (&s.warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        const bool valid = g < n;
+        const uint32_t d = ((ts_key<SEL>(it[i]) - sub) >> shift) & 255u;
+        unsigned p = __ballot_sync(0xffffffffu, valid);
+        if (p == 0u) { rank[i] = 0; continue; }  // warp-uniform: nothing left in this warp's slice
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            p &= bit ? m : ~m;
+        }
+        const unsigned before = p & lt_mask;
+        uint32_t pre = 0;
+        if (valid) pre = s.warp_hist[warp][d];
+        __syncwarp();
+        if (valid && before == 0) s.warp_hist[warp][d] = pre + __popc(p);
+        __syncwarp();
+        rank[i] = pre + __popc(before);
+    }
+    __syncthreads();
+    uint32_t count = 0;
+    if (tid < TS_RADIX) {
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const uint32_t c = s.warp_hist[w][tid];
+            s.warp_hist[w][tid] = count;
+            count += c;
+        }
+    }
+    return count;
+}
+
+// exclusive scan over the 256 digits of `count` (held by threads < 256) -> s.excl; ends with a block barrier
+template <int THREADS>
+__device__ __forceinline__ void ts_digit_scan(TsSmem<THREADS>& s, uint32_t count, uint32_t* dst, uint32_t offset) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (tid < TS_RADIX && lane == 31) s.warp_sums[warp] = incl;
+    __syncthreads();
+    if (tid < TS_RADIX) {
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < TS_RADIX / 32; w++) wbase += (w < (int)warp) ? s.warp_sums[w] : 0u;
+        dst[tid] = offset + wbase + incl - count;
+    }
+    __syncthreads();
+}
+
+// one in-shared-memory pass: items (registers, warp-striped) -> s.items in digit order -> back into the registers
+template <int THREADS, int IPT, int SEL>
+__device__ __forceinline__ void ts_pass_smem(TsSmem<THREADS>& s, uint2 (&it)[IPT], uint32_t n, int shift,
+                                             uint32_t sub = 0u) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t warp_base = warp * 32u * IPT;
+    uint32_t rank[IPT];
+    const uint32_t count = ts_rank<THREADS, IPT, SEL>(s, it, n, shift, rank, sub);
+    ts_digit_scan<THREADS>(s, count, s.excl, 0u);
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        if (g < n) {
+            const uint32_t d = ((ts_key<SEL>(it[i]) - sub) >> shift) & 255u;
+            s.items[s.excl[d] + s.warp_hist[warp][d] + rank[i]] = it[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        if (g < n) it[i] = s.items[g];
+    }
+}
+
+// The reference's order inside a tile is (depth bits, Gaussian id).  After the window passes the list is ordered by
+// (depth - min) >> lo only: entries of one group (equal window value — usually one entry, sometimes two) sit next to
+// each other in arbitrary order.  The thread that finds the start of a group orders a pair on the spot and queues
+// anything longer (equal depths: coincident points, a scene clipped to a box seen face-on); the warps of the block
+// then take the queued groups in turn and rank them by counting — every lane counts the group members that precede
+// its entry, reading the group as warp-wide broadcasts — which keeps the barrier behind this step short (a serial
+// insertion sort of a 30-entry group by one thread, 6000 dependent shared-memory cycles, held up the other 255).
+// Returns true when a group is longer than TS_MAX_GROUP_LEN or the queue overflows: the caller then falls back to the
+// full LSD sort.
+template <int THREADS>
+__device__ __forceinline__ bool ts_fix_groups(TsSmem<THREADS>& s, uint32_t n, uint32_t sub, int lo) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int PER_LANE = TS_MAX_GROUP_LEN / 32;
+    uint2* items = s.items;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t q = threadIdx.x; q + 1 < n; q += THREADS) {
+        const uint2 me = items[q], next = items[q + 1];
+        const uint32_t k = (me.x - sub) >> lo;
+        if (((next.x - sub) >> lo) != k || (q > 0 && ((items[q - 1].x - sub) >> lo) == k)) continue;
+        uint32_t L = 2;
+        while (q + L < n && L <= TS_MAX_GROUP_LEN && ((items[q + L].x - sub) >> lo) == k) L++;
+        if (L == 2) {
+            if (me.x > next.x || (me.x == next.x && me.y > next.y)) {
+                items[q] = next;
+                items[q + 1] = me;
+            }
+            continue;
+        }
+        const uint32_t slot = L <= TS_MAX_GROUP_LEN ? atomicAdd(&s.red[5], 1u) : (uint32_t)TS_MAX_GROUPS;
+        if (slot < (uint32_t)TS_MAX_GROUPS) {
+            s.grp_start[slot] = q;
+            s.grp_len[slot] = L;
+        } else {
+            s.red[2] = 1u;
+        }
+    }
+    __syncthreads();
+    if (s.red[2] != 0u) return true;
+    const uint32_t groups = s.red[5];
+    for (uint32_t gi = warp; gi < groups; gi += WARPS) {
+        const uint32_t start = s.grp_start[gi], L = s.grp_len[gi];
+        uint2 mine[PER_LANE];
+        uint32_t where[PER_LANE];
+#pragma unroll
+        for (int u = 0; u < PER_LANE; u++) {
+            const uint32_t j = lane + 32u * u;
+            mine[u] = j < L ? items[start + j] : make_uint2(0xffffffffu, 0xffffffffu);
+            where[u] = 0;
+        }
+        for (uint32_t i = 0; i < L; i++) {
+            const uint2 w = items[start + i];  // same address for the whole warp: a broadcast
+#pragma unroll
+            for (int u = 0; u < PER_LANE; u++) {
+                if (u * 32u < L) where[u] += (w.x < mine[u].x || (w.x == mine[u].x && w.y < mine[u].y)) ? 1u : 0u;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < PER_LANE; u++) {
+            const uint32_t j = lane + 32u * u;
+            if (j < L) items[start + where[u]] = mine[u];
+        }
+    }
+    __syncthreads();
+    return false;
+}
+
+// Sort of one list that fits the block's shared memory.  Fast path: two 8-bit ballot-ranked passes over a 16-bit
+// window of the depth keys — the top 16 bits of (key - min), i.e. 32769..65536 distinct values across the tile's
+// depth range — after which the few entries that share a window value are put right locally (ts_fix_groups).
+// (Shared-memory atomics would make a counting sort trivial, but ATOMS retires one lane every two cycles per SM: measured
+// 4x slower than nine ballots per entry and digit.)
+// Fallback (long runs of equal / nearly equal depths): full stable LSD sort, id digits first, then every depth digit
+// that varies inside the tile.
+template <int THREADS, int IPT>
+__device__ __forceinline__ void ts_sort_in_smem(TsSmem<THREADS>& s, const uint2* __restrict__ src, uint32_t n,
+                                                uint32_t* __restrict__ out, int id_bits) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t warp_base = warp * 32u * IPT;
+    uint2 it[IPT];
+    uint32_t vor = 0u, vand = 0xffffffffu, vmin = 0xffffffffu, vmax = 0u;
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const uint32_t g = warp_base + i * 32 + lane;
+        it[i] = make_uint2(0u, 0u);
+        if (g < n) {
+            it[i] = src[g];
+            vor |= it[i].x;
+            vand &= it[i].x;
+            vmin = min(vmin, it[i].x);
+            vmax = max(vmax, it[i].x);
+        }
+    }
+    vor = __reduce_or_sync(0xffffffffu, vor);
+    vand = __reduce_and_sync(0xffffffffu, vand);
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane == 0) {
+        atomicOr(&s.red[0], vor);
+        atomicAnd(&s.red[1], vand);
+        atomicMin(&s.red[3], vmin);
+        atomicMax(&s.red[4], vmax);
+    }
+    __syncthreads();
+    const uint32_t kmin = s.red[3], span = s.red[4] - kmin;
+    int lo = 0;
+    if (span == 0u) {  // all depths equal (or a single entry): one group
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const uint32_t g = warp_base + i * 32 + lane;
+            if (g < n) s.items[g] = it[i];
+        }
+        __syncthreads();
+    } else {
+        lo = max(0, (31 - __clz(span)) - 15);
+        ts_pass_smem<THREADS, IPT, 0>(s, it, n, lo, kmin);
+        if ((span >> lo) > 255u) ts_pass_smem<THREADS, IPT, 0>(s, it, n, lo + 8, kmin);
+    }
+    if (ts_fix_groups<THREADS>(s, n, kmin, lo)) {
+        const uint32_t varying = s.red[0] ^ s.red[1];  // depth bits that differ inside this tile
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const uint32_t g = warp_base + i * 32 + lane;
+            if (g < n) it[i] = s.items[g];
+        }
+#pragma unroll 1
+        for (int shift = 0; shift < id_bits; shift += 8) ts_pass_smem<THREADS, IPT, 1>(s, it, n, shift);
+#pragma unroll 1
+        for (int shift = 0; shift < 32; shift += 8) {
+            if (((varying >> shift) & 255u) == 0u) continue;  // a digit every key shares: nothing to reorder
+            ts_pass_smem<THREADS, IPT, 0>(s, it, n, shift);
+        }
+        __syncthreads();
+    }
+    for (uint32_t q = tid; q < n; q += THREADS) out[q] = s.items[q].y;
+}
+
+// Lists longer than the shared-memory capacity: the same LSD passes streamed through global memory, chunk by chunk,
+// between the tile's slices of the two pair buffers (id digits first, then the varying depth digits: no tie fix-up).
+template <int THREADS>
+__device__ void ts_sort_streamed(TsSmem<THREADS>& s, uint2* a, uint2* b, uint32_t n, uint32_t* __restrict__ out,
+                                 int id_bits) {
+    constexpr int IPT = TsSmem<THREADS>::MAXIPT;
+    constexpr uint32_t CAP = TsSmem<THREADS>::CAP;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t warp_base = warp * 32u * IPT;
+    uint32_t vor = 0u, vand = 0xffffffffu;
+    for (uint32_t g = tid; g < n; g += THREADS) {
+        const uint32_t k = a[g].x;
+        vor |= k;
+        vand &= k;
+    }
+    vor = __reduce_or_sync(0xffffffffu, vor);
+    vand = __reduce_and_sync(0xffffffffu, vand);
+    if (lane == 0) {
+        atomicOr(&s.red[0], vor);
+        atomicAnd(&s.red[1], vand);
+    }
+    __syncthreads();
+    const uint32_t varying = s.red[0] ^ s.red[1];
+    const int id_passes = (id_bits + 7) / 8;
+    uint2* src = a;
+    uint2* dst = b;
+#pragma unroll 1
+    for (int pass = 0; pass < id_passes + 4; pass++) {
+        const bool by_id = pass < id_passes;
+        const int shift = by_id ? 8 * pass : 8 * (pass - id_passes);
+        if (!by_id && ((varying >> shift) & 255u) == 0u) continue;
+        // digit totals of the whole list -> where every digit's run starts
+        if (tid < TS_RADIX) s.base[tid] = 0;
+        __syncthreads();
+        for (uint32_t g = tid; g < n; g += THREADS) {
+            const uint2 v = src[g];
+            atomicAdd(&s.base[((by_id ? v.y : v.x) >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        {
+            const uint32_t c = tid < TS_RADIX ? s.base[tid] : 0u;
+            __syncthreads();
+            ts_digit_scan<THREADS>(s, c, s.base, 0u);
+        }
+        for (uint32_t c0 = 0; c0 < n; c0 += CAP) {
+            const uint32_t cn = min(CAP, n - c0);
+            uint2 it[IPT];
+            uint32_t rank[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const uint32_t g = warp_base + i * 32 + lane;
+                it[i] = g < cn ? src[c0 + g] : make_uint2(0u, 0u);
+            }
+            const uint32_t count = by_id ? ts_rank<THREADS, IPT, 1>(s, it, cn, shift, rank)
+                                         : ts_rank<THREADS, IPT, 0>(s, it, cn, shift, rank);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const uint32_t g = warp_base + i * 32 + lane;
+                if (g < cn) {
+                    const uint32_t d = ((by_id ? it[i].y : it[i].x) >> shift) & 255u;
+                    dst[s.base[d] + s.warp_hist[warp][d] + rank[i]] = it[i];
+                }
+            }
+            __syncthreads();
+            if (tid < TS_RADIX) s.base[tid] += count;
+            __syncthreads();
+        }
+        uint2* t = src; src = dst; dst = t;
+        __threadfence_block();
+        __syncthreads();
+    }
+    for (uint32_t q = tid; q < n; q += THREADS) out[q] = src[q].y;
+}
+
+// One block per tile, longest lists first.  LARGE = false: 256 threads, lists of 1..4096 entries; LARGE = true:
+// 1024 threads, lists above 4096 (up to 8192 in shared memory, streamed beyond that).
+template <int THREADS, bool LARGE>
+__global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_kernel(const uint2* __restrict__ ranges,
+                                                            const uint32_t* __restrict__ order, uint2* pairs,
+                                                            uint2* pairs_alt, uint32_t* __restrict__ point_list,
+                                                            int id_bits, const uint32_t* __restrict__ counters,
+                                                            uint32_t capacity, int T) {
+    extern __shared__ __align__(16) unsigned char ts_smem_raw[];
+    TsSmem<THREADS>& s = *reinterpret_cast<TsSmem<THREADS>*>(ts_smem_raw);
+    if (counters[1] > capacity) return;
+    constexpr uint32_t SMALL_CAP = 256 * TS_MAX_IPT;
+    // LARGE: a few persistent blocks walk the launch order and pick out the long lists (empty 1024-thread blocks with
+    // 82 KB of shared memory cost ~6 us per wave to schedule, so one block per tile is not an option here)
+    for (uint32_t slot = blockIdx.x; slot < (uint32_t)T; slot += gridDim.x) {
+    const uint32_t tile = order[slot];
+    const uint2 range = ranges[tile];
+    const uint32_t n = range.y - range.x;
+    if (LARGE ? (n <= SMALL_CAP) : (n == 0 || n > SMALL_CAP)) continue;
+    __syncthreads();  // the previous list of this block is finished with the shared state
+    if (threadIdx.x == 0) {
+        s.red[0] = 0u;
+        s.red[1] = 0xffffffffu;
+        s.red[2] = 0u;
+        s.red[3] = 0xffffffffu;
+        s.red[4] = 0u;
+        s.red[5] = 0u;
+    }
+    __syncthreads();
+    const uint2* src = pairs + range.x;
+    uint32_t* out = point_list + range.x;
+    if constexpr (LARGE) {
+        if (n > TsSmem<THREADS>::CAP) {
+            ts_sort_streamed<THREADS>(s, pairs + range.x, pairs_alt + range.x, n, out, id_bits);
+            continue;
+        }
+    }
+    if constexpr (LARGE) {
+        ts_sort_in_smem<THREADS, TsSmem<THREADS>::MAXIPT>(s, src, n, out, id_bits);
+    } else {
+        const uint32_t per_thread = (n + THREADS - 1) / THREADS;
+        if (per_thread <= 2) ts_sort_in_smem<THREADS, 2>(s, src, n, out, id_bits);
+        else if (per_thread <= 4) ts_sort_in_smem<THREADS, 4>(s, src, n, out, id_bits);
+        else if (per_thread <= 8) ts_sort_in_smem<THREADS, 8>(s, src, n, out, id_bits);
+        else ts_sort_in_smem<THREADS, 16>(s, src, n, out, id_bits);
+    }
+    }
+}
+
+// inspection only (lg_state_read "point_list_keys"): the reference's sorted 64-bit keys, one block per tile
+__global__ void __launch_bounds__(256) rebuild_keys_kernel(const uint2* __restrict__ ranges,
                                                            const uint32_t* __restrict__ point_list,
                                                            const float* __restrict__ depths,
                                                            unsigned long long* __restrict__ keys) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    keys[idx] = ((unsigned long long)tile_keys[idx] << 32) | __float_as_uint(depths[point_list[idx]]);
+    const uint2 r = ranges[blockIdx.x];
+    for (uint32_t i = r.x + threadIdx.x; i < r.y; i += 256)
+        keys[i] = ((unsigned long long)blockIdx.x << 32) | __float_as_uint(depths[point_list[i]]);
 }
 
-// step 1: Gaussian ids in (depth bits, id) order -> g.depth_ids[0] (four 8-bit passes: the result is back in buffer 0)
-int launch_depth_order(int P, GeometryState& g, bool debug, cudaStream_t stream) {
-    bool in_b = false;
-    // the digit histograms were accumulated by the preprocess kernel
-    int rc = radix_sort_pairs_u32_prehist(g.depth_keys[0], g.depth_keys[1], g.depth_ids[0], g.depth_ids[1], (size_t)P, 0,
-                                          32, g.sort_temp, g.sort_temp_bytes, debug, stream, &in_b);
-    if (rc != LG_OK) return rc;
-    if (in_b) {
-        set_error("depth ordering: unexpected pass parity");
-        return LG_ERR_UNSUPPORTED;
+// step 2 (queued right behind the preprocess kernel; needs nothing from the host)
+int launch_tile_scan(int W, int H, ImageState& img, bool debug, cudaStream_t stream) {
+    const int T = num_tiles_x(W) * num_tiles_y(H);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(T, img.tile_ctr, img.ranges, img.tile_order, img.counters);
+    LG_LAUNCH_CHECK(debug, stream);
+    return LG_OK;
+}
+
+// steps 3 and 4 for a binning buffer of `capacity` entries (kernels are no-ops if num_rendered exceeds it)
+int launch_binning(int P, int capacity, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
+                   ImageState& img, bool debug, cudaStream_t stream) {
+    const int gx = num_tiles_x(W), gy = num_tiles_y(H);
+    const int T = gx * gy;
+    if (capacity <= 0 || P <= 0) return LG_OK;
+    const size_t agg_smem = 2 * sizeof(uint32_t) * (size_t)T;
+    if (SCATTER_AGGREGATE && gx <= 255 && gy <= 255 && agg_smem <= 160 * 1024 && P >= 64 * 1024) {
+        LG_CUDA(cudaFuncSetAttribute(scatter_pairs_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem));
+        const int per_block = SCATTER_AGG_BLOCK * SCATTER_AGG_IPT;
+        scatter_pairs_agg_kernel<<<(P + per_block - 1) / per_block, SCATTER_AGG_BLOCK, agg_smem, stream>>>(
+            P, T, g.rect_packed, g.depths, img.tile_ctr, b.pairs, gx, img.counters, (uint32_t)capacity);
+    } else {
+        scatter_pairs_kernel<<<(P + SCATTER_BLOCK - 1) / SCATTER_BLOCK, SCATTER_BLOCK, 0, stream>>>(
+            P, g.tiles_touched, (gx <= 255 && gy <= 255) ? g.rect_packed : nullptr, g.means2D, radii, g.depths,
+            img.tile_ctr, b.pairs, gx, gy, img.counters, (uint32_t)capacity);
+    }
+    LG_LAUNCH_CHECK(debug, stream);
+    const int id_bits = higher_msb((uint32_t)(P > 1 ? P - 1 : 1));
+    const size_t smem_small = sizeof(TsSmem<256>), smem_large = sizeof(TsSmem<1024>);
+    LG_CUDA(cudaFuncSetAttribute(tile_sort_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+    LG_CUDA(cudaFuncSetAttribute(tile_sort_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_large));
+    tile_sort_kernel<256, false><<<T, 256, smem_small, stream>>>(img.ranges, img.tile_order, b.pairs, b.pairs_alt,
+                                                                b.point_list, id_bits, img.counters, (uint32_t)capacity, T);
+    LG_LAUNCH_CHECK(debug, stream);
+    if ((size_t)capacity > 256 * TS_MAX_IPT) {
+        tile_sort_kernel<1024, true><<<min(T, LG_NUM_SMS), 1024, smem_large, stream>>>(
+            img.ranges, img.tile_order, b.pairs, b.pairs_alt, b.point_list, id_bits, img.counters, (uint32_t)capacity, T);
+        LG_LAUNCH_CHECK(debug, stream);
     }
     return LG_OK;
 }
 
-// steps 2 and 3 + tile ranges
-int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
-                   ImageState& img, bool debug, cudaStream_t stream) {
-    const int gx = num_tiles_x(W), gy = num_tiles_y(H);
-    const int T = gx * gy;
-    LG_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, stream));
-    if (R <= 0) return launch_tile_order(T, reinterpret_cast<const uint32_t*>(img.ranges), 2, img.tile_order, stream);
-    const int end_bit = higher_msb((uint32_t)T);
-    const int passes = radix_sort_num_passes(0, end_bit);
-    // ping-pong so that the sorted list ends in tile_keys / point_list
-    uint32_t* ka = (passes & 1) ? b.tile_keys_unsorted : b.tile_keys;
-    uint32_t* kb = (passes & 1) ? b.tile_keys : b.tile_keys_unsorted;
-    uint32_t* va = (passes & 1) ? b.point_list_unsorted : b.point_list;
-    uint32_t* vb = (passes & 1) ? b.point_list : b.point_list_unsorted;
-    const int blocks = (P + EMIT_TILE - 1) / EMIT_TILE;
-    LG_CUDA(cudaMemsetAsync(g.emit_scan_state, 0, sizeof(unsigned long long) * (size_t)blocks, stream));
-    bool in_b = false;
-    int rc;
-    // the emission kernel accumulates the digit histograms of the tile ids it writes (no separate histogram pass);
-    // beyond 16 tile-id bits (more than 65535 tiles) the generic path recomputes them
-    rc = radix_sort_clear(b.sort_temp, (size_t)R, passes, stream);
-    if (rc != LG_OK) return rc;
-    const uint32_t mask0 = (1u << (end_bit < 8 ? end_bit : 8)) - 1u;
-    const uint32_t mask1 = end_bit > 8 ? (1u << (end_bit - 8 < 8 ? end_bit - 8 : 8)) - 1u : 0u;
-    emit_pairs_kernel<<<blocks, EMIT_BLOCK, 0, stream>>>(
-        P, g.depth_ids[0], g.tiles_touched, (gx <= 255 && gy <= 255) ? g.rect_packed : nullptr, g.means2D, radii, ka, va,
-        gx, gy, g.emit_scan_state, g.counters + 2, radix_sort_hist_ptr(b.sort_temp), mask0, mask1);
-    LG_LAUNCH_CHECK(debug, stream);
-    if (passes <= 2)
-        rc = radix_sort_pairs_u32_prehist(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug,
-                                          stream, &in_b);
-    else
-        rc = radix_sort_pairs_u32(ka, kb, va, vb, (size_t)R, 0, end_bit, b.sort_temp, b.sort_temp_bytes, debug, stream,
-                                  &in_b);
-    if (rc != LG_OK) return rc;
-    tile_ranges_kernel<<<((R + 3) / 4 + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, img.ranges);
-    LG_LAUNCH_CHECK(debug, stream);
-    return launch_tile_order(T, reinterpret_cast<const uint32_t*>(img.ranges), 2, img.tile_order, stream);
-}
-
-int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,
-                        cudaStream_t stream) {
-    if (R <= 0) return LG_OK;
-    rebuild_keys_kernel<<<(R + 255) / 256, 256, 0, stream>>>((uint32_t)R, b.tile_keys, b.point_list, g.depths, keys_out);
+int launch_rebuild_keys(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
+                        unsigned long long* keys_out, cudaStream_t stream) {
+    const int T = num_tiles_x(W) * num_tiles_y(H);
+    rebuild_keys_kernel<<<T, 256, 0, stream>>>(img.ranges, b.point_list, g.depths, keys_out);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }

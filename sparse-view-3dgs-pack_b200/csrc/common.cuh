@@ -11,6 +11,7 @@
 #define LG_TILE_PIX (LG_TILE_X * LG_TILE_Y)
 #define LG_MAX_CHANNELS 4
 #define LG_NUM_SMS 148
+#define LG_CTR_STRIDE 32  // words between the binning counters of consecutive tiles (one 128-byte line each)
 
 namespace lg {
 
@@ -57,17 +58,8 @@ struct GeometryState {
     float4* conic_opacity;    // P
     float* rgb;               // channels * P
     uint32_t* tiles_touched;  // P
-    uint32_t* point_offsets;  // unused by the pipeline (lg_state_read rebuilds the reference's scan on demand)
-    unsigned long long* scan_state;  // one descriptor per 256-Gaussian block (decoupled look-back)
-    uint32_t* counters;       // [0] preprocess ticket, [1] num_rendered, [2] emit ticket, [3..] spare
-    float* grad_scratch;      // backward only: 12 floats / Gaussian packed 2-D gradient record
-    // depth ordering of the Gaussians (binning.cu): ping-pong (depth bits, Gaussian id) pairs + radix-sort scratch
-    uint32_t* depth_keys[2];  // P each
-    uint32_t* depth_ids[2];   // P each
     uint32_t* rect_packed;    // P: tile rectangle x0 | y0 << 8 | x1 << 16 | y1 << 24 (grids up to 255 x 255 tiles)
-    unsigned long long* emit_scan_state;  // look-back descriptors of the key-emission scan
-    char* sort_temp;
-    size_t sort_temp_bytes;
+    float* grad_scratch;      // backward only: 12 floats / Gaussian packed 2-D gradient record
     static GeometryState from_chunk(char*& chunk, size_t P, int channels);
 };
 size_t geometry_state_bytes(size_t P, int channels);
@@ -76,22 +68,25 @@ struct ImageState {
     float* accum_alpha;   // W*H final transmittance
     uint32_t* n_contrib;  // W*H
     uint2* ranges;        // T
-    // launch order of the tiles in the blend kernels, heaviest first (longest-processing-time-first scheduling: the
-    // hardware hands out blocks in blockIdx order, so the long tiles of the image centre no longer form the tail)
-    uint32_t* tile_order;      // T: forward, by list length
+    // launch order of the tiles in the sort / blend kernels, heaviest first (longest-processing-time-first scheduling:
+    // the hardware hands out blocks in blockIdx order, so the long tiles of the image centre no longer form the tail)
+    uint32_t* tile_order;      // T: tile sort and blend forward, by list length
     uint32_t* tile_neff;       // T: entries that reached some pixel of the tile (max n_contrib), written by the forward
     uint32_t* tile_order_bwd;  // T: backward, by tile_neff
+    uint32_t* counters;        // 8 words: [1] num_rendered (total list length, written by the tile scan)
+    // Per-tile binning counters, one 128-byte line per tile (atomics on one line serialise in its L2 slice: with the
+    // counters packed, 3.6 M increments on 80 lines took 160 us; one line per tile spreads them over all slices).
+    // word 0 = list length (counted by the preprocess kernel), word 1 = write cursor of the scatter step.
+    // Directly behind `counters`, cleared by the same memset.
+    uint32_t* tile_ctr;        // T * LG_CTR_STRIDE
     static ImageState from_chunk(char*& chunk, size_t W, size_t H);
 };
 size_t image_state_bytes(size_t W, size_t H);
 
 struct BinningState {
-    uint32_t* point_list;            // R Gaussian ids sorted by (tile, depth, id)
-    uint32_t* point_list_unsorted;   // R
-    uint32_t* tile_keys;             // R tile ids, sorted
-    uint32_t* tile_keys_unsorted;    // R
-    char* sort_temp;                 // radix-sort scratch
-    size_t sort_temp_bytes;
+    uint2* pairs;          // R (depth bits, Gaussian id), grouped by tile, unsorted inside a tile
+    uint2* pairs_alt;      // R ping-pong buffer of lists too long for shared memory
+    uint32_t* point_list;  // R Gaussian ids sorted by (tile, depth, id)
     static BinningState from_chunk(char*& chunk, size_t R);
 };
 size_t binning_state_bytes(size_t R);
@@ -122,14 +117,16 @@ struct ForwardArgs {
     bool debug;
 };
 
-int launch_preprocess(const ForwardArgs& a, GeometryState& g, int* radii, cudaStream_t stream);
-int launch_depth_order(int P, GeometryState& g, bool debug, cudaStream_t stream);
-int launch_binning(int P, int R, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
+int launch_preprocess(const ForwardArgs& a, GeometryState& g, ImageState& img, int* radii, cudaStream_t stream);
+// binning (binning.cu): tile scan (ranges, cursors, num_rendered, launch order), then scatter + per-tile sort into a
+// binning buffer of `capacity` entries (no-ops on the device when num_rendered exceeds it)
+int launch_tile_scan(int W, int H, ImageState& img, bool debug, cudaStream_t stream);
+int launch_binning(int P, int capacity, int W, int H, const GeometryState& g, const int* radii, BinningState& b,
                    ImageState& img, bool debug, cudaStream_t stream);
-int launch_rebuild_keys(int R, const GeometryState& g, const BinningState& b, unsigned long long* keys_out,
-                        cudaStream_t stream);
+int launch_rebuild_keys(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
+                        unsigned long long* keys_out, cudaStream_t stream);
 // order[0..T) = tile indices by descending key (bucketed; ties in no particular order) — scheduling only
-int launch_tile_order(int T, const uint32_t* keys, int key_stride, uint32_t* order, cudaStream_t stream);
+int launch_tile_order(int T, const uint32_t* keys, uint32_t* order, cudaStream_t stream);
 int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream);

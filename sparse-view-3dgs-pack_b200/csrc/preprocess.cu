@@ -1,7 +1,7 @@
 // preprocess.cu — per-Gaussian forward stage: frustum cull, EWA projection, 2-D covariance / conic, SH -> RGB,
-// radius and tile rectangle, fused with the prefix sum of tiles_touched (single-pass decoupled look-back), so
-// one kernel replaces the reference's preprocessCUDA + cub::DeviceScan::InclusiveSum
-// (DGR/cuda_rasterizer/forward.cu:151-269, rasterizer_impl.cu:280).
+// radius and tile rectangle (the reference's preprocessCUDA, DGR/cuda_rasterizer/forward.cu:151-269), fused with the
+// first step of the binning: every Gaussian adds 1 to the list length of each tile its rectangle covers
+// (csrc/binning.cu; takes the place of cub::DeviceScan::InclusiveSum over tiles_touched, rasterizer_impl.cu:280).
 //
 // Numerical contract: every quantity that decides radii / tile rectangles / depth bits is evaluated with
 // explicitly rounded intrinsics in exactly the operation order of the reference's sm_100a SASS (nvcc 12.9 -O3):
@@ -14,6 +14,7 @@ namespace lg {
 
 #define PRE_BLOCK 256
 #define PRE_MAX_ROW 48  // widest SH row (floats per Gaussian) staged through shared memory
+#define PRE_COOP 8      // tile rectangles above this many tiles are counted by the whole warp
 
 struct PreArgs {
     int P, D, M, C;
@@ -41,13 +42,8 @@ struct PreArgs {
     float4* __restrict__ conic_opacity;
     uint8_t* __restrict__ clamped;
     uint32_t* __restrict__ tiles_touched;
-    uint32_t* __restrict__ point_offsets;
-    uint32_t* __restrict__ depth_keys;
-    uint32_t* __restrict__ depth_ids;
     uint32_t* __restrict__ rect_packed;
-    uint32_t* depth_hist;  // 4 x 256 digit counters of the depth keys (radix-sort scratch), accumulated here
-    unsigned long long* scan_state;
-    uint32_t* counters;
+    uint32_t* tile_ctr;    // per-tile counter lines (zeroed by the launcher): word 0 = list length, accumulated here
 };
 
 // transformPoint4x3 / 4x4 row (DGR/cuda_rasterizer/auxiliary.h:70-89): m0*x + m4*y + m8*z + m12 compiles to
@@ -125,10 +121,6 @@ template <bool STAGED, int M3C>
 __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     extern __shared__ float s_tile_dyn[];
     __shared__ float s_cam[35];  // view 0..15, proj 16..31, campos 32..34
-    __shared__ uint32_t s_hist[4 * 256];
-#pragma unroll
-    for (int k = 0; k < 4; k++) s_hist[k * 256 + threadIdx.x] = 0;
-
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.viewmatrix + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(a.projmatrix + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(a.cam_pos + threadIdx.x - 32);
@@ -139,6 +131,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
     const float* PM = s_cam + 16;
 
     uint32_t tiles = 0;
+    uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;  // tile rectangle (all zero = emits nothing)
     int radius_out = 0;
     bool need_sh = false;
     float depth_out = 0.0f;
@@ -246,19 +239,34 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
                     const float opacity = __ldg(a.opacities + idx);
                     a.conic_opacity[idx] = make_float4(con_x, con_y, con_z, F_MUL(h_scaling, opacity));
                     tiles = n;
+                    rx0 = x0; ry0 = y0; rx1 = x1; ry1 = y1;
                     radius_out = radius;
                 }
             }
         }
         a.radii[idx] = radius_out;
         a.tiles_touched[idx] = tiles;
-        // input of the depth ordering (binning.cu): Gaussians that emit no key sort behind every real depth
-        const uint32_t dkey = tiles ? __float_as_uint(depth_out) : 0xffffffffu;
-        a.depth_keys[idx] = dkey;
-        a.depth_ids[idx] = (uint32_t)idx;
         a.rect_packed[idx] = rect_out;
-#pragma unroll
-        for (int k = 0; k < 4; k++) atomicAdd(&s_hist[k * 256 + ((dkey >> (8 * k)) & 255u)], 1u);
+    }
+
+    // ---- binning step 1 (binning.cu): list length of every tile.  Fire-and-forget reductions (RED.ADD), one per
+    // overlap; rectangles of more than PRE_COOP tiles are walked by the whole warp.
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        if (tiles > 0 && tiles <= PRE_COOP) {
+            for (uint32_t y = ry0; y < ry1; y++)
+                for (uint32_t x = rx0; x < rx1; x++) atomicAdd(a.tile_ctr + (size_t)(y * (uint32_t)a.grid_x + x) * LG_CTR_STRIDE, 1u);
+        }
+        unsigned big = __ballot_sync(0xffffffffu, tiles > PRE_COOP);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, rx0, src), by0 = __shfl_sync(0xffffffffu, ry0, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, rx1, src) - bx0;
+            const uint32_t bn = __shfl_sync(0xffffffffu, tiles, src);
+            for (uint32_t k = lane; k < bn; k += 32)
+                atomicAdd(a.tile_ctr + (size_t)((by0 + k / bw) * (uint32_t)a.grid_x + bx0 + k % bw) * LG_CTR_STRIDE, 1u);
+        }
     }
 
     // ---- SH -> RGB (forward.cu:20-71) for the Gaussians that survived culling; needs only 1e-5 image parity, the
@@ -347,20 +355,6 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         }
     }
 
-    // ---- num_rendered = sum of tiles_touched (the only scan product the pipeline still needs: the pair offsets are
-    // computed in depth order by the emission kernel, binning.cu); one atomic per warp
-    {
-        uint32_t sum = tiles;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if ((threadIdx.x & 31u) == 0 && sum) atomicAdd(&a.counters[1], sum);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t c = s_hist[k * 256 + threadIdx.x];
-        if (c) atomicAdd(a.depth_hist + k * 256 + threadIdx.x, c);
-    }
 }
 
 // inspection only (lg_state_read "point_offsets"): the reference's inclusive scan of tiles_touched
@@ -405,7 +399,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
     present[idx] = (depth <= 0.2f) ? 0 : 1;  // in_frustum (auxiliary.h:166)
 }
 
-int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaStream_t stream) {
+int launch_preprocess(const ForwardArgs& f, GeometryState& g, ImageState& img, int* radii, cudaStream_t stream) {
     PreArgs a;
     a.P = f.P; a.D = f.D; a.M = f.M; a.C = f.C;
     a.means3D = f.means3D; a.scales = f.scales; a.scale_modifier = f.scale_modifier; a.rotations = f.rotations;
@@ -416,15 +410,10 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, int* radii, cudaSt
     a.prefiltered = f.prefiltered; a.antialiasing = f.antialiasing;
     a.radii = radii; a.means2D = g.means2D; a.depths = g.depths; a.cov3Ds = g.cov3D; a.rgb = g.rgb;
     a.conic_opacity = g.conic_opacity; a.clamped = g.clamped; a.tiles_touched = g.tiles_touched;
-    a.point_offsets = g.point_offsets; a.depth_keys = g.depth_keys[0]; a.depth_ids = g.depth_ids[0];
-    a.rect_packed = g.rect_packed; a.depth_hist = radix_sort_hist_ptr(g.sort_temp);
-    a.scan_state = g.scan_state; a.counters = g.counters;
+    a.rect_packed = g.rect_packed; a.tile_ctr = img.tile_ctr;
     const int blocks = (f.P + PRE_BLOCK - 1) / PRE_BLOCK;
-    LG_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 8, stream));
-    {   // the kernel also accumulates the digit histograms of the depth keys for the depth ordering that follows
-        int rc = radix_sort_clear(g.sort_temp, (size_t)f.P, 4, stream);
-        if (rc != LG_OK) return rc;
-    }
+    // counters and the per-tile counter lines are adjacent: one memset
+    LG_CUDA(cudaMemsetAsync(img.counters, 0, sizeof(uint32_t) * LG_CTR_STRIDE * (1 + (size_t)a.grid_x * a.grid_y), stream));
     const int M3 = 3 * f.M;
     if (f.colors_precomp == nullptr && M3 <= PRE_MAX_ROW) {
         const size_t smem = sizeof(float) * PRE_BLOCK * (size_t)(M3 | 1);

@@ -213,3 +213,44 @@ def test_active_sh_degree_scale_modifier_and_debug(sh_degree, scale_modifier, de
     if used < 16:
         assert not mine["dL_dsh"].view(-1, 16, 3)[:, used:, :].any()
         assert not refs[0]["dL_dsh"].view(-1, 16, 3)[:, used:, :].any()
+
+
+def _binning_case(sc, cam):
+    """forward through both implementations; the whole binning product must be the reference's bit for bit"""
+    t, c = helpers.scene_to_torch(sc), helpers.cam_to_torch(cam)
+    bg = torch.zeros(3, device="cuda")
+    ours = helpers.run_ours(t, c, cam, bg)
+    ref = helpers.run_ref(t, c, cam, bg)
+    assert ours["num_rendered"] == ref["num_rendered"] > 0
+    for k in ("radii", "tiles_touched", "ranges", "point_list_keys", "point_list", "n_contrib", "final_T"):
+        _assert_bit_equal(k, ours[k], ref[k])
+    assert float((ours["color"] - ref["color"]).abs().max()) <= IMG_ATOL
+    r = ours["ranges"].view(-1, 2)
+    return int((r[:, 1] - r[:, 0]).max()), ours
+
+
+@pytest.mark.parametrize("levels", [1, 3, 40])
+def test_equal_depths_are_ordered_by_gaussian_id(levels):
+    """Gaussians on `levels` planes facing the camera share their depth bits exactly, so inside every tile the order is
+    decided by the Gaussian id alone (the reference's stable sort keeps duplicateWithKeys' ascending-id order,
+    rasterizer_impl.cu:93-108,306-311).  One plane = every tile list is a single run of equal keys."""
+    _need_ref()
+    sc = scenes.blender_init_scene(60_000, seed=21, spacing_scale=0.02)
+    z = (np.arange(sc.means3D.shape[0]) % levels).astype(np.float32) * 0.25
+    sc.means3D[:, 2] = z
+    cam = scenes.look_at_camera(320, 240, 0.6911, 0.6911 * 240 / 320, (0.0, 0.0, -4.0))
+    longest, ours = _binning_case(sc, cam)
+    depths = ours["depths"][ours["radii"] > 0]
+    assert int(torch.unique(depths.view(torch.int32)).numel()) == levels
+    assert longest > 64
+
+
+@pytest.mark.parametrize("P,expect_longer_than", [(120_000, 4096), (400_000, 8192)])
+def test_very_long_tile_lists(P, expect_longer_than):
+    """a small image flooded with Gaussians: tile lists beyond 4096 entries (512-thread shared-memory sort) and beyond
+    8192 (sort streamed through global memory), against the reference's global 64-bit sort"""
+    _need_ref()
+    sc = scenes.trained_like_scene(P, seed=22, sigma_xyz=0.12, clip=0.4, log_scale_mean=np.log(0.004))
+    cam = scenes.look_at_camera(96, 64, 0.6911, 0.6911 * 64 / 96, (0.0, 0.0, -4.03))
+    longest, _ = _binning_case(sc, cam)
+    assert longest > expect_longer_than, longest
