@@ -12,14 +12,20 @@ ranks cannot map each other's memory or with LGDWT_EXCHANGE=nccl).  ms/view = ms
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...     # the reference's own CUDA rasterizer (oracle/_ref), same metric
+    python bench.py --impl reference ...     # the UNMODIFIED reference extension (baseline/_ref/site/dgr_3dgs), same metric
 
 One JSON line on rank 0.  `value`: operator fwd+bwd with all inputs resident in HBM.  `e2e`: the same step through
 the public torch operator with the step's inputs (camera matrices + ground-truth image) copied from pinned host
 memory, an L1 loss against that image (`lgdwt_b200.fused_l1_loss` here, the stock torch expression in the
-reference arm), backward, and a device->host read of the loss.  `roofline`: the dominant
-kernel against its bound, timed live with CUDA events on the launching stream; `stages`: every stage likewise.
-`cpu_baseline`: the CPU oracle (a port: the reference has no CPU rasterizer) timed on this box's cores.
+reference arm), backward, and a device->host read of the loss.  `dropin` (N = 1): both numbers again through the
+operator exactly as the unchanged LG/train.py calls it (no GradSinks: fresh gradient tensors, autograd accumulation).
+`roofline`: the dominant kernel against its bound — HBM peak from MEASURED_PEAKS.json, FP32 / MUFU / LDS / SHFL peaks
+measured on the box at the start of the run (csrc/microbench.cu) — timed live with CUDA events on the launching stream;
+`stages`: every stage likewise.  `cpu_baseline`: the CPU oracle (a port: the reference has no CPU rasterizer) timed on
+this box's cores.  `exchange` (N > 1): NCCL vs the peer-memory kernels, plus the correctness of the peer all-reduce
+against NCCL and the bit-identity of the replicas.  `image_loss` / `train_iteration` (N = 1): BASELINE configs 1 and 3.
+`cfg5` (every N): BASELINE config 5 — 6 M Gaussians, 1920x1080, the 32-view batch split over the ranks (strong scaling).
+The reference arm imports nothing of this repo's package: its process maps only the reference's own libraries.
 """
 import argparse
 import json
@@ -34,15 +40,30 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "sparse-view-3dgs-pack_b200"))
+PKG = os.path.join(ROOT, "sparse-view-3dgs-pack_b200")
+REF_SITE = os.path.join(ROOT, "baseline", "_ref", "site")   # the stock reference extensions (baseline/install_reference.sh)
 sys.path.insert(0, ROOT)
+
+
+def _load_scenes():
+    """the numpy-only scene generators, loaded by file path: the reference arm must not put this repo's package
+    (whose import loads liblgdwt_b200.so) on its path"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lgdwt_scenes", os.path.join(PKG, "lgdwt_scenes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["lgdwt_scenes"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+scenes = _load_scenes()
 
 P_GAUSSIANS = 1_000_000
 WIDTH = HEIGHT = 800
 SH_DEGREE = 3
 N_CAMERAS = 8
 VIEWS_PER_RANK = 4  # views per rank per step (gradient accumulation); x 8 ranks = the 32-view batch of config 5
-FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: not in MEASURED_PEAKS.json
+FP32_SIMT_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # only a fallback: the FFMA peak is measured on the box
 
 
 def env_int(name, default):
@@ -94,7 +115,6 @@ class ClockSampler:
 
 
 def make_workload(device):
-    from lgdwt_b200 import scenes
     sc = scenes.trained_like_scene(P_GAUSSIANS, seed=1)
     cams = [scenes.metric_camera(WIDTH, HEIGHT)] + scenes.orbit_cameras(N_CAMERAS - 1, WIDTH, HEIGHT, phase=0.4)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
@@ -103,15 +123,23 @@ def make_workload(device):
 
 
 def cam_dict(cam, device):
-    from lgdwt_b200.dp import camera_to_device
-    return camera_to_device(cam, device)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device)
+    return dict(W=cam.image_width, H=cam.image_height, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), campos=t(cam.campos))
 
 
 class Stepper:
-    """One benchmark step for either implementation; identical work outside the operator."""
+    """One benchmark step for either implementation; identical work outside the operator.
+    mode "sinks"  : this repo's operator with GradSinks (gradients accumulated by the backward kernel itself in one flat
+                    bucket: the data-parallel design, what `value` / `e2e` report);
+    mode "dropin" : this repo's operator exactly as the unchanged LG/train.py calls it (fresh gradient tensors per view,
+                    summed by autograd) — reported next to the headline as `dropin`;
+    mode "stock"  : the UNMODIFIED reference extension dgr_3dgs (built by its own setup.py into baseline/_ref/site)
+                    through its own GaussianRasterizationSettings / GaussianRasterizer;
+    mode "mirror" : fallback when baseline/_ref is absent: the reference's CUDA files behind oracle/ref_cuda.py."""
 
-    def __init__(self, impl, params, device, world):
-        self.impl, self.p, self.device, self.world = impl, params, device, world
+    def __init__(self, mode, params, device, world):
+        self.mode, self.p, self.device, self.world = mode, params, device, world
         self.bg = torch.zeros(3, device=device)
         P = params["means3D"].shape[0]
         self.P = P
@@ -123,7 +151,7 @@ class Stepper:
         self.dev_gt = [torch.empty((3, HEIGHT, WIDTH), device=device) for _ in range(VIEWS_PER_RANK)]
         # the flat gradient bucket (what a data-parallel step all-reduces): means3D 3 | shs 48 | opacity 1 | scales 3 | rot 4
         self.peer, self.peer_unavailable = None, ""
-        if impl == "ours" and world > 1:
+        if mode == "sinks" and world > 1:
             # the exchange step over NVLink peer memory (csrc/peer.cu); NCCL all-reduce when the ranks cannot map
             # each other's memory (LGDWT_EXCHANGE=nccl forces it)
             if os.environ.get("LGDWT_EXCHANGE", "peer") == "peer":
@@ -138,31 +166,39 @@ class Stepper:
             views[k] = self.bucket[off * P:(off + w) * P].view(params[k].shape)
             off += w
         self.views = views
-        if impl == "ours":
+        if mode in ("sinks", "dropin"):
             from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, GradSinks
             self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
             from lgdwt_b200 import fused_l1_loss
             self.l1 = fused_l1_loss
             self.sinks = GradSinks(views["means3D"], views["shs"], views["opacities"], views["scales"],
-                                   views["rotations"])
+                                   views["rotations"]) if mode == "sinks" else None
+        elif mode == "stock":
+            if REF_SITE not in sys.path:
+                sys.path.insert(0, REF_SITE)
+            from dgr_3dgs import GaussianRasterizationSettings, GaussianRasterizer
+            self.RS, self.R = GaussianRasterizationSettings, GaussianRasterizer
         else:
             from oracle import ref_cuda
             self.ref = ref_cuda
 
     def render(self, cam, first):
         p = self.p
-        if self.impl == "ours":
-            rs = self.RS(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], self.bg, 1.0, cam["viewmatrix"],
-                         cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, False)
+        if self.mode == "mirror":
+            return self.ref.RefRasterize.apply(p["means3D"], self.means2D, p["shs"], p["opacities"], p["scales"],
+                                               p["rotations"], cam, self.bg, SH_DEGREE)
+        rs = self.RS(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], self.bg, 1.0, cam["viewmatrix"],
+                     cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, False)
+        kw = dict(means3D=p["means3D"], means2D=self.means2D, shs=p["shs"], opacities=p["opacities"],
+                  scales=p["scales"], rotations=p["rotations"])
+        if self.mode == "sinks":
             self.sinks.accumulate = not first  # the first view of a step overwrites the bucket: no zero-fill pass
-            return self.R(rs)(means3D=p["means3D"], means2D=self.means2D, shs=p["shs"], opacities=p["opacities"],
-                              scales=p["scales"], rotations=p["rotations"], grad_sinks=self.sinks)
-        return self.ref.RefRasterize.apply(p["means3D"], self.means2D, p["shs"], p["opacities"], p["scales"],
-                                           p["rotations"], cam, self.bg, SH_DEGREE)
+            kw["grad_sinks"] = self.sinks
+        return self.R(rs)(**kw)
 
     def begin_step(self):
         self.means2D.grad = None
-        if self.impl != "ours":  # stock path: autograd sums the views into .grad
+        if self.mode != "sinks":  # autograd sums the views into .grad
             for t in self.p.values():
                 t.grad = None
 
@@ -170,7 +206,7 @@ class Stepper:
         """the path's only collective: sum the 236 B/Gaussian gradient bucket over ranks"""
         if self.world <= 1:
             return
-        if self.impl != "ours":
+        if self.mode != "sinks":
             for k, _ in self.fields:
                 self.views[k].copy_(self.p[k].grad)
         if self.peer is not None:
@@ -202,7 +238,7 @@ class Stepper:
                 self.copy_done[v].record(self.copy_stream)
             color, radii, invd = self.render(cam, v == 0)
             main.wait_event(self.copy_done[v])
-            if self.impl == "ours":   # this repo's public loss op; the reference arm keeps the stock torch expression
+            if self.mode in ("sinks", "dropin"):   # this repo's public loss op; the reference arm keeps the stock torch expression
                 loss = self.l1(color, self.dev_gt[v])
             else:
                 loss = (color - self.dev_gt[v]).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
@@ -271,7 +307,27 @@ def exchange_section(stepper, device, world):
             ex.check()
         except RuntimeError as e:   # a flag barrier timed out somewhere in this run: say so instead of dying
             out["peer_barrier_timeout"] = str(e)
+        # correctness of the exchange the timed step uses (the 1-GPU test box cannot run tests/peer_worker.py): the
+        # peer-memory all-reduce of rank-dependent data against NCCL's, and bit-identity of the result across ranks
+        rank = dist.get_rank()
+        gen = torch.Generator(device=device).manual_seed(100 + rank)
+        data = torch.randn(stepper.bucket.numel(), device=device, generator=gen)
+        expect = data.clone()
+        dist.all_reduce(expect)
+        ex.grad.copy_(data)
+        ex.allreduce(1.0)
+        got = ex.grad.clone()
+        err = (got - expect).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        lo, hi = got.clone(), got.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["max_abs_err_vs_nccl"] = float(err)
+        out["max_abs_value"] = float(expect.abs().max())
+        out["replicas_bit_identical"] = bool(torch.equal(lo.view(torch.int32), hi.view(torch.int32)))
+        del data, expect, got, lo, hi
         n = stepper.bucket.numel() * 4
+        out["nvlink_frac_of_900GBps_each_way"] = round(n * (world - 1) / world / (out["peer_allreduce_ms"] * 1e-3) / 900e9, 3)
         out["nvlink_bytes_per_rank_each_way"] = int(n * (world - 1) / world)
         out["peer_fused_GBps_each_way"] = round(n * (world - 1) / world / (out["peer_fused_reduce_adam_gather_ms"] * 1e-3) / 1e9, 1)
     return out
@@ -298,7 +354,7 @@ def image_loss_section(device, hbm_peak):
     """BASELINE config 1 (LGDWT-GS Haar DWT loss on a 3x800x800 render/GT pair) plus the photometric terms: the
     fused kernels forward+backward on the GPU against their HBM roofline, and the CPU port of the reference's
     PyTorch op chain on this box's cores as a reported baseline."""
-    from lgdwt_b200 import fused_dwt_loss, fused_photometric_loss, scenes
+    from lgdwt_b200 import fused_dwt_loss, fused_photometric_loss
     from oracle import dwt_oracle, photometric_oracle
     pred_np, gt_np = scenes.dwt_pair(3, HEIGHT, WIDTH, seed=0)
     pred = torch.from_numpy(pred_np).to(device).requires_grad_(True)
@@ -338,19 +394,18 @@ def train_iteration_section(impl, device, iters=40, warm=10):
     """BASELINE config 3: one LLFF-style training iteration (LG/train.py:105-288) at 1008x756 on the 500k-Gaussian
     slab scene — activations, render, L1 + SSIM + global/patch DWT loss, backward, densification statistics, Adam —
     plus one densify_and_prune call.  `ours`: raw parameters in the flat buffer, every stage a fused kernel of this
-    repo.  `reference`: the stock op chain (six nn.Parameters, torch activations, the reference CUDA rasterizer,
-    the PyTorch loss chain with its host-side running-mean ratio, torch.optim.Adam).  CUDA-event breakdown."""
+    repo (dp.RunningMeanLoss keeps the running-mean DWT scale on the device).  `reference`: the stock op chain (six
+    nn.Parameters, torch activations, the stock reference rasterizer extension, the PyTorch loss chain with its
+    host-side running-mean ratio, torch.optim.Adam) — nothing of this repo's package.  CUDA-event breakdown."""
     import math
-    from lgdwt_b200 import densify, dp, scenes
     Wd, Hd, V = 1008, 756, 3
     sc = scenes.slab_scene(500_000, seed=2)
     fovy = 2 * math.atan(math.tan(0.525) * Hd / Wd)
-    cams = [dp.camera_to_device(scenes.look_at_camera(Wd, Hd, 1.05, fovy, (0.25 * (k - 1), 0.0, 0.0), target=(0.0, 0.0, 5.0)),
-                                device) for k in range(V)]
+    cams = [cam_dict(scenes.look_at_camera(Wd, Hd, 1.05, fovy, (0.25 * (k - 1), 0.0, 0.0), target=(0.0, 0.0, 5.0)), device)
+            for k in range(V)]
     gen = torch.Generator(device=device).manual_seed(11)
     gts = [torch.rand((3, Hd, Wd), device=device, generator=gen) for _ in range(V)]
     bg = torch.zeros(3, device=device)
-    g = dp.FlatGaussians.from_scene(sc, device)
     phases = ("render", "loss", "backward", "stats", "adam")
     marks = []
 
@@ -360,22 +415,18 @@ def train_iteration_section(impl, device, iters=40, warm=10):
         return e
 
     if impl == "ours":
+        from lgdwt_b200 import densify, dp
+        g = dp.FlatGaussians.from_scene(sc, device)
         stats = densify.DensifyStats(g.P, device)
-        rm = torch.ones((), device=device)   # running-mean DWT scale kept on the device (no .item() in the loop)
+        loss_fn = dp.RunningMeanLoss(device)
         cfg = dp.AdamConfig()
 
         def iteration(i, timed):
-            nonlocal rm
             cam, gt = cams[i % V], gts[i % V]
             t = [ev()]
             image, radii, vsp = dp.fused_render(g, cam, bg, accumulate=False)
             t.append(ev())
-            from lgdwt_b200 import fused_dwt_loss, fused_photometric_loss
-            l1, ssim = fused_photometric_loss(image, gt)
-            dwt, patch, _ = fused_dwt_loss(image, gt)
-            base = 0.8 * l1 + 0.2 * (1.0 - ssim)
-            rm = 0.95 * rm + 0.05 * (base / (dwt + 1e-8)).detach()
-            loss = base + rm.clamp(0.1, 10.0) * dwt + 0.1 * patch
+            loss = loss_fn(image, gt)
             t.append(ev())
             loss.backward()
             t.append(ev())
@@ -386,14 +437,19 @@ def train_iteration_section(impl, device, iters=40, warm=10):
             if timed:
                 marks.append(t)
     else:
-        from oracle import dwt_oracle, photometric_oracle, ref_cuda
-        if ref_cuda.load_ref() is None:
-            return {"unavailable": "oracle/_ref not built"}
-        P = g.P
-        raw = {k: torch.nn.Parameter(g.field(k).clone().reshape(P, *shape)) for k, shape in
-               (("xyz", (3,)), ("f_dc", (1, 3)), ("f_rest", (15, 3)), ("opacity", (1,)), ("scaling", (3,)), ("rotation", (4,)))}
-        a = dp.AdamConfig()
-        lrs = dict(xyz=a.lr_xyz, f_dc=a.lr_f_dc, f_rest=a.lr_f_rest, opacity=a.lr_opacity, scaling=a.lr_scaling, rotation=a.lr_rotation)
+        from oracle import dwt_oracle, photometric_oracle
+        if not os.path.isdir(os.path.join(REF_SITE, "dgr_3dgs")):
+            return {"unavailable": "baseline/_ref/site/dgr_3dgs not installed"}
+        if REF_SITE not in sys.path:
+            sys.path.insert(0, REF_SITE)
+        from dgr_3dgs import GaussianRasterizationSettings, GaussianRasterizer
+        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        P = sc.means3D.shape[0]
+        op = tt(sc.opacities).clamp(1e-6, 1 - 1e-6)
+        raw = {"xyz": tt(sc.means3D), "f_dc": tt(sc.shs[:, :1, :]), "f_rest": tt(sc.shs[:, 1:, :]),
+               "opacity": torch.log(op / (1 - op)), "scaling": torch.log(tt(sc.scales)), "rotation": tt(sc.rotations)}
+        raw = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+        lrs = dict(xyz=0.00016, f_dc=0.0025, f_rest=0.0025 / 20.0, opacity=0.025, scaling=0.005, rotation=0.001)
         opt = torch.optim.Adam([{"params": [raw[k]], "lr": lrs[k], "name": k} for k in raw], lr=0.0, eps=1e-15)
         accum, denom, maxr = torch.zeros((P, 1), device=device), torch.zeros((P, 1), device=device), torch.zeros(P, device=device)
         state = {"rm": 1.0}
@@ -404,9 +460,12 @@ def train_iteration_section(impl, device, iters=40, warm=10):
             shs = torch.cat((raw["f_dc"], raw["f_rest"]), dim=1)                    # gaussian_model.py:121-124
             vsp = torch.zeros_like(raw["xyz"], requires_grad=True)                    # gaussian_renderer:26-30
             vsp.retain_grad()
-            image, radii, _ = ref_cuda.RefRasterize.apply(raw["xyz"], vsp, shs, torch.sigmoid(raw["opacity"]),
-                                                          torch.exp(raw["scaling"]),
-                                                          torch.nn.functional.normalize(raw["rotation"]), cam, bg, 3)
+            rs = GaussianRasterizationSettings(Hd, Wd, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"],
+                                               cam["projmatrix"], 3, cam["campos"], False, False, False)
+            image, radii, _ = GaussianRasterizer(rs)(means3D=raw["xyz"], means2D=vsp, shs=shs,
+                                                     opacities=torch.sigmoid(raw["opacity"]),
+                                                     scales=torch.exp(raw["scaling"]),
+                                                     rotations=torch.nn.functional.normalize(raw["rotation"]))
             image = image.clamp(0, 1)
             t.append(ev())
             l1, ssim = photometric_oracle.photometric_terms(image, gt)               # train.py:128,182-188
@@ -458,6 +517,80 @@ def train_iteration_section(impl, device, iters=40, warm=10):
     return out
 
 
+def cfg5_section(device, rank, world, steps=3):
+    """BASELINE config 5 — Mip-NeRF360 scale: 6 M Gaussians, 1920x1080, a 32-view global batch per step, data-parallel
+    over the ranks (rank r renders views r, r+N, ...; STRONG scaling: the batch is fixed, so N = 1 renders all 32).
+    The whole fused training step: activations, render, L1 + SSIM + DWT + patch loss, backward into the flat bucket,
+    one exchange + Adam per step (fused peer-memory kernel at N > 1)."""
+    import math
+    from lgdwt_b200 import dp
+    P, Wd, Hd, batch = 6_000_000, 1920, 1080, 32
+    sc = scenes.trained_like_scene(P, seed=5, sigma_xyz=1.2, clip=3.0, log_scale_mean=math.log(0.006))
+    fovy = 2 * math.atan(math.tan(0.5) * Hd / Wd)
+    cams = [cam_dict(scenes.look_at_camera(Wd, Hd, 1.0, fovy, (5.0 * math.sin(2 * math.pi * k / batch), 0.0,
+                                                                 -5.0 * math.cos(2 * math.pi * k / batch))), device)
+            for k in range(batch)]
+    gen = torch.Generator(device=device).manual_seed(3)
+    mine = set(dp.views_of_rank(batch, rank, world))
+    gts = [torch.rand((3, Hd, Wd), device=device, generator=gen) if k in mine else None for k in range(batch)]
+    bg = torch.zeros(3, device=device)
+    g = dp.FlatGaussians.from_scene(sc, device)
+    del sc
+    tr = dp.ViewParallelTrainer(g, loss_fn=dp.RunningMeanLoss(device), exchange="peer" if world > 1 else "nccl")
+    tr.step(cams, gts, bg)
+    ms = timed_loop(lambda i: tr.step(cams, gts, bg), steps, world, device) / steps
+    ok = tr.replicas_in_sync()
+    out = {"workload": "config 5: 6M Gaussians, 1920x1080, 32-view global batch per step, fused training step "
+                       "(render + L1/SSIM/DWT/patch loss + backward + exchange + Adam)", "scaling": "strong",
+           "ms_per_step": round(ms, 3), "views_per_s": round(batch / (ms * 1e-3), 2), "views_per_rank": len(mine),
+           "exchange": (tr.peer.backend if tr.peer is not None else (tr.peer_unavailable or "none (1 rank)")),
+           "replicas_in_sync": bool(ok), "steps": steps}
+    del tr, g
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure(stepper, cam_devs, host_cams, host_gts, K, W, world, rank, device, sampler=None, stage_timing=None,
+            launch_counter=None):
+    """(ms per resident step, ms per end-to-end step, kernels launched in the timed resident region) of one Stepper:
+    W warm-up steps, then exactly K timed ones, for each of the two measurements"""
+    V = VIEWS_PER_RANK
+    pick = lambda i: [cam_devs[((i * world + rank) * V + v) % len(cam_devs)] for v in range(V)]
+    for i in range(W):
+        stepper.step_resident(pick(i))
+    if stage_timing is not None:
+        stage_timing(min(K * V, 256))
+    if sampler is not None:
+        sampler.mark()
+    n0 = launch_counter() if launch_counter is not None else 0
+    ms_res = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device) / K
+    launches = (launch_counter() - n0) if launch_counter is not None else None
+    ring = lambda i: [((i * world + rank) * V + v) % len(host_cams) for v in range(V)]
+    e2e_fn = lambda i: stepper.step_e2e([host_cams[j] for j in ring(i)], [host_gts[j] for j in ring(i)])
+    for i in range(W):
+        e2e_fn(i)
+    ms_e2e = timed_loop(e2e_fn, K, world, device) / K
+    return ms_res, ms_e2e, launches
+
+
+def host_inputs(cams):
+    host_cams = []
+    for c in cams:
+        d = cam_dict(c, "cpu")
+        d["packed"] = torch.cat([d["viewmatrix"].reshape(-1), d["projmatrix"].reshape(-1), d["campos"].reshape(-1)]).pin_memory()
+        host_cams.append(d)
+    rng = np.random.default_rng(7)
+    host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory() for _ in range(len(host_cams))]
+    return host_cams, host_gts
+
+
+def workload_text(V, world, exchange):
+    return ("1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, %d views per rank per step (global "
+            "view batch %d), rasterize forward+backward with the gradients of the rank's views accumulated in one flat "
+            "bucket" % (V, V * world) + (" + one all-reduce of the 236 B/Gaussian bucket per step (%s)" % exchange
+                                         if world > 1 else ""))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,15 +599,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-iteration", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     W = max(args.warmup, 3)
     K = args.steps
-
-    if args.impl == "reference" and rank != 0:
-        return 0  # rank 0 alone runs the reference arm
     if args.impl == "reference":
-        world = 1
+        if rank != 0:
+            return 0  # rank 0 alone runs the reference arm
+        return reference_arm(args, K, W, local)
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback", "impl": args.impl}))
         return 1
@@ -482,161 +615,136 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    sys.path.insert(0, PKG)
+    from lgdwt_b200 import _lib   # raises when the CUDA library is missing: there is no fallback
 
-    from oracle import ref_cuda
-    impl = "ours"
-    ref_kind = None
-    if args.impl == "reference":
-        if ref_cuda.load_ref() is not None:
-            impl, ref_kind = "reference_cuda", "reference"
-        else:
-            return reference_cpu_port(args, K, W)
-
+    V = VIEWS_PER_RANK
     sc, cams, params = make_workload(device)
     cam_devs = [cam_dict(c, device) for c in cams]
-    stepper = Stepper("ours" if impl == "ours" else "ref", params, device, world)
-    V = VIEWS_PER_RANK
-    # step i of rank r renders views (i*world + r)*V .. +V-1 of the camera ring
-    pick = lambda i: [cam_devs[((i * world + rank) * V + v) % len(cam_devs)] for v in range(V)]
-
-    from lgdwt_b200 import _lib
+    host_cams, host_gts = host_inputs(cams)
+    stepper = Stepper("sinks", params, device, world)
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- value: inputs resident in HBM
-    for i in range(W):
-        stepper.step_resident(pick(i))
-    launches0 = _lib.lib.lg_launch_count()
-    if impl == "ours":
-        _lib.stage_timing(min(K * V, 256))
-    sampler.mark()
-    ms_total = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device)
-    launches = _lib.lib.lg_launch_count() - launches0
-    ms_step = ms_total / K
-    value = world * K * V / (ms_total / 1e3)
+    ms_step, ms_e2e, launches = measure(stepper, cam_devs, host_cams, host_gts, K, W, world, rank, device, sampler,
+                                        _lib.stage_timing, _lib.lib.lg_launch_count)
+    clocks = sampler.stop()
+    value = world * V / (ms_step / 1e3)
 
-    # ---- per-stage times recorded during that same timed region
-    stages, roofline = None, None
-    if impl == "ours":
-        rows = [_lib.read_stage_times(s) for s in range(min(K * V, 256))]
-        _lib.stage_timing(0)
-        mean_ms = {k: float(np.mean([r[k] for r in rows if r[k] >= 0])) for k in _lib.STAGES}
-        from diff_gaussian_rasterization import _RasterizeGaussians
-        # work terms of the metric camera (step 0's view on rank 0)
-        stepper.step_resident([cam_devs[0]])
-        lc = _RasterizeGaussians.last_call
-        counts = torch.zeros(2, dtype=torch.int64, device=device)
-        _lib.check(_lib.lib.lg_blend_work_count(lc["P"], lc["channels"], lc["W"], lc["H"], lc["num_rendered"],
-                                                lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
-                                                counts.data_ptr(), _lib.stream_ptr(device)))
-        n_contrib = torch.zeros(WIDTH * HEIGHT, dtype=torch.int32, device=device)
-        _lib.check(_lib.lib.lg_state_read(b"n_contrib", lc["P"], lc["channels"], lc["W"], lc["H"], lc["num_rendered"],
-                                          lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
-                                          n_contrib.data_ptr(), n_contrib.numel() * 4, _lib.stream_ptr(device)))
-        radii = torch.zeros(lc["P"], dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        n_eval, n_hit = int(counts[0]), int(counts[1])
-        n_trav = int(n_contrib.long().sum())
-        R = lc["num_rendered"]
-        P = lc["P"]
-        peaks = {}
+    # ---- per-stage times recorded during the timed resident region
+    rows = [_lib.read_stage_times(s) for s in range(min(K * V, 256))]
+    _lib.stage_timing(0)
+    mean_ms = {k: float(np.mean([r[k] for r in rows if r[k] >= 0])) for k in _lib.STAGES}
+    import diff_gaussian_rasterization as dgr
+    seen = []   # work terms of the metric camera (step 0's view on rank 0)
+    dgr.set_inspection_hook(seen.append)
+    stepper.step_resident([cam_devs[0]])
+    dgr.set_inspection_hook(None)
+    lc = seen[-1]
+    counts = torch.zeros(2, dtype=torch.int64, device=device)
+    _lib.check(_lib.lib.lg_blend_work_count(lc["P"], lc["channels"], lc["W"], lc["H"], lc["binning_capacity"],
+                                            lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
+                                            counts.data_ptr(), _lib.stream_ptr(device)))
+    n_contrib = torch.zeros(WIDTH * HEIGHT, dtype=torch.int32, device=device)
+    _lib.check(_lib.lib.lg_state_read(b"n_contrib", lc["P"], lc["channels"], lc["W"], lc["H"], lc["binning_capacity"],
+                                      lc["geom"].data_ptr(), lc["binning"].data_ptr(), lc["img"].data_ptr(),
+                                      n_contrib.data_ptr(), n_contrib.numel() * 4, _lib.stream_ptr(device)))
+    torch.cuda.synchronize(device)
+    n_eval, n_hit = int(counts[0]), int(counts[1])
+    n_trav = int(n_contrib.long().sum())
+    R, P = lc["num_rendered"], lc["P"]
+    del seen, lc
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    simt = _lib.simt_peaks(device)   # FFMA / MUFU / LDS / SHFL ceilings measured on THIS box, now (csrc/microbench.cu)
+    fp32_peak = simt["ffma_tflops"] if simt["ffma_tflops"] > 1.0 else FP32_SIMT_NOMINAL_TFLOPS
+    T = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+    alg = {  # algorithmic work per launch, SURVEY.md §8(d)
+        "preprocess": ("hbm", P * (44 + 12 * 16) + 8 * P + 67 * P),
+        "binning": ("hbm", 20 * P + 12 * R + 24 * R + 8 * R + 8 * T),
+        "blend_forward": ("fp32_simt", 15 * n_eval + 15 * n_hit),
+        "blend_backward": ("fp32_simt", 15 * n_trav + 80 * n_hit),
+        "preprocess_backward": ("hbm", 560 * P),
+    }
+    stages = {}
+    for k in _lib.STAGES:
+        bound, work = alg[k]
+        ach = work / (mean_ms[k] * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+        peak = hbm_peak if bound == "hbm" else fp32_peak
+        stages[k] = {"ms": round(mean_ms[k], 4), "bound": bound, "achieved": round(ach, 2),
+                     "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "peak": round(peak, 2),
+                     "frac": round(ach / peak, 4)}
+    dom = max(_lib.STAGES, key=lambda k: mean_ms[k])
+    roofline = dict(stages[dom])
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    for prof in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        T = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
-        alg = {  # algorithmic work per launch, SURVEY.md §8(d)
-            "preprocess": ("hbm", P * (44 + 12 * 16) + 8 * P + 67 * P),
-            "binning": ("hbm", 20 * P + 12 * R + 24 * R + 8 * R + 8 * T),
-            "blend_forward": ("fp32_simt", 15 * n_eval + 15 * n_hit),
-            "blend_backward": ("fp32_simt", 15 * n_trav + 80 * n_hit),
-            "preprocess_backward": ("hbm", 560 * P),
-        }
-        stages = {}
-        for k in _lib.STAGES:
-            bound, work = alg[k]
-            ach = work / (mean_ms[k] * 1e-3) / (1e9 if bound == "hbm" else 1e12)
-            peak = hbm_peak if bound == "hbm" else FP32_SIMT_PEAK_TFLOPS
-            stages[k] = {"ms": round(mean_ms[k], 4), "bound": bound, "achieved": round(ach, 2),
-                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "peak": round(peak, 2),
-                         "frac": round(ach / peak, 4)}
-        dom = max(_lib.STAGES, key=lambda k: mean_ms[k])
-        roofline = dict(stages[dom])
-        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["kernels"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", prof)))["kernels"]
             for name, recs in tr.items():
-                if name.startswith(dom + "_kernel") or name.startswith(dom.replace("blend_", "blend_") + "_kernel"):
+                if name.startswith(dom + "_kernel"):
                     traffic = int(recs[0]["dram_read_bytes"] + recs[0]["dram_write_bytes"])
                     roofline["ncu_issue_slots_busy"] = round(recs[0].get("issue_active_pct", 0.0) / 100.0, 3)
+                    roofline["traffic_source"] = "profiles/" + prof
+            if traffic is not None:
+                break
         except Exception:
             pass
-        roofline.update({"kernel": dom, "traffic": traffic, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
-                         "peak_source": hbm_src if roofline["bound"] == "hbm" else
-                         "nominal FP32 SIMT peak 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak in "
-                         "MEASURED_PEAKS.json)",
-                         "work_terms": {"num_rendered": R, "n_eval_fwd": n_eval, "n_trav": n_trav, "n_hit": n_hit}})
+    roofline.update({"kernel": dom, "traffic": traffic, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
+                     "peak_source": hbm_src if roofline["bound"] == "hbm" else
+                     "FFMA rate measured on this box by csrc/microbench.cu (lg_simt_peaks) at the start of this run; "
+                     "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s" % FP32_SIMT_NOMINAL_TFLOPS,
+                     "work_terms": {"num_rendered": R, "n_eval_fwd": n_eval, "n_trav": n_trav, "n_hit": n_hit}})
+    if dom.startswith("blend"):
+        # the other ceilings this kernel runs against (per hit-warp 12 SHFL + per evaluated warp-entry 4 broadcast LDS.128
+        # go through the MIO pipe: SHFL 1 / clk / SM, LDS.128 1 / 2.6 clk / SM)
+        roofline["simt_peaks"] = {k: round(v, 1) for k, v in simt.items()}
 
-    # ---- the exchange step alone (N > 1): NCCL vs the peer-memory kernels, with and without the optimizer
-    exchange = None
-    if impl == "ours" and world > 1:
-        exchange = exchange_section(stepper, device, world)
+    exchange = exchange_section(stepper, device, world) if world > 1 else None
+    exch_name = ("peer-memory kernel over NVLink" if stepper.peer is not None else "NCCL")
+    del stepper
 
-    # ---- e2e: host inputs every step + loss read-back
-    host_cams = []
-    for c in cams:
-        d = cam_dict(c, "cpu")
-        d["packed"] = torch.cat([d["viewmatrix"].reshape(-1), d["projmatrix"].reshape(-1), d["campos"].reshape(-1)]).pin_memory()
-        host_cams.append(d)
-    rng = np.random.default_rng(7)
-    host_gts = [torch.from_numpy(rng.random((3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory()
-                for _ in range(len(host_cams))]
-    ring = lambda i: [((i * world + rank) * V + v) % len(host_cams) for v in range(V)]
-    e2e_fn = lambda i: stepper.step_e2e([host_cams[j] for j in ring(i)], [host_gts[j] for j in ring(i)])
-    for i in range(W):
-        e2e_fn(i)
-    ms_e2e = timed_loop(e2e_fn, K, world, device)
-    clocks = sampler.stop()
-    e2e_value = world * K * V / (ms_e2e / 1e3)
     h2d = V * (3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4)
-    e2e = {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_step": round(ms_e2e / K, 4),
-           "ms_per_view": round(ms_e2e / K / V, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
-
+    e2e = {"value": round(world * V / (ms_e2e / 1e3), 3), "unit": "views/s", "ms_per_step": round(ms_e2e, 4),
+           "ms_per_view": round(ms_e2e / V, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
     line = {
         "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)", "value": round(value, 3),
         "unit": "views/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_step, 4),
         "ms_per_view": round(ms_step / V, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1M-Gaussian trained-like synthetic scene (seed 1), 800x800, SH degree 3, %d views per "
-                               "rank per step (global view batch %d), rasterize forward+backward with the gradients "
-                               "of the rank's views accumulated in one flat bucket" % (V, V * world) +
-                               (" + one all-reduce of the 236 B/Gaussian bucket per step (%s)" %
-                                ("peer-memory kernel over NVLink" if stepper.peer is not None else "NCCL") if world > 1 else ""),
-                   "views_per_rank_per_step": V, "global_view_batch": V * world, "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
-                   "cameras": N_CAMERAS, "parallelism": "view-parallel dp%d" % world,
-                   "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 43 MB of sort keys per step)"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "config": {"workload": workload_text(V, world, exch_name),
+                   "views_per_rank_per_step": V, "global_view_batch": V * world, "gaussians": P_GAUSSIANS, "width": WIDTH,
+                   "height": HEIGHT, "sh_degree": SH_DEGREE, "cameras": N_CAMERAS, "parallelism": "view-parallel dp%d" % world,
+                   "gradient_path": "GradSinks: the backward kernel accumulates the views of a step in one flat bucket "
+                                    "(extension of the operator; `dropin` below is the unchanged-caller path)",
+                   "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 72 MB of binning state per view)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "stages": stages,
     }
     if exchange is not None:
         line["exchange"] = exchange
-    if impl == "ours":
-        line["roofline"], line["stages"] = roofline, stages
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sc, cams[0])
-            line["image_loss"] = image_loss_section(device, hbm_peak)
-        if rank == 0 and world == 1 and not args.no_train_iteration:
-            line["train_iteration"] = train_iteration_section("ours", device)
-    else:
-        line["impl"] = "reference"
-        line["gpu_launches"] = None
-        line["reference_kind"] = ("reference CUDA rasterizer compiled for sm_100a from its own sources "
-                                  "(oracle/_ref/libref_dgr.so) behind a line-for-line mirror of its torch glue")
-        line["cpu_baseline"] = {"value": line["value"], "unit": "views/s", "cores": 0, "kind": ref_kind,
-                                "sample": "the reference has no CPU implementation of this path; this arm times its "
-                                          "own CUDA implementation on the same GPU (cores = 0 host threads)"}
-        if not args.no_train_iteration:
-            line["train_iteration"] = train_iteration_section("reference", device)
+    if world == 1:
+        # the same metric through the operator exactly as the unchanged LG/train.py uses it: no grad_sinks, fresh
+        # gradient tensors per view, autograd sums the views of a step
+        d_step, d_e2e, _ = measure(Stepper("dropin", params, device, 1), cam_devs, host_cams, host_gts, K, W, 1, 0, device)
+        line["dropin"] = {"value": round(V / (d_step / 1e3), 3), "unit": "views/s", "ms_per_view": round(d_step / V, 4),
+                          "e2e_value": round(V / (d_e2e / 1e3), 3), "e2e_ms_per_view": round(d_e2e / V, 4),
+                          "note": "plain GaussianRasterizer(...) call as in LG/gaussian_renderer/__init__.py:98-110; "
+                                  "gradients returned as new tensors and accumulated by autograd"}
+    del params
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sc, cams[0])
+        line["image_loss"] = image_loss_section(device, hbm_peak)
+    if rank == 0 and world == 1 and not args.no_train_iteration:
+        line["train_iteration"] = train_iteration_section("ours", device)
+    if not args.no_cfg5:
+        try:
+            line["cfg5"] = cfg5_section(device, rank, world)
+        except Exception as e:   # never lose the headline to the extra section
+            line["cfg5"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -644,9 +752,67 @@ def main():
     return 0
 
 
+def reference_arm(args, K, W, local):
+    """`--impl reference`: the UNMODIFIED reference on the same metric, config and harness.  The reference has no CPU
+    implementation of this path, so its own implementation — the CUDA extension dgr_3dgs built by its own setup.py for
+    sm_100a into baseline/_ref/site — is what is timed, through its own GaussianRasterizationSettings /
+    GaussianRasterizer; this process never imports this repo's package or library.  Fallbacks: oracle/_ref (the
+    reference's .cu files behind a ctypes mirror of its glue), then the CPU oracle port."""
+    if not torch.cuda.is_available():
+        return reference_cpu_port(args, K, W)
+    mode = None
+    if os.path.isdir(os.path.join(REF_SITE, "dgr_3dgs")):
+        mode = "stock"
+    else:
+        from oracle import ref_cuda
+        if ref_cuda.load_ref() is not None:
+            mode = "mirror"
+    if mode is None:
+        return reference_cpu_port(args, K, W)
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    V = VIEWS_PER_RANK
+    sc, cams, params = make_workload(device)
+    cam_devs = [cam_dict(c, device) for c in cams]
+    host_cams, host_gts = host_inputs(cams)
+    stepper = Stepper(mode, params, device, 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_step, ms_e2e, _ = measure(stepper, cam_devs, host_cams, host_gts, K, W, 1, 0, device, sampler)
+    clocks = sampler.stop()
+    del stepper, params
+    torch.cuda.empty_cache()
+    value = V / (ms_step / 1e3)
+    h2d = V * (3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4)
+    kind = ("the reference's stock CUDA extension dgr_3dgs (diff-gaussian-rasterization built by its own setup.py for "
+            "sm_100a, baseline/_ref/site) through its own Python API" if mode == "stock" else
+            "reference CUDA rasterizer compiled for sm_100a from its own sources (oracle/_ref/libref_dgr.so) behind a "
+            "line-for-line mirror of its torch glue")
+    line = {
+        "impl": "reference", "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)",
+        "value": round(value, 3), "unit": "views/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms_step, 4),
+        "ms_per_view": round(ms_step / V, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(V, 1, ""), "views_per_rank_per_step": V, "global_view_batch": V,
+                   "gaussians": P_GAUSSIANS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE, "cameras": N_CAMERAS,
+                   "parallelism": "single GPU (the reference has no multi-GPU path)",
+                   "gradient_path": "autograd accumulation of the views of a step (the reference's only path)",
+                   "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters per view)"},
+        "clocks": clocks, "gpu_launches": None, "reference_kind": kind,
+        "e2e": {"value": round(V / (ms_e2e / 1e3), 3), "unit": "views/s", "ms_per_step": round(ms_e2e, 4),
+                "ms_per_view": round(ms_e2e / V, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 0, "kind": "reference",
+                         "sample": "the reference has no CPU implementation of this path; this arm times its own CUDA "
+                                   "implementation on the same GPU (cores = 0 host threads)"},
+    }
+    if not args.no_train_iteration:
+        line["train_iteration"] = train_iteration_section("reference", device)
+    print(json.dumps(line))
+    return 0
+
+
 def reference_cpu_port(args, K, W):
-    """fallback when oracle/_ref was not prebuilt: the CPU oracle port, bounded sample"""
-    from lgdwt_b200 import scenes
+    """last resort when neither baseline/_ref nor oracle/_ref was prebuilt: the CPU oracle port, bounded sample"""
     sc = scenes.trained_like_scene(P_GAUSSIANS, seed=1)
     cb = cpu_baseline(sc, scenes.metric_camera(WIDTH, HEIGHT))
     line = {"impl": "reference", "metric": "train views/sec (rasterize fwd+bwd per view @1M Gaussians 800x800 SH3)",

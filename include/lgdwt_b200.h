@@ -80,6 +80,43 @@ int lg_rasterize_forward(
     void* stream,
     int* num_rendered);
 
+/* The same call without the mid-forward host stall (extension; the reference blocks on a cudaMemcpy of num_rendered
+ * before it can size the binning buffer, rasterizer_impl.cu:283-288).  capacity_hint > 0: the binning buffer is
+ * requested for that many entries and the whole forward is queued at once; the host then waits only for the entry count
+ * (an event behind the scan), and re-queues binning + blending at the exact size if the hint was too small.
+ * capacity_hint <= 0: identical to lg_rasterize_forward.  *binning_capacity receives the entry count the binning state
+ * was laid out for (>= *num_rendered): pass THAT as `R` to lg_rasterize_backward* / lg_state_read / lg_blend_work_count.
+ * A good hint is 1.25 x the num_rendered of the previous call with the same scene and image size. */
+int lg_rasterize_forward_hinted(
+    lg_alloc_fn geometry_alloc, void* geometry_ctx,
+    lg_alloc_fn binning_alloc, void* binning_ctx,
+    lg_alloc_fn image_alloc, void* image_ctx,
+    int P, int D, int M, int channels,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_invdepth,
+    int antialiasing,
+    int* radii,
+    int debug,
+    void* stream,
+    int capacity_hint,
+    int* num_rendered,
+    int* binning_capacity);
+
 /* Replaces CudaRasterizer::Rasterizer::backward (DGR/cuda_rasterizer/rasterizer.h:61-97,
  * rasterizer_impl.cu:345-450) as bound by RasterizeGaussiansBackwardCUDA (DGR/rasterize_points.cu:126-223).
  * All dL_* outputs are fully written by the call (zero for invisible Gaussians); the caller does NOT need to

@@ -75,6 +75,7 @@ size_t binning_state_bytes(size_t R) {
 }
 
 static thread_local uint32_t* g_pinned_word = nullptr;  // pinned staging for the num_rendered read-back
+static thread_local cudaEvent_t g_count_event = nullptr;  // recorded behind that copy
 
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
@@ -116,15 +117,17 @@ size_t lg_binning_state_bytes(int num_rendered, int width, int height) {
     return binning_state_bytes((size_t)num_rendered);
 }
 
-int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_alloc_fn binning_alloc, void* binning_ctx,
-                         lg_alloc_fn image_alloc, void* image_ctx, int P, int D, int M, int channels,
-                         const float* background, int width, int height, const float* means3D, const float* shs,
-                         const float* colors_precomp, const float* opacities, const float* scales,
-                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
-                         const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
-                         float tan_fovy, int prefiltered, float* out_color, float* out_invdepth, int antialiasing,
-                         int* radii, int debug, void* stream_v, int* num_rendered) {
+int lg_rasterize_forward_hinted(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_alloc_fn binning_alloc,
+                                void* binning_ctx, lg_alloc_fn image_alloc, void* image_ctx, int P, int D, int M,
+                                int channels, const float* background, int width, int height, const float* means3D,
+                                const float* shs, const float* colors_precomp, const float* opacities,
+                                const float* scales, float scale_modifier, const float* rotations,
+                                const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                                float* out_invdepth, int antialiasing, int* radii, int debug, void* stream_v,
+                                int capacity_hint, int* num_rendered, int* binning_capacity) {
     cudaStream_t stream = (cudaStream_t)stream_v;
+    if (binning_capacity) *binning_capacity = 0;
     if (num_rendered) *num_rendered = 0;
     if (P < 0 || width <= 0 || height <= 0 || !geometry_alloc || !binning_alloc || !image_alloc || !num_rendered) {
         set_error("lg_rasterize_forward: invalid sizes or missing allocator");
@@ -182,29 +185,65 @@ int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_allo
     rc = launch_tile_scan(width, height, img, f.debug, stream);
     if (rc != LG_OK) return rc;
 
-    // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288)
-    if (!g_pinned_word) LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
-    LG_CUDA(cudaMemcpyAsync(g_pinned_word, img.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    LG_CUDA(cudaStreamSynchronize(stream));
-    const int R = (int)*g_pinned_word;
-    *num_rendered = R;
-
-    char* bchunk = binning_alloc(binning_ctx, binning_state_bytes((size_t)R));
-    if (!bchunk) {
-        set_error("lg_rasterize_forward: binning allocation callback returned NULL");
-        return LG_ERR_ALLOC;
+    // num_rendered sizes the binning buffer, so it has to reach the host (rasterizer_impl.cu:283-288).  The reference
+    // blocks right here.  With a capacity hint from the caller (typically 1.25 x the previous call's num_rendered) the
+    // rest of the forward is queued FIRST, for a buffer of that capacity — every kernel behind this point reads
+    // num_rendered on the device and does nothing if it exceeds the capacity — and only then does the host wait, on an
+    // event recorded behind the copy, so the GPU never idles for the host's wake-up and launches.  If the hint was
+    // too small (rare) the tail is simply queued again for the exact size.
+    if (!g_pinned_word) {
+        LG_CUDA(cudaMallocHost((void**)&g_pinned_word, 64));
+        LG_CUDA(cudaEventCreateWithFlags(&g_count_event, cudaEventDisableTiming));
     }
-    BinningState b = BinningState::from_chunk(bchunk, (size_t)R);
-    rc = launch_binning(P, R, width, height, g, radii, b, img, f.debug, stream);
-    if (rc != LG_OK) return rc;
-    stage_end(ST_BINNING, stream);
-
+    LG_CUDA(cudaMemcpyAsync(g_pinned_word, img.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LG_CUDA(cudaEventRecord(g_count_event, stream));
     const float* features = colors_precomp ? colors_precomp : g.rgb;
-    stage_begin(ST_BLEND_FWD, stream);
-    rc = launch_blend_forward(channels, width, height, g, b, img, features, background, out_color, out_invdepth,
-                              f.debug, stream);
-    stage_end(ST_BLEND_FWD, stream);
-    return rc;
+    int R = -1;
+    int capacity = capacity_hint;
+    if (capacity <= 0) {  // no hint: the reference's synchronous protocol
+        LG_CUDA(cudaEventSynchronize(g_count_event));
+        R = capacity = (int)*g_pinned_word;
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        char* bchunk = binning_alloc(binning_ctx, binning_state_bytes((size_t)capacity));
+        if (!bchunk) {
+            set_error("lg_rasterize_forward: binning allocation callback returned NULL");
+            return LG_ERR_ALLOC;
+        }
+        BinningState b = BinningState::from_chunk(bchunk, (size_t)capacity);
+        rc = launch_binning(P, capacity, width, height, g, radii, b, img, f.debug, stream);
+        if (rc != LG_OK) return rc;
+        if (attempt == 0) stage_end(ST_BINNING, stream);
+        if (attempt == 0) stage_begin(ST_BLEND_FWD, stream);
+        rc = launch_blend_forward(channels, width, height, capacity, g, b, img, features, background, out_color,
+                                  out_invdepth, f.debug, stream);
+        if (rc != LG_OK) return rc;
+        if (attempt == 0) stage_end(ST_BLEND_FWD, stream);
+        if (R < 0) {
+            LG_CUDA(cudaEventSynchronize(g_count_event));
+            R = (int)*g_pinned_word;
+        }
+        if (R <= capacity) break;
+        capacity = R;  // the hint was too small: nothing behind the scan has run; queue it again at the exact size
+    }
+    *num_rendered = R;
+    if (binning_capacity) *binning_capacity = capacity;
+    return LG_OK;
+}
+
+int lg_rasterize_forward(lg_alloc_fn geometry_alloc, void* geometry_ctx, lg_alloc_fn binning_alloc, void* binning_ctx,
+                         lg_alloc_fn image_alloc, void* image_ctx, int P, int D, int M, int channels,
+                         const float* background, int width, int height, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* opacities, const float* scales,
+                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                         float tan_fovy, int prefiltered, float* out_color, float* out_invdepth, int antialiasing,
+                         int* radii, int debug, void* stream_v, int* num_rendered) {
+    return lg_rasterize_forward_hinted(geometry_alloc, geometry_ctx, binning_alloc, binning_ctx, image_alloc, image_ctx,
+                                       P, D, M, channels, background, width, height, means3D, shs, colors_precomp,
+                                       opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+                                       projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, out_invdepth,
+                                       antialiasing, radii, debug, stream_v, 0, num_rendered, nullptr);
 }
 
 int lg_rasterize_backward_raw(int P, int D, int M, int R, int channels, const float* background, int width, int height,

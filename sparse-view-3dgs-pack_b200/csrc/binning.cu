@@ -104,58 +104,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, uint32_t* __rest
     }
 }
 
-// Tile launch order from an arbitrary per-tile key (used by the backward pass on tile_neff): same bucketing.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint32_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ order) {
-    __shared__ uint32_t s_cnt[1024];
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_max;
-    const int tid = threadIdx.x;
-    const unsigned lane = tid & 31u, warp = tid >> 5;
-    s_cnt[tid] = 0;
-    if (tid == 0) s_max = 1;
-    __syncthreads();
-    uint32_t m = 0;
-    for (int t = tid; t < T; t += 1024) m = max(m, keys[t]);
-    m = __reduce_max_sync(0xffffffffu, m);
-    if (lane == 0) atomicMax(&s_max, m);
-    __syncthreads();
-    const float scale = 1023.0f / (float)s_max;
-    for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
-    __syncthreads();
-    const uint32_t c = s_cnt[tid];
-    uint32_t x = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((int)lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane], z = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
-            if ((int)lane >= o) z += y;
-        }
-        s_warp[lane] = z - w;
-    }
-    __syncthreads();
-    s_cnt[tid] = x - c + s_warp[warp];
-    __syncthreads();
-    for (int t = tid; t < T; t += 1024) {
-        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
-        order[pos] = (uint32_t)t;
-    }
-}
-
-int launch_tile_order(int T, const uint32_t* keys, uint32_t* order, cudaStream_t stream) {
-    tile_order_kernel<<<1, 1024, 0, stream>>>(T, keys, order);
-    LG_LAUNCH_CHECK(false, stream);
-    return LG_OK;
-}
-
 // ------------------------------------------------------------------------------------------------ 3. SCATTER
 #define SCATTER_BLOCK 256
 #define SCATTER_COOP 8  // rectangles of more tiles than this are written by the whole warp

@@ -234,8 +234,6 @@ int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, co
                           cudaStream_t stream) {
     LG_CUDA(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * LG_REC * (size_t)P, stream));
     const int gx = num_tiles_x(W), T = gx * num_tiles_y(H);
-    int rc = launch_tile_order(T, img.tile_neff, img.tile_order_bwd, stream);
-    if (rc != LG_OK) return rc;
     const dim3 grid(T, 1, 1), block(LG_TILE_PIX, 1, 1);
 #define LG_LAUNCH_BWD(CH, INVD)                                                                                    \
     blend_backward_kernel<CH, INVD><<<grid, block, 0, stream>>>(                                                     \

@@ -21,9 +21,6 @@ namespace lg {
 #define FWD_MIN_BLOCKS 5
 #endif
 
-#ifndef FWD_CP_ASYNC
-#define FWD_CP_ASYNC 0
-#endif
 #ifndef BLEND_BATCH
 #define BLEND_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
 #endif
@@ -34,7 +31,11 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth,
-    const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff) {
+    const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff, uint32_t* __restrict__ counters,
+    uint32_t capacity, uint32_t* __restrict__ tile_order_bwd) {
+    // The list was only built if it fits the binning buffer the caller sized speculatively (abi.cu); otherwise this
+    // launch is void and the host queues the tail of the forward again.
+    if (counters[1] > capacity) return;
     // one staged entry = three float4: (mean.x, mean.y, -, 1/depth) (conic a, b, c, opacity) (colours, C <= 4), read
     // as warp-wide broadcasts from a single base address
     __shared__ float4 s_ent[BLEND_BATCH * 3];
@@ -142,7 +143,6 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     __syncthreads();  // s_neff initialised (every thread passes here: the loop above has no early return)
     if (lane == 0 && warp_max) atomicMax(&s_neff, warp_max);
     __syncthreads();
-    if (tid == 0) tile_neff[tile] = s_neff;
     if (inside) {
         final_T[pix_id] = T;
         n_contrib[pix_id] = last_contributor;
@@ -150,164 +150,20 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
         for (int c = 0; c < C; c++) out_color[(size_t)c * H * W + pix_id] = F_FMA(T, bg_color[c], acc[c]);
         if (out_invdepth) out_invdepth[pix_id] = acc_invd;
     }
-}
-
-#if FWD_CP_ASYNC
-// EXPERIMENT (north_star: "Gaussians staged into shared memory by TMA/cp.async in batches"): the same kernel with the
-// gathers of batch i+1 issued as cp.async (LDGSTS) into the other half of a double buffer while batch i is blended.
-// The per-entry reach mask and 1/depth need the staged values, so every thread post-processes its own slot after
-// cp.async.wait_group.  Results are identical; see DESIGN.md §4.3 for the measurement.
-#ifndef FWD_CPA_BATCH
-#define FWD_CPA_BATCH 256
-#endif
-__device__ __forceinline__ void cpa4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void cpa8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void cpa16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
-}
-
-template <int C>
-__global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_cpa_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
-    const float2* __restrict__ means2D, const float* __restrict__ features, const float4* __restrict__ conic_opacity,
-    const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth,
-    const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff) {
-    constexpr int NB = FWD_CPA_BATCH, PER = NB / LG_TILE_PIX;
-    extern __shared__ __align__(16) unsigned char cpa_smem[];
-    float4* s_ent = reinterpret_cast<float4*>(cpa_smem);                       // [2][NB * 3]
-    lg_slot_t* s_list_all = reinterpret_cast<lg_slot_t*>(s_ent + 2 * NB * 3);  // [8][NB]
-    uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_list_all + (LG_TILE_PIX / 32) * NB);
-    __shared__ uint32_t s_neff;
-
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile = tile_order[blockIdx.x];
-    const uint32_t tile_x = tile % (uint32_t)grid_x, tile_y = tile / (uint32_t)grid_x;
-    if (tid == 0) s_neff = 0;
-    const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
-    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
-    const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
-    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
-    const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
-    lg_slot_t* s_list = s_list_all + warp * NB;
-
-    const uint2 range = ranges[tile];
-    const int total = (int)(range.y - range.x);
-    const int rounds = (total + NB - 1) / NB;
-
-    auto issue = [&](int r) {
-        float4* buf = s_ent + (r & 1) * NB * 3;
-#pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const unsigned slot = u * LG_TILE_PIX + tid;
-            const uint32_t progress = (uint32_t)r * NB + slot;
-            if (range.x + progress < range.y) {
-                const uint32_t id = point_list[range.x + progress];
-                float* e0 = reinterpret_cast<float*>(buf + slot * 3);
-                cpa8(e0, means2D + id);
-                cpa4(e0 + 3, depths + id);
-                cpa16(buf + slot * 3 + 1, conic_opacity + id);
-#pragma unroll
-                for (int c = 0; c < C; c++) cpa4(e0 + 8 + c, features + (size_t)id * C + c);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    bool done = !inside;
-    float T = 1.0f;
-    uint32_t last_contributor = 0;
-    float acc[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) acc[c] = 0.0f;
-    float acc_invd = 0.0f;
-
-    if (rounds > 0) issue(0);
-    for (int i = 0; i < rounds; i++) {
-        if (__syncthreads_count(done) == LG_TILE_PIX) break;
-        const bool more = i + 1 < rounds;
-        if (more) issue(i + 1);
-        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        float4* buf = s_ent + (i & 1) * NB * 3;
-        const int batch = min(NB, total - i * NB);
-        // every thread finishes the slots it copied itself (its own cp.async results are visible to it)
-#pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const int slot = u * LG_TILE_PIX + (int)tid;
-            unsigned mask = 0;
-            if (slot < batch) {
-                const float4 e0 = buf[slot * 3 + 0];
-                const float4 co = buf[slot * 3 + 1];
-                mask = lg_patch_mask(e0.x, e0.y, co, tile_x0, tile_y0);
-                reinterpret_cast<float*>(buf + slot * 3)[3] = F_RCP(e0.w);
-            }
-            s_mask[slot] = (uint8_t)mask;
-        }
-        __syncthreads();
-        const int cnt = lg_compact_patch_list(s_mask, s_list, warp, lane, 0, batch);
-        const uint32_t batch_base = (uint32_t)i * NB;
-        for (int k = 0; !done && k < cnt; k += FWD_UNROLL) {
-            int js[FWD_UNROLL];
-            float4 xys[FWD_UNROLL];
-            float alphas[FWD_UNROLL];
-            bool pass[FWD_UNROLL];
-#pragma unroll
-            for (int u = 0; u < FWD_UNROLL; u++) {
-                const bool has = k + u < cnt;
-                const int j = s_list[has ? k + u : k];
-                const float4 xy = buf[j * 3 + 0];
-                const float4 co = buf[j * 3 + 1];
-                const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
-                const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
-                const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));
-                const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
-                js[u] = j;
-                xys[u] = xy;
-                alphas[u] = alpha;
-                pass[u] = has && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            }
-#pragma unroll
-            for (int u = 0; u < FWD_UNROLL; u++) {
-                if (pass[u] && !done) {
-                    const float alpha = alphas[u];
-                    const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
-                    if (test_T < 0.0001f) {
-                        done = true;
-                    } else {
-                        const float4 f = buf[js[u] * 3 + 2];
-                        const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-                        for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
-                        acc_invd = F_FMA(T, F_MUL(alpha, xys[u].w), acc_invd);
-                        T = test_T;
-                        last_contributor = batch_base + (uint32_t)js[u] + 1u;
-                    }
-                }
-            }
-        }
+    // The block that finishes last turns tile_neff into the backward's launch order (deepest tiles first), which
+    // used to be a kernel launch of its own at the head of the backward pass.
+    if (tid == 0) {
+        tile_neff[tile] = s_neff;
+        __threadfence();
+        s_neff = atomicAdd(&counters[3], 1u);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");  // a prefetched batch may still be in flight after an early exit
-
-    const uint32_t warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
     __syncthreads();
-    if (lane == 0 && warp_max) atomicMax(&s_neff, warp_max);
-    __syncthreads();
-    if (tid == 0) tile_neff[tile] = s_neff;
-    if (inside) {
-        final_T[pix_id] = T;
-        n_contrib[pix_id] = last_contributor;
-#pragma unroll
-        for (int c = 0; c < C; c++) out_color[(size_t)c * H * W + pix_id] = F_FMA(T, bg_color[c], acc[c]);
-        if (out_invdepth) out_invdepth[pix_id] = acc_invd;
+    if (s_neff == gridDim.x - 1) {
+        __threadfence();
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(s_ent);  // 1024 + 33 words of the staging buffer
+        lg_bucket_order<LG_TILE_PIX>((int)gridDim.x, tile_neff, tile_order_bwd, scratch, scratch + 1024);
     }
 }
-#endif  // FWD_CP_ASYNC
 
 // Instrumentation: replays the blend decisions and counts, over all pixels, the list entries evaluated before early
 // termination (N_eval) and the (pixel, Gaussian) pairs that pass all three tests (N_hit) — the work terms of the
@@ -364,7 +220,7 @@ int launch_blend_count(int W, int H, const GeometryState& g, const BinningState&
     return LG_OK;
 }
 
-int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
+int launch_blend_forward(int C, int W, int H, int capacity, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream) {
     const int gx = num_tiles_x(W);
@@ -373,21 +229,8 @@ int launch_blend_forward(int C, int W, int H, const GeometryState& g, const Binn
     blend_forward_kernel<CH><<<grid, block, 0, stream>>>(img.ranges, b.point_list, W, H, gx, g.means2D,              \
                                                          features, g.conic_opacity, g.depths, img.accum_alpha,       \
                                                          img.n_contrib, background, out_color, out_invdepth,         \
-                                                         img.tile_order, img.tile_neff)
-#if FWD_CP_ASYNC
-    {
-        const size_t smem = (size_t)2 * FWD_CPA_BATCH * 3 * sizeof(float4) + (LG_TILE_PIX / 32) * FWD_CPA_BATCH * sizeof(lg_slot_t) + FWD_CPA_BATCH;
-        if (C == 3) {
-            LG_CUDA(cudaFuncSetAttribute(blend_forward_cpa_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            blend_forward_cpa_kernel<3><<<grid, block, smem, stream>>>(img.ranges, b.point_list, W, H, gx, g.means2D, features,
-                                                                       g.conic_opacity, g.depths, img.accum_alpha, img.n_contrib,
-                                                                       background, out_color, out_invdepth, img.tile_order,
-                                                                       img.tile_neff);
-            LG_LAUNCH_CHECK(debug, stream);
-            return LG_OK;
-        }
-    }
-#endif
+                                                         img.tile_order, img.tile_neff, img.counters,                \
+                                                         (uint32_t)capacity, img.tile_order_bwd)
     switch (C) {
         case 1: LG_LAUNCH_FWD(1); break;
         case 2: LG_LAUNCH_FWD(2); break;

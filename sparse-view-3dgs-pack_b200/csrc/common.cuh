@@ -73,7 +73,8 @@ struct ImageState {
     uint32_t* tile_order;      // T: tile sort and blend forward, by list length
     uint32_t* tile_neff;       // T: entries that reached some pixel of the tile (max n_contrib), written by the forward
     uint32_t* tile_order_bwd;  // T: backward, by tile_neff
-    uint32_t* counters;        // 8 words: [1] num_rendered (total list length, written by the tile scan)
+    uint32_t* counters;        // [1] num_rendered (total list length, written by the tile scan), [3] blend-forward
+                               // completion ticket (the last block derives the backward's launch order)
     // Per-tile binning counters, one 128-byte line per tile (atomics on one line serialise in its L2 slice: with the
     // counters packed, 3.6 M increments on 80 lines took 160 us; one line per tile spreads them over all slices).
     // word 0 = list length (counted by the preprocess kernel), word 1 = write cursor of the scatter step.
@@ -125,9 +126,7 @@ int launch_binning(int P, int capacity, int W, int H, const GeometryState& g, co
                    ImageState& img, bool debug, cudaStream_t stream);
 int launch_rebuild_keys(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
                         unsigned long long* keys_out, cudaStream_t stream);
-// order[0..T) = tile indices by descending key (bucketed; ties in no particular order) — scheduling only
-int launch_tile_order(int T, const uint32_t* keys, uint32_t* order, cudaStream_t stream);
-int launch_blend_forward(int C, int W, int H, const GeometryState& g, const BinningState& b, ImageState& img,
+int launch_blend_forward(int C, int W, int H, int capacity, const GeometryState& g, const BinningState& b, ImageState& img,
                          const float* features, const float* background, float* out_color, float* out_invdepth,
                          bool debug, cudaStream_t stream);
 int launch_blend_count(int W, int H, const GeometryState& g, const BinningState& b, const ImageState& img,
@@ -425,6 +424,107 @@ __device__ __forceinline__ uint32_t lg_lookback_exclusive(volatile unsigned long
     }
     if (lane == 0) st[tile] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
     return exclusive;
+}
+
+// Tile launch order for the sort / blend kernels: bucket the T tiles by key (1024 buckets scaled to the largest key)
+// and list them heaviest bucket first (longest-processing-time-first: the hardware hands out blocks in blockIdx
+// order).  Executed by one whole block of THREADS threads; s_cnt = 1024 words, s_warp = 33 words of shared memory.
+template <int THREADS>
+__device__ __forceinline__ void lg_bucket_order(int T, const uint32_t* keys, uint32_t* __restrict__ order,
+                                                uint32_t* s_cnt, uint32_t* s_warp) {
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    for (int k = tid; k < 1024; k += THREADS) s_cnt[k] = 0;
+    if (tid == 0) s_warp[32] = 1;
+    __syncthreads();
+    uint32_t m = 0;
+    for (int t = tid; t < T; t += THREADS) m = max(m, keys[t]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) atomicMax(&s_warp[32], m);
+    __syncthreads();
+    const float scale = 1023.0f / (float)s_warp[32];
+    for (int t = tid; t < T; t += THREADS) atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 bucket counts: thread t owns buckets [t * PER, (t + 1) * PER)
+    constexpr int PER = 1024 / THREADS;
+    uint32_t c[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        c[k] = s_cnt[tid * PER + k];
+        sum += c[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int w = 0; w < (int)warp; w++) run += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        s_cnt[tid * PER + k] = run;
+        run += c[k];
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += THREADS) {
+        const uint32_t pos = atomicAdd(&s_cnt[1023 - min((int)((float)keys[t] * scale), 1023)], 1u);
+        order[pos] = (uint32_t)t;
+    }
+}
+
+// ---- bulk asynchronous copies (TMA, 1-D) and the mbarrier that tracks them.  Used where a Gaussian's data is one
+// contiguous, 16-byte-sized row (the 192-byte SH row): the copy engine moves the row into shared memory while the thread
+// does its projection math, instead of 48 LDG + 48 STS per thread through registers.
+__device__ __forceinline__ uint32_t lg_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lg_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lg_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lg_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void lg_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lg_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void lg_mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lg_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lg_mbar_wait(uint64_t* bar, unsigned phase) {
+    const uint32_t addr = lg_smem_addr(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(phase) : "memory");
+    } while (!done);
+}
+// global -> shared, completion counted in bytes on `bar` (dst, src and bytes multiples of 16)
+__device__ __forceinline__ void lg_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(lg_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(lg_smem_addr(bar)) : "memory");
+}
+// shared -> global (plain store, or element-wise fp32 add into global memory), tracked by the thread's bulk group
+__device__ __forceinline__ void lg_bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(lg_smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lg_bulk_reduce_add_f32(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(lg_smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void lg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (before a shared -> global bulk copy)
+__device__ __forceinline__ void lg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// SH degree 3: a Gaussian's 16 coefficients x 3 channels = one 192-byte row.  The bulk-copy instruction is issued by
+// one lane at a time (UBLKCP takes warp-uniform operands: per-lane copies become a 32-trip loop), so the rows travel
+// in PAIRS — the rows of lanes 2p and 2p+1 are adjacent in global memory: one 384-byte copy per even lane — into
+// shared memory at a pair stride of 400 bytes: with 25 sixteen-byte chunks per pair, chunk j of eight consecutive
+// lanes falls into eight different bank groups (25 p + 12 q + j mod 8, p = 0..3, q = 0..1), so the per-lane float4 reads
+// and writes of the rows are conflict-free.
+#define LG_SH_ROW_FLOATS 48
+#define LG_SH_PAIR_FLOATS 100
+__device__ __forceinline__ float* lg_sh_row(float* base, unsigned tid) {
+    return base + (size_t)(tid >> 1) * LG_SH_PAIR_FLOATS + (tid & 1u) * LG_SH_ROW_FLOATS;
 }
 
 // 128-bit read-only streaming load

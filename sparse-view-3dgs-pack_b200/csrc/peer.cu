@@ -340,6 +340,7 @@ extern "C" int lg_peer_check(void* stream_v) {
     LG_CUDA(cudaMemcpyAsync(&s, g_peer_status, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     LG_CUDA(cudaStreamSynchronize(stream));
     if (s) {
+        LG_CUDA(cudaMemsetAsync(g_peer_status, 0, sizeof(unsigned), stream));  // reported once
         set_error("lg_peer_barrier timed out: a peer rank did not reach the exchange step");
         return LG_ERR_CUDA;
     }

@@ -53,14 +53,26 @@ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 // the coefficients (read by the owner thread), then the gradients (written by it), then the warp streams them out.
 // STAGED = false (3M > PG_MAX_ROW, or no SH path) keeps direct global accesses.
 #define PG_MAX_ROW 48
+#ifndef PG_SH_BULK
+#define PG_SH_BULK 1  // 0: keep the register-staged SH tile even where bulk copies apply (A/B measurements)
+#endif
+#ifndef PG_BULK_PLAIN_STORE
+#define PG_BULK_PLAIN_STORE 0
+#endif
 #ifndef PG_MIN_BLOCKS
 #define PG_MIN_BLOCKS 4  // 64 registers: 4 resident blocks per SM measured 4 % faster than 3 at 79 registers
 #endif
 
-template <bool STAGED, int M3C>
+// SH staging modes as in preprocess.cu: 0 = global memory, 1 = register-staged odd-stride tile per warp, 2 = bulk
+// asynchronous copies: the 192-byte coefficient rows of the visible Gaussians come in by TMA (one 384-byte copy per lane
+// pair, awaited on a per-warp mbarrier), the gradient rows go out the same way — a plain bulk store, or, when the caller
+// accumulates several views, cp.reduce.async.bulk .add.f32, which adds the row into global memory inside the L2
+// instead of a load-add-store through registers.
+template <int STAGED, int M3C>
 __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel(PreGradArgs a) {
-    extern __shared__ float s_tile_dyn[];
+    extern __shared__ __align__(16) float s_tile_dyn[];
     __shared__ float s_cam[35];
+    __shared__ __align__(8) uint64_t s_bar[8];
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.view + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(a.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(a.campos + threadIdx.x - 32);
@@ -71,20 +83,43 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
     const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32u;
     float* s_wtile = s_tile_dyn + (size_t)warp * 32u * row;
     int warp_floats = 0;
-    if (STAGED) {
+    bool pair_visible = false;
+    if (STAGED == 2 && lane == 0) {
+        lg_mbar_init(&s_bar[warp], 32);  // every lane of the warp arrives once
+        lg_mbar_init_fence();
+    }
+    if (STAGED == 1) {
         const long long left = (long long)a.P - (long long)warp_first;
         warp_floats = left <= 0 ? 0 : (int)(left < 32 ? left : 32) * M3;
         lg_warp_rows_to_tile<M3C>(a.shs + warp_first * M3, s_wtile, M3, warp_floats, lane);
     }
     __syncthreads();
+    if (STAGED == 2) {
+        const bool vis = idx < a.P && a.radii[idx] > 0;
+        const bool other_vis = __shfl_xor_sync(0xffffffffu, vis, 1);  // (not inside `||`: every lane must take part)
+        pair_visible = vis || other_vis;
+        if (pair_visible && (lane & 1u) == 0) {
+            const unsigned bytes = (idx + 1 < a.P ? 2u : 1u) * LG_SH_ROW_FLOATS * 4u;
+            lg_mbar_arrive_expect_tx(&s_bar[warp], bytes);
+            lg_bulk_load(lg_sh_row(s_tile_dyn, threadIdx.x), a.shs + (size_t)idx * LG_SH_ROW_FLOATS, bytes, &s_bar[warp]);
+        } else {
+            lg_mbar_arrive(&s_bar[warp]);
+        }
+    }
+    // bulk variant: the coefficients of this thread's row, and what its gradient row is made of —
+    // dL/dsh[3k + c] = basis_k(direction) * g[c], zero above the active degree — kept as 16 + 3 values until the store
+    float sh_regs[STAGED == 2 ? LG_SH_ROW_FLOATS : 1];
+    float basis[16], sh_g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 16; k++) basis[k] = 0.f;
     if (idx < a.P) {
     const float* V = s_cam;
     const float* PR = s_cam + 16;
     const size_t i = (size_t)idx;
     const int C = a.C;
     // SH rows: the staged tile row is read (coefficients) and then overwritten (gradients) by this thread alone
-    const float* sh = STAGED ? s_wtile + lane * row : a.shs + i * M3;
-    float* out_sh = STAGED ? s_wtile + lane * row : a.dL_dsh + i * M3;
+    const float* sh = STAGED == 2 ? sh_regs : (STAGED == 1 ? s_wtile + lane * row : a.shs + i * M3);
+    float* out_sh = STAGED == 1 ? s_wtile + lane * row : a.dL_dsh + i * M3;  // unused by the bulk variant
 
     const bool visible = a.radii[idx] > 0;
     float r[LG_REC];
@@ -239,8 +274,18 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
     // in the staged variant `sh` and `out_sh` are the same shared-memory row.
     if (a.sh_path) {
         if (!visible) {
-            for (int k = 0; k < M3; k++) out_sh[k] = 0.f;
+            if (STAGED != 2)
+                for (int k = 0; k < M3; k++) out_sh[k] = 0.f;
         } else {
+            if (STAGED == 2) {  // the row has arrived (or arrives now): 12 conflict-free float4 reads
+                lg_mbar_wait(&s_bar[warp], 0);
+                const float4* row4 = reinterpret_cast<const float4*>(lg_sh_row(s_tile_dyn, threadIdx.x));
+#pragma unroll
+                for (int j = 0; j < LG_SH_ROW_FLOATS / 4; j++) {
+                    const float4 v = row4[j];
+                    sh_regs[4 * j + 0] = v.x; sh_regs[4 * j + 1] = v.y; sh_regs[4 * j + 2] = v.z; sh_regs[4 * j + 3] = v.w;
+                }
+            }
             const float mx = a.means3D[3 * i + 0], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
             const float ox = mx - V[32], oy = my - V[33], oz = mz - V[34];
             const float ilen = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
@@ -252,8 +297,9 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
             const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
             const int deg = a.D;
             int written = 1;
+            basis[0] = C0;
 #pragma unroll
-            for (int c = 0; c < 3; c++) out_sh[c] = C0 * g[c];
+            for (int c = 0; c < 3; c++) if (STAGED != 2) out_sh[c] = C0 * g[c];
             if (deg > 0) {
                 written = 4;
 #pragma unroll
@@ -262,10 +308,13 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
                     dx[c] = -C1 * s3;
                     dy[c] = -C1 * s1;
                     dz[c] = C1 * s2;
-                    out_sh[3 + c] = -C1 * y * g[c];
-                    out_sh[6 + c] = C1 * z * g[c];
-                    out_sh[9 + c] = -C1 * x * g[c];
+                    if (STAGED != 2) {
+                        out_sh[3 + c] = -C1 * y * g[c];
+                        out_sh[6 + c] = C1 * z * g[c];
+                        out_sh[9 + c] = -C1 * x * g[c];
+                    }
                 }
+                basis[1] = -C1 * y; basis[2] = C1 * z; basis[3] = -C1 * x;
                 if (deg > 1) {
                     written = 9;
                     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
@@ -277,12 +326,15 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
                         dx[c] += c_SH_C2[0] * y * s4 + c_SH_C2[2] * 2.f * -x * s6 + c_SH_C2[3] * z * s7 + c_SH_C2[4] * 2.f * x * s8;
                         dy[c] += c_SH_C2[0] * x * s4 + c_SH_C2[1] * z * s5 + c_SH_C2[2] * 2.f * -y * s6 + c_SH_C2[4] * 2.f * -y * s8;
                         dz[c] += c_SH_C2[1] * y * s5 + c_SH_C2[2] * 2.f * 2.f * z * s6 + c_SH_C2[3] * x * s7;
-                        out_sh[12 + c] = b4 * g[c];
-                        out_sh[15 + c] = b5 * g[c];
-                        out_sh[18 + c] = b6 * g[c];
-                        out_sh[21 + c] = b7 * g[c];
-                        out_sh[24 + c] = b8 * g[c];
+                        if (STAGED != 2) {
+                            out_sh[12 + c] = b4 * g[c];
+                            out_sh[15 + c] = b5 * g[c];
+                            out_sh[18 + c] = b6 * g[c];
+                            out_sh[21 + c] = b7 * g[c];
+                            out_sh[24 + c] = b8 * g[c];
+                        }
                     }
+                    basis[4] = b4; basis[5] = b5; basis[6] = b6; basis[7] = b7; basis[8] = b8;
                     if (deg > 2) {
                         written = 16;
                         const float b9 = c_SH_C3[0] * y * (3.f * xx - yy), b10 = c_SH_C3[1] * xy * z,
@@ -304,18 +356,24 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
                             dz[c] += c_SH_C3[1] * s10 * xy + c_SH_C3[2] * s11 * 4.f * 2.f * yz +
                                      c_SH_C3[3] * s12 * 3.f * (2.f * zz - xx - yy) + c_SH_C3[4] * s13 * 4.f * 2.f * xz +
                                      c_SH_C3[5] * s14 * (xx - yy);
-                            out_sh[27 + c] = b9 * g[c];
-                            out_sh[30 + c] = b10 * g[c];
-                            out_sh[33 + c] = b11 * g[c];
-                            out_sh[36 + c] = b12 * g[c];
-                            out_sh[39 + c] = b13 * g[c];
-                            out_sh[42 + c] = b14 * g[c];
-                            out_sh[45 + c] = b15 * g[c];
+                            if (STAGED != 2) {
+                                out_sh[27 + c] = b9 * g[c];
+                                out_sh[30 + c] = b10 * g[c];
+                                out_sh[33 + c] = b11 * g[c];
+                                out_sh[36 + c] = b12 * g[c];
+                                out_sh[39 + c] = b13 * g[c];
+                                out_sh[42 + c] = b14 * g[c];
+                                out_sh[45 + c] = b15 * g[c];
+                            }
                         }
+                        basis[9] = b9; basis[10] = b10; basis[11] = b11; basis[12] = b12; basis[13] = b13;
+                        basis[14] = b14; basis[15] = b15;
                     }
                 }
             }
-            for (int k = written * 3; k < M3; k++) out_sh[k] = 0.f;  // coefficients above the active degree
+            if (STAGED != 2)
+                for (int k = written * 3; k < M3; k++) out_sh[k] = 0.f;  // coefficients above the active degree
+            sh_g[0] = g[0]; sh_g[1] = g[1]; sh_g[2] = g[2];
             const float ddir_x = dx[0] * g[0] + dx[1] * g[1] + dx[2] * g[2];
             const float ddir_y = dy[0] * g[0] + dy[1] * g[1] + dy[2] * g[2];
             const float ddir_z = dz[0] * g[0] + dz[1] * g[1] + dz[2] * g[2];
@@ -417,9 +475,48 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
         for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * i + k] = dcov[k];
     }  // idx < P
 
-    if (STAGED) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
+    if (STAGED == 1) {  // stream the warp's 32 x 3M gradient block out with coalesced stores
         __syncwarp();
         lg_warp_tile_to_rows<M3C>(a.dL_dsh + warp_first * M3, s_wtile, M3, warp_floats, lane, a.accumulate != 0);
+    }
+    if (STAGED == 2) {
+        // gradient rows: registers -> the thread's shared-memory row (over the coefficients, which every lane of the
+        // warp has read by now: the mbarrier wait below also covers warps whose lanes never needed them) -> global memory
+        // by one bulk copy per lane pair.  Accumulation adds inside the L2 (cp.reduce.async.bulk); pairs without a
+        // visible Gaussian contribute nothing then and are skipped.
+        lg_mbar_wait(&s_bar[warp], 0);
+        const bool write_pair = a.accumulate ? pair_visible : true;
+        if (idx < a.P && write_pair) {
+            float4* row4 = reinterpret_cast<float4*>(lg_sh_row(s_tile_dyn, threadIdx.x));
+#pragma unroll
+            for (int j = 0; j < LG_SH_ROW_FLOATS / 4; j++)  // element e = 4 j + q is coefficient e / 3, channel e % 3
+                row4[j] = make_float4(basis[(4 * j) / 3] * sh_g[(4 * j) % 3], basis[(4 * j + 1) / 3] * sh_g[(4 * j + 1) % 3],
+                                      basis[(4 * j + 2) / 3] * sh_g[(4 * j + 2) % 3], basis[(4 * j + 3) / 3] * sh_g[(4 * j + 3) % 3]);
+        }
+        lg_fence_proxy_async();
+        __syncwarp();
+#if PG_BULK_PLAIN_STORE
+        if (idx < a.P && write_pair) {  // diagnostic variant: rows written back with ordinary stores
+            const float4* src4 = reinterpret_cast<const float4*>(lg_sh_row(s_tile_dyn, threadIdx.x));
+            float4* dst4 = reinterpret_cast<float4*>(a.dL_dsh + (size_t)idx * LG_SH_ROW_FLOATS);
+            for (int j = 0; j < LG_SH_ROW_FLOATS / 4; j++) {
+                float4 v = src4[j];
+                if (a.accumulate) { const float4 o = dst4[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                dst4[j] = v;
+            }
+        }
+        if (false) {
+            const unsigned bytes = 0; float* dst = nullptr;
+#else
+        if (idx < a.P && write_pair && (lane & 1u) == 0) {
+            const unsigned bytes = (idx + 1 < a.P ? 2u : 1u) * LG_SH_ROW_FLOATS * 4u;
+            float* dst = a.dL_dsh + (size_t)idx * LG_SH_ROW_FLOATS;
+#endif
+            if (a.accumulate) lg_bulk_reduce_add_f32(dst, lg_sh_row(s_tile_dyn, threadIdx.x), bytes);
+            else lg_bulk_store(dst, lg_sh_row(s_tile_dyn, threadIdx.x), bytes);
+            lg_bulk_commit();
+            lg_bulk_wait_read();  // the rows must stay in place until the copy engine has read them
+        }
     }
 }
 
@@ -443,22 +540,27 @@ int launch_preprocess_backward(const BackwardArgs& b, const GeometryState& g, co
     const int M3 = 3 * b.M;
     if (a.sh_path && M3 <= PG_MAX_ROW) {
         const size_t smem = sizeof(float) * 256 * (size_t)(M3 | 1);
-        if (M3 == 48) {
-            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true, 48>,
+        if (M3 == LG_SH_ROW_FLOATS && PG_SH_BULK && ((reinterpret_cast<uintptr_t>(b.shs) | reinterpret_cast<uintptr_t>(b.dL_dsh)) & 15u) == 0) {
+            const size_t bulk_smem = sizeof(float) * 128 * (size_t)LG_SH_PAIR_FLOATS;
+            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<2, 48>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+            preprocess_backward_kernel<2, 48><<<(b.P + 255) / 256, 256, bulk_smem, stream>>>(a);
+        } else if (M3 == 48) {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<1, 48>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            preprocess_backward_kernel<true, 48><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+            preprocess_backward_kernel<1, 48><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
         } else {
-            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true, 0>,
+            LG_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<1, 0>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(float) * 256 * (PG_MAX_ROW | 1))));
-            preprocess_backward_kernel<true, 0><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
+            preprocess_backward_kernel<1, 0><<<(b.P + 255) / 256, 256, smem, stream>>>(a);
         }
     } else {
         if (a.sh_path && a.accumulate) {
             set_error("gradient accumulation needs SH rows of at most %d floats (got %d)", PG_MAX_ROW, M3);
             return LG_ERR_UNSUPPORTED;
         }
-        preprocess_backward_kernel<false, 0><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
+        preprocess_backward_kernel<0, 0><<<(b.P + 255) / 256, 256, 0, stream>>>(a);
     }
     LG_LAUNCH_CHECK(debug, stream);
     return LG_OK;

@@ -15,6 +15,9 @@ namespace lg {
 #define PRE_BLOCK 256
 #define PRE_MAX_ROW 48  // widest SH row (floats per Gaussian) staged through shared memory
 #define PRE_COOP 8      // tile rectangles above this many tiles are counted by the whole warp
+#ifndef PRE_SH_BULK
+#define PRE_SH_BULK 1   // 0: keep the register-staged SH tile even where bulk copies apply (A/B measurements)
+#endif
 
 struct PreArgs {
     int P, D, M, C;
@@ -117,18 +120,47 @@ __device__ __forceinline__ void compute_cov3d(float sx0, float sy0, float sz0, f
     cov[5] = dot3_mid_first(M20, M20, M21, M21, M22, M22);   // f445
 }
 
-template <bool STAGED, int M3C>
+// SH staging modes: 0 = read the coefficients straight from global memory; 1 = per-warp register-staged copy into an
+// odd-stride shared tile (any row length); 2 = bulk asynchronous copies (TMA) of the 192-byte rows, one 384-byte copy
+// per pair of Gaussians (SH degree 3, 16-byte aligned tensor), issued as soon as a Gaussian of the pair is known to be
+// in front of the camera and awaited on a per-warp mbarrier right before the SH evaluation.
+template <int STAGED, int M3C>
 __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
-    extern __shared__ float s_tile_dyn[];
+    extern __shared__ __align__(16) float s_tile_dyn[];
     __shared__ float s_cam[35];  // view 0..15, proj 16..31, campos 32..34
+    __shared__ __align__(8) uint64_t s_bar[PRE_BLOCK / 32];
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(a.viewmatrix + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(a.projmatrix + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(a.cam_pos + threadIdx.x - 32);
+    if (STAGED == 2 && (threadIdx.x & 31u) == 0) {
+        lg_mbar_init(&s_bar[threadIdx.x >> 5], 32);  // every lane of the warp arrives once
+        lg_mbar_init_fence();
+    }
     __syncthreads();
     const uint32_t tile = blockIdx.x;
     const int idx = (int)(tile * PRE_BLOCK + threadIdx.x);
     const float* V = s_cam;
     const float* PM = s_cam + 16;
+    if (STAGED == 2) {
+        // start the SH row on its way before anything else: it arrives while the projection is computed
+        bool fetch = false;
+        if (idx < a.P) {
+            const float qx = __ldg(a.means3D + 3 * (size_t)idx + 0), qy = __ldg(a.means3D + 3 * (size_t)idx + 1),
+                        qz = __ldg(a.means3D + 3 * (size_t)idx + 2);
+            fetch = !(xform_row(qx, qy, qz, V[2], V[6], V[10], V[14]) <= 0.2f);  // same predicate as in_frustum below
+        }
+        // rows travel in pairs (lanes 2p, 2p+1): the even lane fetches both if either Gaussian may need its colours
+        const bool other_fetch = __shfl_xor_sync(0xffffffffu, fetch, 1);  // (not inside `||`: every lane must take part)
+        const bool pair_fetch = fetch || other_fetch;
+        uint64_t* bar = &s_bar[threadIdx.x >> 5];
+        if (pair_fetch && (threadIdx.x & 1u) == 0) {
+            const unsigned bytes = (idx + 1 < a.P ? 2u : 1u) * LG_SH_ROW_FLOATS * 4u;
+            lg_mbar_arrive_expect_tx(bar, bytes);
+            lg_bulk_load(lg_sh_row(s_tile_dyn, threadIdx.x), a.shs + (size_t)idx * LG_SH_ROW_FLOATS, bytes, bar);
+        } else {
+            lg_mbar_arrive(bar);
+        }
+    }
 
     uint32_t tiles = 0;
     uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;  // tile rectangle (all zero = emits nothing)
@@ -278,7 +310,21 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_kernel(PreArgs a) {
         const int M3 = a.M * 3;
         const float* sh = a.shs + (size_t)idx * M3;
         const unsigned need_mask = __ballot_sync(0xffffffffu, need_sh);
-        if (STAGED && need_mask) {
+        float shv[LG_SH_ROW_FLOATS];
+        if (STAGED == 2) {
+            // every lane waits (a warp must not retire while the copy engine still writes into its rows)
+            lg_mbar_wait(&s_bar[warp], 0);
+            if (need_sh) {
+                const float4* row4 = reinterpret_cast<const float4*>(lg_sh_row(s_tile_dyn, threadIdx.x));
+#pragma unroll
+                for (int j = 0; j < LG_SH_ROW_FLOATS / 4; j++) {
+                    const float4 v = row4[j];
+                    shv[4 * j + 0] = v.x; shv[4 * j + 1] = v.y; shv[4 * j + 2] = v.z; shv[4 * j + 3] = v.w;
+                }
+                sh = shv;
+            }
+        }
+        if (STAGED == 1 && need_mask) {
             const int row = M3 | 1;
             float* s_wtile = s_tile_dyn + (size_t)warp * 32u * row;
             const size_t warp_first = (size_t)tile * PRE_BLOCK + (size_t)warp * 32u;
@@ -417,17 +463,23 @@ int launch_preprocess(const ForwardArgs& f, GeometryState& g, ImageState& img, i
     const int M3 = 3 * f.M;
     if (f.colors_precomp == nullptr && M3 <= PRE_MAX_ROW) {
         const size_t smem = sizeof(float) * PRE_BLOCK * (size_t)(M3 | 1);
-        if (M3 == 48) {
-            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (M3 == LG_SH_ROW_FLOATS && (reinterpret_cast<uintptr_t>(f.shs) & 15u) == 0 && PRE_SH_BULK) {
+            // SH degree 3, 16-byte aligned rows: bulk asynchronous copies (one per Gaussian in front of the camera)
+            const size_t bulk_smem = sizeof(float) * (PRE_BLOCK / 2) * (size_t)LG_SH_PAIR_FLOATS;
+            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<2, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bulk_smem));
+            preprocess_kernel<2, 48><<<blocks, PRE_BLOCK, bulk_smem, stream>>>(a);
+        } else if (M3 == 48) {
+            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<1, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-            preprocess_kernel<true, 48><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+            preprocess_kernel<1, 48><<<blocks, PRE_BLOCK, smem, stream>>>(a);
         } else {
-            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            LG_CUDA(cudaFuncSetAttribute(preprocess_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(float) * PRE_BLOCK * (PRE_MAX_ROW | 1))));
-            preprocess_kernel<true, 0><<<blocks, PRE_BLOCK, smem, stream>>>(a);
+            preprocess_kernel<1, 0><<<blocks, PRE_BLOCK, smem, stream>>>(a);
         }
     } else {
-        preprocess_kernel<false, 0><<<blocks, PRE_BLOCK, 0, stream>>>(a);
+        preprocess_kernel<0, 0><<<blocks, PRE_BLOCK, 0, stream>>>(a);
     }
     LG_LAUNCH_CHECK(f.debug, stream);
     return LG_OK;

@@ -76,8 +76,39 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      cov3Ds_precomp, raster_settings, grad_sinks)
 
 
+# Binning-capacity hints (performance only): the library sizes the binning buffer for `hint` entries and queues the whole
+# forward before it waits for the exact count (lg_rasterize_forward_hinted), instead of stalling the GPU in the middle of
+# every forward as the reference does (rasterizer_impl.cu:283-288).  The hint is 1.25 x the largest entry count of the
+# last few calls on that device; a hint that turns out too small only costs a re-queue of the tail of that one call.
+_CAPACITY_HISTORY = {}
+_HISTORY_LEN = 8
+_inspection_hook = None
+
+
+def set_inspection_hook(fn):
+    """Opt-in hook for benchmarks / tests: `fn(info)` is called after every forward with the sizes and the three state
+    buffers of that call (keeping them alive for as long as the callee holds on to `info`).  None disables it."""
+    global _inspection_hook
+    _inspection_hook = fn
+
+
+def _capacity_hint(device, P, W, H):
+    hist = _CAPACITY_HISTORY.get((device, P, W, H))
+    return 0 if not hist else int(1.25 * max(hist)) + 1024
+
+
+def _record_num_rendered(device, P, W, H, R):
+    hist = _CAPACITY_HISTORY.setdefault((device, P, W, H), [])
+    hist.append(R)
+    if len(hist) > _HISTORY_LEN:
+        del hist[0]
+    if len(_CAPACITY_HISTORY) > 64:  # scenes come and go (densification changes P): forget the oldest shapes
+        for key in list(_CAPACITY_HISTORY)[:32]:
+            if key != (device, P, W, H):
+                del _CAPACITY_HISTORY[key]
+
+
 class _RasterizeGaussians(torch.autograd.Function):
-    last_call = None
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -108,9 +139,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         invdepth = alloc((1, H, W), dtype=torch.float32, device=device)
         radii = alloc((P,), dtype=torch.int32, device=device)
         geom, binning, img = (_lib.ResizableBuffer(device) for _ in range(3))
-        num_rendered = ctypes.c_int(0)
+        num_rendered, capacity = ctypes.c_int(0), ctypes.c_int(0)
+        # debug keeps the reference's synchronous protocol (it syncs after every stage anyway)
+        hint = 0 if rs.debug else _capacity_hint(device, P, W, H)
         with torch.cuda.device(device):
-            rc = _lib.lib.lg_rasterize_forward(
+            rc = _lib.lib.lg_rasterize_forward_hinted(
                 geom.callback, None, binning.callback, None, img.callback, None,
                 P, int(rs.sh_degree), M, channels,
                 _lib.ptr(bg_c), W, H,
@@ -119,14 +152,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _lib.ptr(view_c), _lib.ptr(proj_c), _lib.ptr(campos_c),
                 float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)),
                 _lib.ptr(color), _lib.ptr(invdepth), int(bool(rs.antialiasing)), _lib.ptr(radii),
-                int(bool(rs.debug)), _lib.stream_ptr(device), ctypes.byref(num_rendered))
+                int(bool(rs.debug)), _lib.stream_ptr(device), hint, ctypes.byref(num_rendered),
+                ctypes.byref(capacity))
         _lib.check(rc, RuntimeError)
-
-        # inspection hook for benchmarks / tests (work counters, state read-back); not used by the operator itself
-        _RasterizeGaussians.last_call = dict(num_rendered=num_rendered.value, P=P, channels=channels, W=W, H=H,
-                                             geom=geom.tensor, binning=binning.tensor, img=img.tensor)
+        _record_num_rendered(device, P, W, H, num_rendered.value)
+        if _inspection_hook is not None:
+            _inspection_hook(dict(num_rendered=num_rendered.value, binning_capacity=capacity.value, P=P,
+                                  channels=channels, W=W, H=H, geom=geom.tensor, binning=binning.tensor,
+                                  img=img.tensor))
         ctx.raster_settings = rs
-        ctx.num_rendered = num_rendered.value
+        ctx.num_rendered = capacity.value  # the entry count the binning state was laid out for (>= num_rendered)
         ctx.channels = channels
         ctx.M = M
         ctx.cam = (bg_c, view_c, proj_c, campos_c)

@@ -50,6 +50,11 @@ def _load():
         [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f, i,
                                                                                       _P, _P, i, _P, i, _P,
                                                                                       ctypes.POINTER(i)])
+    lib.lg_rasterize_forward_hinted.restype = i
+    lib.lg_rasterize_forward_hinted.argtypes = (
+        [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f, i,
+                                                                                      _P, _P, i, _P, i, _P, i,
+                                                                                      ctypes.POINTER(i), ctypes.POINTER(i)])
     lib.lg_rasterize_backward.restype = i
     lib.lg_rasterize_backward.argtypes = (
         [i, i, i, i, i, _P, i, i] + [_P] * 5 + [f, _P, _P, _P, _P, _P, f, f] + [_P] * 16 + [i, i, _P])

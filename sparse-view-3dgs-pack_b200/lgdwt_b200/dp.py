@@ -5,7 +5,10 @@ it has no distributed code at all.  The path shards naturally 
 replica of the Gaussian parameters, renders its slice of the step's view batch (views r, r+N, ...), accumulates the
 parameter gradients in ONE flat fp32 bucket (59 floats = 236 B per Gaussian at SH degree 3), and the only exchange
 step is a single in-place all-reduce of that bucket before an identical Adam update on every rank.  N = 1 with one
-view per step reproduces the reference iteration.  Every `densification_interval` steps the densification statistics
+view per step and a `TrainSchedule` reproduces the reference iteration: the running-mean DWT scale (LG/train.py:190-196,
+kept on the device), `oneupSHdegree` every 1000 iterations (:101-103), the exponential position learning rate
+(LG/scene/gaussian_model.py:203-223) and the inverse-depth L1 term (LG/train.py:204-216) — checked parameter for
+parameter against the stock op chain in tests/test_trainer_gpu.py.  Every `densification_interval` steps the densification statistics
 are all-reduced too (sum, sum, max) and `densify_and_prune` runs identically on every rank with unit normals drawn
 from a generator all ranks seed alike.
 
@@ -53,6 +56,38 @@ class AdamConfig(NamedTuple):
     eps: float = 1e-15
 
 
+class TrainSchedule(NamedTuple):
+    """What LG/train.py changes from one iteration to the next besides the parameters themselves
+    (defaults: LG/arguments/__init__.py:77-100)."""
+    iterations: int = 30_000
+    position_lr_init: float = 0.00016
+    position_lr_final: float = 0.0000016
+    position_lr_delay_mult: float = 0.01      # unused by the reference too: it never passes lr_delay_steps
+    position_lr_max_steps: int = 30_000
+    spatial_lr_scale: float = 1.0             # = scene.cameras_extent (create_from_pcd, gaussian_model.py:149-150)
+    oneup_sh_every: int = 1000                # LG/train.py:101-103
+    start_sh_degree: int = 0                  # GaussianModel.active_sh_degree starts at 0 (gaussian_model.py:53)
+    depth_l1_weight_init: float = 1.0
+    depth_l1_weight_final: float = 0.01
+
+    def position_lr(self, iteration):
+        """get_expon_lr_func(lr_init * scale, lr_final * scale, max_steps) — LG/utils/general_utils.py:29-63 with
+        lr_delay_steps = 0, as GaussianModel.training_setup calls it (gaussian_model.py:203-206)"""
+        a, b = self.position_lr_init * self.spatial_lr_scale, self.position_lr_final * self.spatial_lr_scale
+        if iteration < 0 or (a == 0.0 and b == 0.0):
+            return 0.0
+        t = min(max(iteration / self.position_lr_max_steps, 0.0), 1.0)
+        return math.exp(math.log(a) * (1 - t) + math.log(b) * t)
+
+    def depth_l1_weight(self, iteration):
+        """get_expon_lr_func(depth_l1_weight_init, depth_l1_weight_final, max_steps=iterations) — LG/train.py:69"""
+        a, b = self.depth_l1_weight_init, self.depth_l1_weight_final
+        if iteration < 0 or (a == 0.0 and b == 0.0):
+            return 0.0
+        t = min(max(iteration / self.iterations, 0.0), 1.0)
+        return math.exp(math.log(a) * (1 - t) + math.log(b) * t)
+
+
 class DensifyConfig(NamedTuple):
     """LG/arguments/__init__.py:91-97 and the constants of LG/train.py:265-276"""
     densify_from_iter: int = 500
@@ -64,6 +99,7 @@ class DensifyConfig(NamedTuple):
     percent_dense: float = 0.01
     size_threshold: float = 20.0  # used once iteration > opacity_reset_interval (train.py:272)
     cameras_extent: float = 1.0
+    white_background: bool = False  # extra opacity reset at densify_from_iter (train.py:275)
 
 
 class FlatGaussians:
@@ -71,6 +107,7 @@ class FlatGaussians:
 
     def __init__(self, P, device, sh_degree=3):
         self.device, self.sh_degree = device, sh_degree
+        self.active_sh_degree = sh_degree  # a TrainSchedule starts it at 0 and raises it (oneupSHdegree)
         self.fields = fields_for(sh_degree)
         self.floats = sum(w for _, w in self.fields)
         self.M = (sh_degree + 1) ** 2
@@ -250,16 +287,19 @@ def default_render(act, cam, bg, sh_degree=3, antialiasing=False):
     return color.clamp(0, 1), radii, means2D
 
 
-def fused_render(g: FlatGaussians, cam, bg, accumulate, antialiasing=False):
-    """One view of the fused path: raw parameters -> lg_activate_forward -> rasterizer; the backward adds the
-    RAW-parameter gradients into g.grad.  Returns (image, radii, means2D) like the reference's render()."""
+def fused_render(g: FlatGaussians, cam, bg, accumulate, antialiasing=False, with_depth=False):
+    """One view of the fused path: raw parameters -> lg_activate_forward -> rasterizer at the active SH degree; the
+    backward adds the RAW-parameter gradients into g.grad.  Returns (image, radii, means2D[, invdepth]) like the
+    reference's render() (LG/gaussian_renderer/__init__.py:119-128)."""
     from diff_gaussian_rasterization import GaussianRasterizer
     act = g.activate()
     means2D = torch.zeros((g.P, 3), dtype=torch.float32, device=g.device, requires_grad=True)
-    color, radii, invdepth = GaussianRasterizer(_raster_settings(cam, bg, g.sh_degree, antialiasing))(
+    color, radii, invdepth = GaussianRasterizer(_raster_settings(cam, bg, g.active_sh_degree, antialiasing))(
         means3D=act["means3D"], means2D=means2D, shs=act["shs"], colors_precomp=None, opacities=act["opacities"],
         scales=act["scales"], rotations=act["rotations"], cov3D_precomp=None,
         grad_sinks=g.grad_sinks(act["rot_norm"], accumulate))
+    if with_depth:
+        return color.clamp(0, 1), radii, means2D, invdepth
     return color.clamp(0, 1), radii, means2D
 
 
@@ -274,6 +314,37 @@ def default_loss(image, gt, lambda_dssim=0.2, dwt_scale=1.0, patch_weight=0.1, c
     return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ssim) + dwt_scale * dwt + patch_weight * patch
 
 
+class RunningMeanLoss:
+    """The whole iteration loss of LG/train.py:128-216 as one callable with the reference's state: the running-mean
+    ratio that rescales the DWT term every iteration (:190-196 — `rm = 0.95 rm + 0.05 base/(dwt + 1e-8)`, used clamped
+    to [0.1, 10] in the SAME iteration) lives in a device scalar, so there is no `.item()` in the loop.  With a depth
+    target the inverse-depth L1 term of :204-216 is added."""
+
+    def __init__(self, device, lambda_dssim=0.2, patch_weight=0.1, cfg=None):
+        self.running_mean = torch.ones((), dtype=torch.float32, device=device)
+        self.lambda_dssim, self.patch_weight, self.cfg = lambda_dssim, patch_weight, cfg
+
+    def __call__(self, image, gt, invdepth=None, depth_target=None, depth_weight=0.0):
+        from .dwt_loss import DWTLossConfig, fused_dwt_loss
+        from .photometric import fused_photometric_loss
+        l1, ssim = fused_photometric_loss(image, gt)
+        dwt, patch, _ = fused_dwt_loss(image, gt, self.cfg or DWTLossConfig())
+        base = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ssim)
+        self.running_mean = 0.95 * self.running_mean + 0.05 * (base.detach() / (dwt.detach() + 1e-8))
+        loss = base + self.running_mean.clamp(0.1, 10.0) * dwt + self.patch_weight * patch
+        if depth_target is not None and depth_weight > 0.0 and invdepth is not None:
+            mono, mask = depth_target
+            loss = loss + depth_weight * torch.abs((invdepth - mono) * mask).mean()
+        return loss
+
+    def sync(self, group=None):
+        """data-parallel runs: the ranks saw different views; average the running mean so that the replicas weigh the
+        next step alike (one 4-byte all-reduce, issued before the exchange step)"""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.running_mean, op=dist.ReduceOp.SUM, group=group)
+            self.running_mean = self.running_mean / dist.get_world_size(group)
+
+
 def _default_densify(g, stats, cfg, max_screen_size, generator):
     from . import densify
     return densify.densify_and_prune(g, stats, cfg.densify_grad_threshold, cfg.min_opacity, cfg.cameras_extent,
@@ -285,12 +356,15 @@ class ViewParallelTrainer:
                  render_fn: Optional[Callable] = None, loss_fn: Callable = default_loss,
                  group: Optional[dist.ProcessGroup] = None, densify: Optional[DensifyConfig] = None,
                  densify_fn: Optional[Callable] = None, stats_fn: Optional[Callable] = None,
-                 reset_opacity_fn: Optional[Callable] = None, seed: int = 0, exchange: str = "nccl"):
+                 reset_opacity_fn: Optional[Callable] = None, seed: int = 0, exchange: str = "nccl",
+                 schedule: Optional[TrainSchedule] = None):
         """render_fn=None selects the fused CUDA path (`fused_render`); a custom render_fn(act, cam, bg) ->
         (image, radii[, viewspace_points]) runs through autograd leaves.  densify=None disables density control.
         exchange="nccl": all-reduce of the bucket + the same full Adam pass on every rank; exchange="peer": the
         fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (lgdwt_b200.peer), falling back to
-        "nccl" (with `peer_unavailable` saying why) when the ranks cannot map each other's memory."""
+        "nccl" (with `peer_unavailable` saying why) when the ranks cannot map each other's memory.
+        schedule: a TrainSchedule turns on what LG/train.py varies per iteration (active SH degree from 0, position
+        learning rate decay, depth-L1 weight); loss_fn may be a RunningMeanLoss (stateful DWT scale)."""
         self.g, self.adam, self.render_fn, self.loss_fn, self.group = gaussians, adam, render_fn, loss_fn, group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -299,6 +373,9 @@ class ViewParallelTrainer:
         self.densify_fn = densify_fn or _default_densify
         self.stats_fn, self.reset_opacity_fn = stats_fn, reset_opacity_fn
         self.iteration = 0
+        self.schedule = schedule
+        if schedule is not None:
+            gaussians.active_sh_degree = min(schedule.start_sh_degree, gaussians.sh_degree)
         self.stats = None
         # every rank seeds this generator alike: the split samples are identical on all replicas
         self.generator = torch.Generator(device=gaussians.device).manual_seed(seed)
@@ -313,6 +390,11 @@ class ViewParallelTrainer:
         """(re)create the IPC-shared parameter / gradient block for the current buffer size — collective"""
         self.peer = None
         if not (self._want_peer and self.distributed and self.world > 1 and self.g.data.is_cuda and self.g.P > 0):
+            return
+        if (3 * self.g.M) % 4 != 0:
+            # the 16-byte Adam path of the peer kernels needs the SH row (3, 12, 27 or 48 floats) to be a multiple of 4
+            # floats; SH degree 0 and 2 take the NCCL exchange (same decision on every rank: it only depends on M)
+            self.peer_unavailable = "SH row of %d floats is not a multiple of 4 (peer kernels use 16-byte accesses)" % (3 * self.g.M)
             return
         from .peer import PeerExchange
         self.peer, self.peer_unavailable = PeerExchange.create(self.g.data.numel(), self.g.device, self.group)
@@ -344,23 +426,36 @@ class ViewParallelTrainer:
             from . import densify
             densify.add_densification_stats(self.stats, viewspace.grad, radii)
 
-    def accumulate_views(self, cams: Sequence[dict], gts: Sequence[torch.Tensor], bg: torch.Tensor):
-        """forward + backward of this rank's views, gradients summed into the flat bucket; returns the local loss sum"""
+    def accumulate_views(self, cams: Sequence[dict], gts: Sequence[torch.Tensor], bg: torch.Tensor,
+                         depths: Optional[Sequence] = None):
+        """forward + backward of this rank's views, gradients summed into the flat bucket; returns the local loss sum.
+        depths[v] = (mono_invdepth (1,H,W), depth_mask (1,H,W)) or None: the view's inverse-depth target
+        (`viewpoint_cam.invdepthmap` / `depth_mask` of a depth-reliable camera, LG/train.py:206-213)."""
         total = torch.zeros((), dtype=torch.float32, device=self.g.device)
         mine = views_of_rank(len(cams), self.rank, self.world)
         fused = self.render_fn is None
         if not fused or not mine:
             self.g.grad.zero_()
+        depth_w = self.schedule.depth_l1_weight(self.iteration) if self.schedule is not None else 0.0
         for k, v in enumerate(mine):
+            target = depths[v] if depths is not None else None
+            invdepth = None
             if fused:  # the first view of the step overwrites the bucket: no zero-fill pass
-                image, radii, viewspace = fused_render(self.g, cams[v], bg, accumulate=k > 0)
+                if target is not None and depth_w > 0.0:
+                    image, radii, viewspace, invdepth = fused_render(self.g, cams[v], bg, accumulate=k > 0, with_depth=True)
+                else:
+                    image, radii, viewspace = fused_render(self.g, cams[v], bg, accumulate=k > 0)
                 leaves = None
             else:
                 leaves = self.g.leaves()
                 out = self.render_fn(self.g.activated(leaves), cams[v], bg)
                 image, radii = out[0], out[1]
                 viewspace = out[2] if len(out) > 2 else None
-            loss = self.loss_fn(image, gts[v])
+                invdepth = out[3] if len(out) > 3 else None
+            if target is not None and depth_w > 0.0 and invdepth is not None:
+                loss = self.loss_fn(image, gts[v], invdepth=invdepth, depth_target=target, depth_weight=depth_w)
+            else:
+                loss = self.loss_fn(image, gts[v])
             loss.backward()
             if leaves is not None:
                 self.g.accumulate(leaves)
@@ -398,7 +493,7 @@ class ViewParallelTrainer:
             self._new_stats()
             self._make_peer()
             rebuilt = True
-        if it % c.opacity_reset_interval == 0:
+        if it % c.opacity_reset_interval == 0 or (c.white_background and it == c.densify_from_iter):
             if self.reset_opacity_fn is not None:
                 self.reset_opacity_fn(self.g)
             else:
@@ -406,9 +501,21 @@ class ViewParallelTrainer:
                 densify.reset_opacity(self.g)
         return rebuilt
 
-    def step(self, cams, gts, bg, num_views_scale=True):
+    def begin_iteration(self):
+        """what LG/train.py does at the top of an iteration (:99-103): position learning rate of this iteration, and
+        one more SH degree every 1000 iterations"""
         self.iteration += 1
-        loss = self.accumulate_views(cams, gts, bg)
+        sch = self.schedule
+        if sch is not None:
+            self.adam = self.adam._replace(lr_xyz=sch.position_lr(self.iteration))
+            if sch.oneup_sh_every > 0 and self.iteration % sch.oneup_sh_every == 0:
+                self.g.active_sh_degree = min(self.g.active_sh_degree + 1, self.g.sh_degree)
+
+    def step(self, cams, gts, bg, num_views_scale=True, depths=None):
+        self.begin_iteration()
+        loss = self.accumulate_views(cams, gts, bg, depths)
+        if hasattr(self.loss_fn, "sync"):
+            self.loss_fn.sync(self.group)
         if not self.maybe_densify():
             scale = 1.0 / len(cams) if (num_views_scale and len(cams) > 1) else 1.0  # mean over the view batch
             self.exchange_and_update(scale)
@@ -420,6 +527,8 @@ class ViewParallelTrainer:
             self.g.step_count += 1
             self.peer.reduce_adam(self.g.exp_avg, self.g.exp_avg_sq, self.g.adam_segments(self.adam), self.adam,
                                   self.g.step_count, grad_scale)
+            if self.g.step_count % 64 == 0:
+                self.peer.check()  # a timed-out flag barrier must not go unnoticed once densification is over
         else:
             self.reduce_gradients()
             self.g.adam_step(self.adam, grad_scale=grad_scale)

@@ -52,8 +52,9 @@ class _Buf:
 
 
 def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None, antialiasing=False,
-             scale_modifier=1.0, debug=False, want_state=True, with_invdepth=True, prefiltered=False):
-    """Low-level call through the C ABI (no autograd).  Returns dict of outputs, state tensors and raw buffers."""
+             scale_modifier=1.0, debug=False, want_state=True, with_invdepth=True, prefiltered=False, capacity_hint=0):
+    """Low-level call through the C ABI (no autograd).  Returns dict of outputs, state tensors and raw buffers.
+    capacity_hint > 0 takes the speculative entry point (lg_rasterize_forward_hinted)."""
     from lgdwt_b200 import _lib
     dev = t["means3D"].device
     P = t["means3D"].shape[0]
@@ -68,14 +69,16 @@ def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None
     M = 0 if shs is None else shs.shape[1]
     scales = None if cov3D_precomp is not None else t["scales"]
     rots = None if cov3D_precomp is not None else t["rotations"]
-    rc = _lib.lib.lg_rasterize_forward(
+    cap = ctypes.c_int(0)
+    rc = _lib.lib.lg_rasterize_forward_hinted(
         geom.callback, None, binning.callback, None, img.callback, None, P, sh_degree, M, C, _ptr(bg), W, H,
         _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp), _ptr(t["opacities"]), _ptr(scales), scale_modifier,
         _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]), _ptr(c["projmatrix"]), _ptr(c["campos"]),
         cam.tanfovx, cam.tanfovy, int(prefiltered), _ptr(color), _ptr(invd) if with_invdepth else None, int(antialiasing),
-        _ptr(radii), int(debug), _lib.stream_ptr(dev), ctypes.byref(R))
+        _ptr(radii), int(debug), _lib.stream_ptr(dev), int(capacity_hint), ctypes.byref(R), ctypes.byref(cap))
     _lib.check(rc)
-    out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "geom": geom.tensor,
+    out = {"color": color, "invdepth": invd, "radii": radii, "num_rendered": R.value, "binning_capacity": cap.value,
+           "geom": geom.tensor,
            "binning": binning.tensor, "img": img.tensor, "C": C, "M": M}
     if want_state:
         N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
@@ -83,8 +86,8 @@ def run_ours(t, c, cam, bg, sh_degree=3, colors_precomp=None, cov3D_precomp=None
             if name == "rgb" and colors_precomp is not None:
                 continue
             n = nfn(P, C, N, T, R.value)
-            dst = torch.zeros(max(n, 1), dtype=dt, device=dev)
-            rc = _lib.lib.lg_state_read(name.encode(), P, C, W, H, R.value, _ptr(geom.tensor), _ptr(binning.tensor),
+            dst = torch.zeros(max(nfn(P, C, N, T, cap.value), 1), dtype=dt, device=dev)  # laid out for the capacity
+            rc = _lib.lib.lg_state_read(name.encode(), P, C, W, H, cap.value, _ptr(geom.tensor), _ptr(binning.tensor),
                                         _ptr(img.tensor), dst.data_ptr(), dst.numel() * dst.element_size(),
                                         _lib.stream_ptr(dev))
             _lib.check(rc)
@@ -109,7 +112,7 @@ def backward_ours(t, c, cam, bg, fwd, dL_dpix, dL_dinvd=None, sh_degree=3, color
          "dL_dsh": new(P, M, 3) if shs is not None else None, "dL_dscale": new(P, 3) if scales is not None else None,
          "dL_drot": new(P, 4) if scales is not None else None}
     rc = _lib.lib.lg_rasterize_backward(
-        P, sh_degree, M, fwd["num_rendered"], C, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp),
+        P, sh_degree, M, fwd["binning_capacity"], C, _ptr(bg), W, H, _ptr(t["means3D"]), _ptr(shs), _ptr(colors_precomp),
         _ptr(t["opacities"]), _ptr(scales), scale_modifier, _ptr(rots), _ptr(cov3D_precomp), _ptr(c["viewmatrix"]),
         _ptr(c["projmatrix"]), _ptr(c["campos"]), cam.tanfovx, cam.tanfovy, _ptr(fwd["radii"]), _ptr(fwd["geom"]),
         _ptr(fwd["binning"]), _ptr(fwd["img"]), _ptr(dL_dpix), _ptr(dL_dinvd), _ptr(g["dL_dmean2D"]),

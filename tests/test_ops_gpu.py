@@ -406,3 +406,30 @@ def test_fused_adam_matches_torch_optim_adam():
         g.adam_step(cfg, grad_scale=scale)
     for n in dp.GROUPS:
         torch.testing.assert_close(g.field(n), ref_params[n].detach(), rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("hint_factor", [0.3, 1.0, 4.0])
+def test_speculative_binning_capacity_gives_identical_results(hint_factor):
+    """lg_rasterize_forward_hinted: the whole forward is queued for a guessed binning capacity before the host learns
+    num_rendered.  Whatever the guess (too small -> the tail is queued again at the exact size; exact; generous), the
+    outputs, the state and the gradients are those of the synchronous call."""
+    from lgdwt_b200 import scenes
+    sc = scenes.trained_like_scene(40_000, seed=31, log_scale_mean=np.log(0.02))
+    cam = scenes.look_at_camera(400, 304, 0.6911, 0.6911 * 304 / 400, (0.2, -0.1, -4.03))
+    t, c = helpers.scene_to_torch(sc), helpers.cam_to_torch(cam)
+    bg = torch.tensor([0.3, 0.2, 0.1], device="cuda")
+    base = helpers.run_ours(t, c, cam, bg)
+    R = base["num_rendered"]
+    assert R > 1000 and base["binning_capacity"] == R
+    hinted = helpers.run_ours(t, c, cam, bg, capacity_hint=max(1, int(R * hint_factor)))
+    assert hinted["num_rendered"] == R
+    assert hinted["binning_capacity"] == (R if hint_factor < 1.0 else int(R * hint_factor))
+    for k in ("radii", "tiles_touched", "ranges", "point_list_keys", "point_list", "n_contrib", "final_T", "color",
+              "invdepth"):
+        assert torch.equal(hinted[k], base[k]), k
+    dL = torch.randn((3, cam.image_height, cam.image_width), device="cuda",
+                     generator=torch.Generator(device="cuda").manual_seed(2))
+    g0 = helpers.backward_ours(t, c, cam, bg, base, dL, None)
+    g1 = helpers.backward_ours(t, c, cam, bg, hinted, dL, None)
+    for k in ("dL_dmean2D", "dL_dmean3D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot"):
+        assert helpers.rel_err(g1[k], g0[k]) <= 1e-5, k

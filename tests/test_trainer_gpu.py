@@ -251,3 +251,101 @@ def test_fused_ssim_dropin_matches_pytorch_ssim():
     torch.testing.assert_close(two, 0.5 * (v.detach() + 1.0), rtol=1e-5, atol=1e-6)
     with pytest.raises(NotImplementedError):
         fused_ssim(a, gt, padding="valid")
+
+
+def test_fused_trainer_reproduces_the_reference_iteration():
+    """N = 1, one view per step: 30 iterations of the fused trainer with a TrainSchedule and the stateful loss against
+    the STOCK op chain of LG/train.py:99-288 — six nn.Parameters, torch activations (gaussian_model.py:102-130), the
+    rasterizer as an ordinary autograd op (the reference CUDA when oracle/_ref is built), the PyTorch losses, the
+    host-side running-mean DWT scale (:190-196), oneupSHdegree (:101-103, every 10 iterations here), the exponential
+    position learning rate (gaussian_model.py:203-223), the depth-L1 term (:204-216) and torch.optim.Adam.
+    Adam turns a gradient into a step of size ~lr whatever its magnitude, so a parameter whose gradient is summation
+    noise around zero can move differently in the two chains; the bar is therefore 99.9 % of the parameters within
+    1e-4 (absolute, after 30 steps of lr up to 2.5e-2), every parameter within 30 x its learning rate x 2, and the
+    per-iteration loss within 1e-4 relative."""
+    from oracle import dwt_oracle, photometric_oracle, ref_cuda
+    sc = scenes.trained_like_scene(20_000, seed=41, log_scale_mean=np.log(0.03))
+    W, H, iters = 272, 200, 30
+    cams_np = scenes.orbit_cameras(5, W, H)
+    cams = [dp.camera_to_device(c, dev) for c in cams_np]
+    gen = torch.Generator(device=dev).manual_seed(5)
+    gts = [torch.rand((3, H, W), device=dev, generator=gen) for _ in cams]
+    depth_targets = [(torch.rand((1, H, W), device=dev, generator=gen), (torch.rand((1, H, W), device=dev, generator=gen) > 0.3).float())
+                     for _ in cams]
+    bg = torch.zeros(3, device=dev)
+    sched = dp.TrainSchedule(iterations=60, position_lr_max_steps=40, spatial_lr_scale=2.5, oneup_sh_every=10)
+
+    # ---- fused trainer
+    g = dp.FlatGaussians.from_scene(sc, dev)
+    tr = dp.ViewParallelTrainer(g, loss_fn=dp.RunningMeanLoss(dev), schedule=sched)
+    fused_losses = []
+    for it in range(iters):
+        k = it % len(cams)
+        fused_losses.append(float(tr.step([cams[k]], [gts[k]], bg, depths=[depth_targets[k]])))
+    assert g.active_sh_degree == 3 and tr.iteration == iters
+
+    # ---- stock op chain
+    g0 = dp.FlatGaussians.from_scene(sc, dev)
+    P = g0.P
+    raw = {k: torch.nn.Parameter(g0.field(k).clone().reshape(P, *shape)) for k, shape in
+           (("xyz", (3,)), ("f_dc", (1, 3)), ("f_rest", (15, 3)), ("opacity", (1,)), ("scaling", (3,)), ("rotation", (4,)))}
+    a = dp.AdamConfig()
+    lrs = dict(xyz=sched.position_lr_init * sched.spatial_lr_scale, f_dc=a.lr_f_dc, f_rest=a.lr_f_rest,
+               opacity=a.lr_opacity, scaling=a.lr_scaling, rotation=a.lr_rotation)
+    opt = torch.optim.Adam([{"params": [raw[k]], "lr": lrs[k], "name": k} for k in raw], lr=0.0, eps=1e-15)
+    use_ref = ref_cuda.load_ref() is not None
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    rm, active, stock_losses = 1.0, 0, []
+    for it in range(1, iters + 1):
+        for group in opt.param_groups:                       # update_learning_rate (gaussian_model.py:213-223)
+            if group["name"] == "xyz":
+                group["lr"] = sched.position_lr(it)
+        if it % sched.oneup_sh_every == 0:
+            active = min(active + 1, 3)
+        k = (it - 1) % len(cams)
+        cam, gt = cams[k], gts[k]
+        shs = torch.cat((raw["f_dc"], raw["f_rest"]), dim=1)
+        vsp = torch.zeros_like(raw["xyz"], requires_grad=True)
+        args = (raw["xyz"], vsp, shs, torch.sigmoid(raw["opacity"]), torch.exp(raw["scaling"]),
+                torch.nn.functional.normalize(raw["rotation"]))
+        if use_ref:
+            image, radii, invd = ref_cuda.RefRasterize.apply(*args, cam, bg, active)
+        else:
+            rs = GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"],
+                                               cam["projmatrix"], active, cam["campos"], False, False, False)
+            image, radii, invd = GaussianRasterizer(rs)(means3D=args[0], means2D=vsp, shs=shs, opacities=args[3],
+                                                         scales=args[4], rotations=args[5])
+        image = image.clamp(0, 1)
+        l1, ssim = photometric_oracle.photometric_terms(image, gt)
+        dwt, patch, _, _ = dwt_oracle.lgdwt_losses(image, gt)
+        base = 0.8 * l1 + 0.2 * (1.0 - ssim)
+        rm = 0.95 * rm + 0.05 * (base / (dwt + 1e-8)).item()
+        loss = base + float(max(0.1, min(10.0, rm))) * dwt + 0.1 * patch
+        mono, mask = depth_targets[k]
+        loss = loss + sched.depth_l1_weight(it) * torch.abs((invd - mono) * mask).mean()
+        loss.backward()
+        stock_losses.append(float(loss))
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    rel = np.abs(np.array(fused_losses) - np.array(stock_losses)) / np.abs(np.array(stock_losses))
+    assert rel.max() <= 1e-4, "per-iteration loss: max rel diff %.3g at iteration %d" % (rel.max(), int(rel.argmax()) + 1)
+    assert abs(float(tr.loss_fn.running_mean) - rm) <= 1e-5 * abs(rm)
+    worst = {}
+    for k in raw:
+        mine, ref = g.field(k).reshape(-1), raw[k].detach().reshape(-1)
+        d = (mine - ref).abs()
+        frac = float((d <= 1e-4).float().mean())
+        worst[k] = (frac, float(d.max()))
+        assert frac >= 0.999, "%s: only %.5f of the parameters within 1e-4" % (k, frac)
+        assert float(d.max()) <= 2 * iters * max(lrs[k], sched.position_lr(1)), "%s: max diff %g" % (k, float(d.max()))
+    print("fused trainer vs stock chain after %d iterations: loss rel %.2g; per group (fraction within 1e-4, max): %s"
+          % (iters, rel.max(), worst))
+
+
+def test_peer_exchange_falls_back_when_sh_row_is_not_16_byte_sized():
+    """SH degree 0 / 2 (rows of 3 / 27 floats) cannot take the 16-byte peer Adam path: the trainer must say so and
+    keep the NCCL exchange instead of failing at the first step (single process: the decision is local)"""
+    for deg, ok in ((0, False), (1, True), (2, False), (3, True)):
+        g = dp.FlatGaussians(1000, torch.device(dev), sh_degree=deg)
+        assert ((3 * g.M) % 4 == 0) == ok
