@@ -148,7 +148,10 @@ class Stepper:
         self.means2D = torch.zeros((P, 3), device=device, requires_grad=True)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.copy_done = [torch.cuda.Event() for _ in range(VIEWS_PER_RANK)]
-        self.dev_gt = [torch.empty((3, HEIGHT, WIDTH), device=device) for _ in range(VIEWS_PER_RANK)]
+        self.dev_gt = [[torch.empty((3, HEIGHT, WIDTH), device=device) for _ in range(VIEWS_PER_RANK)] for _ in range(2)]
+        self.host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_ready = [torch.cuda.Event() for _ in range(2)]
+        self.e2e_steps, self.last_loss = 0, float("nan")
         # the flat gradient bucket (what a data-parallel step all-reduces): means3D 3 | shs 48 | opacity 1 | scales 3 | rot 4
         self.peer, self.peer_unavailable = None, ""
         if mode == "sinks" and world > 1:
@@ -222,9 +225,10 @@ class Stepper:
         self.exchange()
 
     def step_e2e(self, host_cams, host_gts):
-        """every view's inputs come from pinned host memory; the step's loss goes back to the host.  The camera
-        (needed first) is copied on the compute stream; the 7.7 MB ground-truth image is copied on a side stream while
-        the rasterizer runs and joined right before the loss (same harness for both implementations)."""
+        """every view's inputs come from pinned host memory; the step's loss goes back to the host (read one step
+        late, see below).  The camera (needed first) is copied on the compute stream; the 7.7 MB ground-truth image is
+        copied on a side stream while the rasterizer runs and joined right before the loss (same harness for both
+        implementations)."""
         self.begin_step()
         main = torch.cuda.current_stream(self.device)
         total = torch.zeros((), device=self.device)
@@ -232,20 +236,32 @@ class Stepper:
             cam = dict(host_cam)
             pk = host_cam["packed"].to(self.device, non_blocking=True)  # one 140-byte upload per view
             cam["viewmatrix"], cam["projmatrix"], cam["campos"] = pk[:16].view(4, 4), pk[16:32].view(4, 4), pk[32:35]
+            gt_buf = self.dev_gt[self.e2e_steps % 2][v]
             with torch.cuda.stream(self.copy_stream):
-                # readers of this buffer belong to the previous step, which ended in .item()
-                self.dev_gt[v].copy_(host_gt, non_blocking=True)
+                # double-buffered: the readers of this buffer belong to the step before the previous one, whose loss
+                # has been read back (so it has completed) before this step was started
+                gt_buf.copy_(host_gt, non_blocking=True)
                 self.copy_done[v].record(self.copy_stream)
             color, radii, invd = self.render(cam, v == 0)
             main.wait_event(self.copy_done[v])
             if self.mode in ("sinks", "dropin"):   # this repo's public loss op; the reference arm keeps the stock torch expression
-                loss = self.l1(color, self.dev_gt[v])
+                loss = self.l1(color, gt_buf)
             else:
-                loss = (color - self.dev_gt[v]).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
+                loss = (color - gt_buf).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
             loss.backward()
             total += loss.detach()
         self.exchange()
-        return float(total.item())
+        # device -> host read of the step's loss: an asynchronous copy into pinned memory, waited for only after the NEXT
+        # step has been queued (a trainer logs the loss one step late rather than draining the GPU every step; the
+        # reference's train.py blocks on .item() every iteration).  Every step's loss is read inside the timed region.
+        slot = self.e2e_steps % 2
+        self.e2e_steps += 1
+        self.host_loss[slot].copy_(total, non_blocking=True)
+        self.loss_ready[slot].record(main)
+        if self.e2e_steps >= 2:
+            self.loss_ready[1 - slot].synchronize()
+            self.last_loss = float(self.host_loss[1 - slot])
+        return self.last_loss
 
 
 def timed_loop(fn, steps, world, device):

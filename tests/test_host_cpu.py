@@ -224,3 +224,82 @@ def test_density_control_schedule_follows_train_py():
     assert [c for c in calls if c[0] == "reset"] == [("reset", 6), ("reset", 12)]
     # iterations 6, 9 and 12 rebuilt the set: no optimizer step there (the reference's new Parameters have no .grad)
     assert [i + 1 for i, s in enumerate(steps_before) if s == 0] == [6, 9, 12]
+
+
+def test_white_background_adds_the_reset_at_densify_from_iter():
+    """LG/train.py:275: `iteration % opacity_reset_interval == 0 or (white_background and iteration == densify_from_iter)`"""
+    from lgdwt_b200 import dp
+    for white, want in ((False, [6, 12]), (True, [4, 6, 12])):
+        g = dp.FlatGaussians(8, torch.device("cpu"))
+        calls = []
+        cfg = dp.DensifyConfig(densify_from_iter=4, densify_until_iter=13, densification_interval=3,
+                               opacity_reset_interval=6, white_background=white)
+        render = lambda act, cam, bg: ((act["means3D"].sum() + act["opacities"].sum()).view(1, 1, 1),
+                                       torch.ones(8, dtype=torch.int32))
+        tr = dp.ViewParallelTrainer(g, render_fn=render, loss_fn=lambda img, gt: img.sum(), densify=cfg,
+                                    densify_fn=lambda *a: None, stats_fn=lambda *a: None,
+                                    reset_opacity_fn=lambda g_: calls.append(tr.iteration))
+        for _ in range(15):
+            tr.step([{}], [None], None)
+        assert calls == want, (white, calls)
+
+
+def test_train_schedule_matches_reference_lr_functions_and_sh_schedule():
+    """TrainSchedule.position_lr / depth_l1_weight against a line-by-line restatement of get_expon_lr_func
+    (LG/utils/general_utils.py:29-63) as GaussianModel.training_setup (gaussian_model.py:203-206) and LG/train.py:69
+    call it; oneupSHdegree every `oneup_sh_every` iterations from degree 0 (LG/train.py:101-103); the position learning
+    rate of iteration i is what the Adam step of iteration i uses (update_learning_rate is called first, :99)."""
+    import math
+    from lgdwt_b200 import dp
+
+    def expon(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+        def helper(step):
+            if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+                return 0.0
+            if lr_delay_steps > 0:
+                delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+            else:
+                delay_rate = 1.0
+            t = np.clip(step / max_steps, 0, 1)
+            return delay_rate * np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
+        return helper
+
+    s = dp.TrainSchedule(iterations=7000, position_lr_max_steps=3000, spatial_lr_scale=4.7)
+    ref_xyz = expon(s.position_lr_init * 4.7, s.position_lr_final * 4.7, lr_delay_mult=s.position_lr_delay_mult,
+                    max_steps=3000)
+    ref_depth = expon(s.depth_l1_weight_init, s.depth_l1_weight_final, max_steps=7000)
+    for it in (1, 2, 17, 1500, 2999, 3000, 3001, 6999, 7000, 9000):
+        assert math.isclose(s.position_lr(it), float(ref_xyz(it)), rel_tol=1e-12), it
+        assert math.isclose(s.depth_l1_weight(it), float(ref_depth(it)), rel_tol=1e-12), it
+
+    g = dp.FlatGaussians(8, torch.device("cpu"))
+    render = lambda act, cam, bg: ((act["means3D"].sum() + act["opacities"].sum()).view(1, 1, 1),
+                                   torch.ones(8, dtype=torch.int32))
+    sched = dp.TrainSchedule(oneup_sh_every=4, position_lr_max_steps=10, spatial_lr_scale=2.0)
+    tr = dp.ViewParallelTrainer(g, render_fn=render, loss_fn=lambda img, gt: img.sum(), schedule=sched)
+    assert g.active_sh_degree == 0 and g.sh_degree == 3
+    degrees, lrs = [], []
+    for _ in range(18):
+        tr.step([{}], [None], None)
+        degrees.append(g.active_sh_degree)
+        lrs.append(tr.adam.lr_xyz)
+    assert degrees == [0] * 3 + [1] * 4 + [2] * 4 + [3] * 7          # raised at iterations 4, 8, 12, capped at 3
+    assert all(math.isclose(lr, sched.position_lr(i + 1), rel_tol=1e-12) for i, lr in enumerate(lrs))
+    assert lrs[0] > lrs[5] > lrs[9] and math.isclose(lrs[9], lrs[17])   # decays until max_steps, then constant
+
+
+def test_binning_capacity_hint_bookkeeping():
+    """the operator's speculative binning capacity: no hint before the first call of a (device, P, W, H) shape,
+    afterwards 1.25 x the largest entry count of the last eight calls"""
+    import diff_gaussian_rasterization as dgr
+    dgr._CAPACITY_HISTORY.clear()
+    key = ("cuda:0", 1000, 64, 48)
+    assert dgr._capacity_hint(*key) == 0
+    for r in (100, 400, 300):
+        dgr._record_num_rendered(*key, r)
+    assert dgr._capacity_hint(*key) == int(1.25 * 400) + 1024
+    for r in range(8):
+        dgr._record_num_rendered(*key, 50)
+    assert dgr._capacity_hint(*key) == int(1.25 * 50) + 1024          # the large value aged out
+    assert dgr._capacity_hint("cuda:0", 2000, 64, 48) == 0            # another shape: no history
+    dgr._CAPACITY_HISTORY.clear()
