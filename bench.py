@@ -370,22 +370,34 @@ def image_loss_section(device, hbm_peak):
     """BASELINE config 1 (LGDWT-GS Haar DWT loss on a 3x800x800 render/GT pair) plus the photometric terms: the
     fused kernels forward+backward on the GPU against their HBM roofline, and the CPU port of the reference's
     PyTorch op chain on this box's cores as a reported baseline."""
-    from lgdwt_b200 import fused_dwt_loss, fused_photometric_loss
+    from lgdwt_b200 import fused_image_loss
     from oracle import dwt_oracle, photometric_oracle
     pred_np, gt_np = scenes.dwt_pair(3, HEIGHT, WIDTH, seed=0)
     pred = torch.from_numpy(pred_np).to(device).requires_grad_(True)
     gt = torch.from_numpy(gt_np).to(device)
+    rm = torch.ones((), device=device)
 
     def gpu_step():
         pred.grad = None
-        dwt, patch, _ = fused_dwt_loss(pred, gt)
-        l1, ssim = fused_photometric_loss(pred, gt)
-        (0.8 * l1 + 0.2 * (1.0 - ssim) + dwt + 0.1 * patch).backward()
+        loss, _ = fused_image_loss(pred, gt, rm)   # L1 + SSIM + DWT + patch + running-mean scale: one autograd node
+        loss.backward()
 
     for _ in range(5):
         gpu_step()
     n = 20
     ms = timed_loop(lambda i: gpu_step(), n, 1, device) / n
+    # the L1 + SSIM kernels alone, for comparison with the reference's fused-ssim CUDA kernel (SSIM/ssim.cu, timed by the
+    # reference arm as `fused_ssim_fwd_bwd_ms` on the same tensors)
+    from lgdwt_b200 import fused_photometric_loss
+
+    def ph_step():
+        pred.grad = None
+        l1, ss = fused_photometric_loss(pred, gt)
+        (0.8 * l1 + 0.2 * (1.0 - ss)).backward()
+
+    for _ in range(5):
+        ph_step()
+    ph_ms = timed_loop(lambda i: ph_step(), n, 1, device) / n
     chw = 3 * HEIGHT * WIDTH
     alg = (8 + 12) * chw + (8 + 12 + 20 + 4) * chw  # dwt fwd+bwd, photometric fwd (+maps) + bwd, SURVEY.md §8(d)
     cpu_pred = torch.from_numpy(pred_np).requires_grad_(True)
@@ -399,11 +411,39 @@ def image_loss_section(device, hbm_peak):
         (0.8 * l1 + 0.2 * (1.0 - ss) + d + 0.1 * p).backward()
     cpu_ms = (time.perf_counter() - t0) / reps * 1e3
     return {"workload": "config 1: L1 + SSIM + 2-level DWT + patch-ELF loss, fwd+bwd, 3x%dx%d pair" % (HEIGHT, WIDTH),
-            "gpu_fused_ms": round(ms, 4), "gpu_launches": 7, "bound": "hbm", "algorithmic_bytes": alg,
+            "gpu_fused_ms": round(ms, 4), "gpu_launches": 10, "bound": "hbm", "algorithmic_bytes": alg,
             "achieved_GBps": round(alg / (ms * 1e-3) / 1e9, 1), "peak_GBps": hbm_peak,
             "frac": round(alg / (ms * 1e-3) / 1e9 / hbm_peak, 4),
-            "note": "includes torch autograd/launch overhead of 2 ops; the 5 kernels are launch-bound at this size",
+            "note": "one autograd node (lgdwt_b200.fused_image_loss): 6 launches forward, 4 backward; launch-bound at this size",
+            "photometric_fwd_bwd_ms": round(ph_ms, 4),
             "cpu_port_ms": round(cpu_ms, 2), "cpu_threads": torch.get_num_threads(), "cpu_kind": "port"}
+
+
+def reference_fused_ssim_section(device):
+    """the reference's own fused SSIM CUDA kernel (submodules/fused-ssim, built by its setup.py into baseline/_ref/site)
+    forward + backward on the config-1 tensors, with the L1 term as LG/train.py computes it (torch) — the counterpart of
+    `image_loss.photometric_fwd_bwd_ms` of this repo's arm"""
+    if not os.path.isdir(os.path.join(REF_SITE, "fused_ssim")):
+        return {"unavailable": "baseline/_ref/site/fused_ssim not installed"}
+    if REF_SITE not in sys.path:
+        sys.path.insert(0, REF_SITE)
+    from fused_ssim import fused_ssim
+    pred_np, gt_np = scenes.dwt_pair(3, HEIGHT, WIDTH, seed=0)
+    pred = torch.from_numpy(pred_np).to(device).requires_grad_(True)
+    gt = torch.from_numpy(gt_np).to(device)
+
+    def step():
+        pred.grad = None
+        l1 = torch.abs(pred - gt).mean()                                   # l1_loss, LG/utils/loss_utils.py:40-41
+        ss = fused_ssim(pred.unsqueeze(0), gt.unsqueeze(0))                # LG/train.py:182-183
+        (0.8 * l1 + 0.2 * (1.0 - ss)).backward()
+
+    for _ in range(5):
+        step()
+    n = 20
+    ms = timed_loop(lambda i: step(), n, 1, device) / n
+    return {"workload": "L1 (torch) + fused_ssim (reference CUDA kernel) forward+backward, 3x%dx%d pair" % (HEIGHT, WIDTH),
+            "fused_ssim_fwd_bwd_ms": round(ms, 4)}
 
 
 def train_iteration_section(impl, device, iters=40, warm=10):
@@ -823,6 +863,7 @@ def reference_arm(args, K, W, local):
     }
     if not args.no_train_iteration:
         line["train_iteration"] = train_iteration_section("reference", device)
+        line["image_loss"] = reference_fused_ssim_section(device)
     print(json.dumps(line))
     return 0
 

@@ -379,6 +379,18 @@ int lg_photometric_loss_forward(const float* pred, const float* gt, int C, int H
 int lg_photometric_loss_backward(const float* pred, const float* gt, int C, int H, int W, const char* workspace,
                                  const float* g_l1, const float* g_ssim, float* dL_dpred, void* stream);
 
+/* Loss assembly of one training iteration on the device (LG/train.py:188-202), between the forward kernels above and
+ * their backward: photometric_out = the two floats of lg_photometric_loss_forward, dwt_out = the out_losses of
+ * lg_dwt_loss_forward.  base = (1 - lambda) * L1 + lambda * (1 - SSIM); with update_running_mean != 0 the running-mean
+ * ratio of LG/train.py:190-196 is advanced in place (device scalar, no host round trip: the reference calls .item());
+ * loss_out[0] = base + clamp(rm, 0.1, 10) * dwt + patch_weight * patch, loss_out[1] = base; coef_out[4] =
+ * d(loss)/d(l1, ssim, dwt, patch).  lg_image_loss_backward_coefs multiplies them by the upstream gradient (device
+ * scalar) -> the g_* inputs of the two backward entry points; lg_image_loss_add sums their two image gradients. */
+int lg_image_loss_combine(const float* photometric_out, const float* dwt_out, float* running_mean, float lambda_dssim,
+                          float patch_weight, int update_running_mean, float* loss_out, float* coef_out, void* stream);
+int lg_image_loss_backward_coefs(const float* coef, const float* g, float* out4, void* stream);
+int lg_image_loss_add(float* a, const float* b, long long n, void* stream);
+
 /* Single-level Haar analysis (the pytorch_wavelets.DWTForward(J=1,'symmetric','db1') call sites at
  * LG/utils/loss_utils.py:140-148).  x (N*C,H,W) -> ll (N*C,H2,W2), yh (N*C,3,H2,W2) with H2=(H+1)/2.
  * and its adjoint (for autograd through the compat module).                                              */

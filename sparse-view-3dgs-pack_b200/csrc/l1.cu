@@ -85,3 +85,84 @@ extern "C" int lg_l1_loss_backward(const float* pred, const float* gt, long long
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
+
+// ---------------------------------------------------------------- loss assembly (LG/train.py:188-202)
+namespace lg {
+// One thread: base = (1 - lambda) * L1 + lambda * (1 - SSIM); the running-mean ratio that rescales the DWT term
+// (rm <- 0.95 rm + 0.05 base / (dwt + 1e-8), used clamped to [0.1, 10] in the same iteration); loss = base + scale * dwt
+// + patch_weight * patch.  Also leaves d(loss)/d(l1, ssim, dwt, patch) for the backward.  Replaces a dozen scalar
+// PyTorch kernels and the reference's `.item()` host round trip (LG/train.py:193).
+__global__ void image_loss_combine_kernel(const float* __restrict__ photometric, const float* __restrict__ dwt_out,
+                                          float* running_mean, float lambda_dssim, float patch_weight,
+                                          int update_running_mean, float* __restrict__ loss_out,
+                                          float* __restrict__ coef_out) {
+    const float l1 = photometric[0], ssim = photometric[1], dwt = dwt_out[0], patch = dwt_out[1];
+    const float base = (1.0f - lambda_dssim) * l1 + lambda_dssim * (1.0f - ssim);
+    float rm = running_mean[0];
+    if (update_running_mean) {
+        rm = 0.95f * rm + 0.05f * (base / (dwt + 1e-8f));
+        running_mean[0] = rm;
+    }
+    const float scale = fminf(fmaxf(rm, 0.1f), 10.0f);
+    loss_out[0] = base + scale * dwt + patch_weight * patch;
+    loss_out[1] = base;
+    coef_out[0] = 1.0f - lambda_dssim;
+    coef_out[1] = -lambda_dssim;
+    coef_out[2] = scale;
+    coef_out[3] = patch_weight;
+}
+// coefficients of the backward: d(loss)/d(term) * upstream gradient (device scalar)
+__global__ void image_loss_scale_kernel(const float* __restrict__ coef, const float* __restrict__ g, float* __restrict__ out) {
+    if (threadIdx.x < 4) out[threadIdx.x] = coef[threadIdx.x] * g[0];
+}
+// dL_dpred = a + b over n floats (the two backward kernels write one image each)
+__global__ void __launch_bounds__(256) image_loss_add_kernel(float4* __restrict__ a, const float4* __restrict__ b, long long n4,
+                                                             float* a_tail, const float* b_tail, int tail) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 x = a[i];
+        const float4 y = b[i];
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        a[i] = x;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) a_tail[threadIdx.x] += b_tail[threadIdx.x];
+}
+}  // namespace lg
+
+extern "C" int lg_image_loss_combine(const float* photometric_out, const float* dwt_out, float* running_mean,
+                                     float lambda_dssim, float patch_weight, int update_running_mean, float* loss_out,
+                                     float* coef_out, void* stream_v) {
+    if (!photometric_out || !dwt_out || !running_mean || !loss_out || !coef_out) {
+        set_error("lg_image_loss_combine: null pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    image_loss_combine_kernel<<<1, 1, 0, (cudaStream_t)stream_v>>>(photometric_out, dwt_out, running_mean, lambda_dssim,
+                                                                  patch_weight, update_running_mean, loss_out, coef_out);
+    LG_LAUNCH_CHECK(false, (cudaStream_t)stream_v);
+    return LG_OK;
+}
+
+extern "C" int lg_image_loss_backward_coefs(const float* coef, const float* g, float* out4, void* stream_v) {
+    if (!coef || !g || !out4) {
+        set_error("lg_image_loss_backward_coefs: null pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    image_loss_scale_kernel<<<1, 32, 0, (cudaStream_t)stream_v>>>(coef, g, out4);
+    LG_LAUNCH_CHECK(false, (cudaStream_t)stream_v);
+    return LG_OK;
+}
+
+extern "C" int lg_image_loss_add(float* a, const float* b, long long n, void* stream_v) {
+    if (!a || !b || n < 0 || (((uintptr_t)a | (uintptr_t)b) & 15u)) {
+        set_error("lg_image_loss_add: invalid arguments (16-byte aligned buffers)");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return LG_OK;
+    const long long n4 = n / 4;
+    const long long want = (n4 + 255) / 256;
+    const int blocks = (int)(want < (long long)LG_NUM_SMS * 8 ? (want > 0 ? want : 1) : (long long)LG_NUM_SMS * 8);
+    image_loss_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream_v>>>((float4*)a, (const float4*)b, n4, a + 4 * n4, b + 4 * n4,
+                                                                      (int)(n - 4 * n4));
+    LG_LAUNCH_CHECK(false, (cudaStream_t)stream_v);
+    return LG_OK;
+}

@@ -127,6 +127,12 @@ def _load():
     lib.lg_l1_loss_forward.argtypes = [_P, _P, ctypes.c_longlong, _P, _P, _P]
     lib.lg_l1_loss_backward.restype = i
     lib.lg_l1_loss_backward.argtypes = [_P, _P, ctypes.c_longlong, _P, _P, _P]
+    lib.lg_image_loss_combine.restype = i
+    lib.lg_image_loss_combine.argtypes = [_P, _P, _P, f, f, i, _P, _P, _P]
+    lib.lg_image_loss_backward_coefs.restype = i
+    lib.lg_image_loss_backward_coefs.argtypes = [_P, _P, _P, _P]
+    lib.lg_image_loss_add.restype = i
+    lib.lg_image_loss_add.argtypes = [_P, _P, ctypes.c_longlong, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

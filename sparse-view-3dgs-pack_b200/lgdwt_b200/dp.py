@@ -323,15 +323,13 @@ class RunningMeanLoss:
     def __init__(self, device, lambda_dssim=0.2, patch_weight=0.1, cfg=None):
         self.running_mean = torch.ones((), dtype=torch.float32, device=device)
         self.lambda_dssim, self.patch_weight, self.cfg = lambda_dssim, patch_weight, cfg
+        self.terms = None  # the last call's term values (fused_image_loss), for logging
 
     def __call__(self, image, gt, invdepth=None, depth_target=None, depth_weight=0.0):
-        from .dwt_loss import DWTLossConfig, fused_dwt_loss
-        from .photometric import fused_photometric_loss
-        l1, ssim = fused_photometric_loss(image, gt)
-        dwt, patch, _ = fused_dwt_loss(image, gt, self.cfg or DWTLossConfig())
-        base = (1.0 - self.lambda_dssim) * l1 + self.lambda_dssim * (1.0 - ssim)
-        self.running_mean = 0.95 * self.running_mean + 0.05 * (base.detach() / (dwt.detach() + 1e-8))
-        loss = base + self.running_mean.clamp(0.1, 10.0) * dwt + self.patch_weight * patch
+        from .dwt_loss import DWTLossConfig
+        from .image_loss import fused_image_loss
+        loss, self.terms = fused_image_loss(image, gt, self.running_mean, self.cfg or DWTLossConfig(), self.lambda_dssim,
+                                            self.patch_weight, update_running_mean=True)
         if depth_target is not None and depth_weight > 0.0 and invdepth is not None:
             mono, mask = depth_target
             loss = loss + depth_weight * torch.abs((invdepth - mono) * mask).mean()
@@ -342,7 +340,7 @@ class RunningMeanLoss:
         next step alike (one 4-byte all-reduce, issued before the exchange step)"""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.running_mean, op=dist.ReduceOp.SUM, group=group)
-            self.running_mean = self.running_mean / dist.get_world_size(group)
+            self.running_mean.div_(dist.get_world_size(group))
 
 
 def _default_densify(g, stats, cfg, max_screen_size, generator):

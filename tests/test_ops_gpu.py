@@ -433,3 +433,38 @@ def test_speculative_binning_capacity_gives_identical_results(hint_factor):
     g1 = helpers.backward_ours(t, c, cam, bg, hinted, dL, None)
     for k in ("dL_dmean2D", "dL_dmean3D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot"):
         assert helpers.rel_err(g1[k], g0[k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("shape", [(3, 264, 392), (3, 800, 800), (4, 301, 257)])
+def test_fused_image_loss_equals_the_reference_loss_assembly(shape):
+    """fused_image_loss (one autograd node) against the loss assembly of LG/train.py:128-202 written out with the CPU
+    oracle's PyTorch restatement of the reference terms: value, the running-mean update over three consecutive
+    iterations, and the image gradient."""
+    from lgdwt_b200 import fused_image_loss
+    from oracle import photometric_oracle
+    C, H, W = shape
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    gt = torch.rand((C, H, W), device="cuda", generator=gen)
+    rm_dev = torch.ones((), device="cuda")
+    rm_host = 1.0
+    for it in range(3):
+        pred = (gt + 0.05 * (it + 1) * torch.randn((C, H, W), device="cuda", generator=gen)).clamp(0, 1).requires_grad_(True)
+        loss, terms = fused_image_loss(pred, gt, rm_dev)
+        loss.backward()
+        ref_pred = pred.detach().clone().requires_grad_(True)
+        l1, ssim = photometric_oracle.photometric_terms(ref_pred, gt)
+        dwt, patch, _, _ = dwt_oracle.lgdwt_losses(ref_pred, gt)
+        base = 0.8 * l1 + 0.2 * (1.0 - ssim)
+        rm_host = 0.95 * rm_host + 0.05 * (base / (dwt + 1e-8)).item()          # LG/train.py:193-195
+        ref = base + float(max(0.1, min(10.0, rm_host))) * dwt + 0.1 * patch
+        ref.backward()
+        assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref)), (it, float(loss), float(ref))
+        assert abs(float(rm_dev) - rm_host) <= 1e-6 * abs(rm_host), (it, float(rm_dev), rm_host)
+        np.testing.assert_allclose(terms[:4].cpu().numpy(), [float(l1), float(ssim), float(dwt), float(patch)], rtol=2e-6, atol=1e-8)
+        err = (pred.grad - ref_pred.grad).abs().max()
+        assert float(err) <= 1e-5 * float(ref_pred.grad.abs().max()) + 1e-9, (it, float(err))
+    # update_running_mean=False leaves the scalar alone and uses it as given
+    before = float(rm_dev)
+    pred = gt.clone().mul_(0.9).requires_grad_(True)
+    fused_image_loss(pred, gt, rm_dev, update_running_mean=False)[0].backward()
+    assert float(rm_dev) == before
