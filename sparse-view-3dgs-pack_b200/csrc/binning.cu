@@ -245,7 +245,8 @@ template <int THREADS>
 struct TsSmem {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int MAXIPT = THREADS >= 1024 ? 8 : TS_MAX_IPT;  // entries per thread held in registers
-    static constexpr int CAP = THREADS * MAXIPT;
+    static constexpr int HALF = THREADS * MAXIPT;                    // longest list sorted in one go
+    static constexpr int CAP = THREADS >= 1024 ? HALF : 2 * HALF;    // 256 threads: two sorted halves + a merge
     uint32_t warp_hist[WARPS][TS_RADIX];  // per warp and digit: running count, then exclusive prefix over warps
     uint32_t excl[TS_RADIX];              // per digit: first slot inside the chunk
     uint32_t base[TS_RADIX];              // multi-chunk passes: running global offset of every digit
@@ -331,7 +332,7 @@ __device__ __forceinline__ void ts_digit_scan(TsSmem<THREADS>& s, uint32_t count
 
 // one in-shared-memory pass: items (registers, warp-striped) -> s.items in digit order -> back into the registers
 template <int THREADS, int IPT, int SEL>
-__device__ __forceinline__ void ts_pass_smem(TsSmem<THREADS>& s, uint2 (&it)[IPT], uint32_t n, int shift,
+__device__ __forceinline__ void ts_pass_smem(TsSmem<THREADS>& s, uint2* items, uint2 (&it)[IPT], uint32_t n, int shift,
                                              uint32_t sub = 0u) {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t warp_base = warp * 32u * IPT;
@@ -343,14 +344,14 @@ __device__ __forceinline__ void ts_pass_smem(TsSmem<THREADS>& s, uint2 (&it)[IPT
         const uint32_t g = warp_base + i * 32 + lane;
         if (g < n) {
             const uint32_t d = ((ts_key<SEL>(it[i]) - sub) >> shift) & 255u;
-            s.items[s.excl[d] + s.warp_hist[warp][d] + rank[i]] = it[i];
+            items[s.excl[d] + s.warp_hist[warp][d] + rank[i]] = it[i];
         }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
         const uint32_t g = warp_base + i * 32 + lane;
-        if (g < n) it[i] = s.items[g];
+        if (g < n) it[i] = items[g];
     }
 }
 
@@ -364,10 +365,9 @@ __device__ __forceinline__ void ts_pass_smem(TsSmem<THREADS>& s, uint2 (&it)[IPT
 // Returns true when a group is longer than TS_MAX_GROUP_LEN or the queue overflows: the caller then falls back to the
 // full LSD sort.
 template <int THREADS>
-__device__ __forceinline__ bool ts_fix_groups(TsSmem<THREADS>& s, uint32_t n, uint32_t sub, int lo) {
+__device__ __forceinline__ bool ts_fix_groups(TsSmem<THREADS>& s, uint2* items, uint32_t n, uint32_t sub, int lo) {
     constexpr int WARPS = THREADS / 32;
     constexpr int PER_LANE = TS_MAX_GROUP_LEN / 32;
-    uint2* items = s.items;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t q = threadIdx.x; q + 1 < n; q += THREADS) {
         const uint2 me = items[q], next = items[q + 1];
@@ -429,8 +429,8 @@ __device__ __forceinline__ bool ts_fix_groups(TsSmem<THREADS>& s, uint32_t n, ui
 // Fallback (long runs of equal / nearly equal depths): full stable LSD sort, id digits first, then every depth digit
 // that varies inside the tile.
 template <int THREADS, int IPT>
-__device__ __forceinline__ void ts_sort_in_smem(TsSmem<THREADS>& s, const uint2* __restrict__ src, uint32_t n,
-                                                uint32_t* __restrict__ out, int id_bits) {
+__device__ __noinline__ void ts_sort_in_smem(TsSmem<THREADS>& s, uint2* items, const uint2* __restrict__ src,
+                                                uint32_t n, uint32_t* __restrict__ out, int id_bits) {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t warp_base = warp * 32u * IPT;
     uint2 it[IPT];
@@ -464,31 +464,62 @@ __device__ __forceinline__ void ts_sort_in_smem(TsSmem<THREADS>& s, const uint2*
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
             const uint32_t g = warp_base + i * 32 + lane;
-            if (g < n) s.items[g] = it[i];
+            if (g < n) items[g] = it[i];
         }
         __syncthreads();
     } else {
         lo = max(0, (31 - __clz(span)) - 15);
-        ts_pass_smem<THREADS, IPT, 0>(s, it, n, lo, kmin);
-        if ((span >> lo) > 255u) ts_pass_smem<THREADS, IPT, 0>(s, it, n, lo + 8, kmin);
+        ts_pass_smem<THREADS, IPT, 0>(s, items, it, n, lo, kmin);
+        if ((span >> lo) > 255u) ts_pass_smem<THREADS, IPT, 0>(s, items, it, n, lo + 8, kmin);
     }
-    if (ts_fix_groups<THREADS>(s, n, kmin, lo)) {
+    if (ts_fix_groups<THREADS>(s, items, n, kmin, lo)) {
         const uint32_t varying = s.red[0] ^ s.red[1];  // depth bits that differ inside this tile
 #pragma unroll
         for (int i = 0; i < IPT; i++) {
             const uint32_t g = warp_base + i * 32 + lane;
-            if (g < n) it[i] = s.items[g];
+            if (g < n) it[i] = items[g];
         }
 #pragma unroll 1
-        for (int shift = 0; shift < id_bits; shift += 8) ts_pass_smem<THREADS, IPT, 1>(s, it, n, shift);
+        for (int shift = 0; shift < id_bits; shift += 8) ts_pass_smem<THREADS, IPT, 1>(s, items, it, n, shift);
 #pragma unroll 1
         for (int shift = 0; shift < 32; shift += 8) {
             if (((varying >> shift) & 255u) == 0u) continue;  // a digit every key shares: nothing to reorder
-            ts_pass_smem<THREADS, IPT, 0>(s, it, n, shift);
+            ts_pass_smem<THREADS, IPT, 0>(s, items, it, n, shift);
         }
         __syncthreads();
     }
-    for (uint32_t q = tid; q < n; q += THREADS) out[q] = s.items[q].y;
+    if (out != nullptr)
+        for (uint32_t q = tid; q < n; q += THREADS) out[q] = items[q].y;
+}
+
+// Lists of HALF < n <= 2 * HALF entries (256-thread blocks): the two halves of the scattered list are sorted one
+// after the other into the two halves of the shared item buffer and merged on the way out.  Every thread produces a
+// run of consecutive output slots: a merge-path binary search finds how many entries of each half precede its run,
+// then it merges serially (keys are (depth bits, id) pairs: distinct, so the merge is unambiguous).
+__device__ __forceinline__ bool ts_pair_less(const uint2& a, const uint2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+
+template <int THREADS>
+__device__ __forceinline__ void ts_merge_out(const uint2* __restrict__ A, uint32_t nA, const uint2* __restrict__ B,
+                                             uint32_t nB, uint32_t* __restrict__ out) {
+    const uint32_t n = nA + nB;
+    const uint32_t per = (n + THREADS - 1) / THREADS;
+    const uint32_t d0 = min(threadIdx.x * per, n), d1 = min(d0 + per, n);
+    // largest i with i + j = d0 such that the first i entries of A and j of B are the d0 smallest
+    uint32_t lo = d0 > nB ? d0 - nB : 0u, hi = min(d0, nA);
+    while (lo < hi) {
+        const uint32_t i = (lo + hi) >> 1;   // candidate: take i from A, d0 - i from B; too few from A if A[i] < B[d0-i-1]
+        if (ts_pair_less(A[i], B[d0 - i - 1])) lo = i + 1;
+        else hi = i;
+    }
+    uint32_t i = lo, j = d0 - lo;
+    uint2 a = i < nA ? A[i] : make_uint2(0xffffffffu, 0xffffffffu);
+    uint2 b = j < nB ? B[j] : make_uint2(0xffffffffu, 0xffffffffu);
+    for (uint32_t k = d0; k < d1; k++) {
+        const bool take_a = j >= nB || (i < nA && ts_pair_less(a, b));
+        out[k] = take_a ? a.y : b.y;
+        if (take_a) { i++; a = i < nA ? A[i] : make_uint2(0xffffffffu, 0xffffffffu); }
+        else { j++; b = j < nB ? B[j] : make_uint2(0xffffffffu, 0xffffffffu); }
+    }
 }
 
 // Lists longer than the shared-memory capacity: the same LSD passes streamed through global memory, chunk by chunk,
@@ -566,8 +597,9 @@ __device__ void ts_sort_streamed(TsSmem<THREADS>& s, uint2* a, uint2* b, uint32_
     for (uint32_t q = tid; q < n; q += THREADS) out[q] = src[q].y;
 }
 
-// One block per tile, longest lists first.  LARGE = false: 256 threads, lists of 1..4096 entries; LARGE = true:
-// 1024 threads, lists above 4096 (up to 8192 in shared memory, streamed beyond that).
+// One block per tile, longest lists first.  LARGE = false: 256 threads, lists of 1..8192 entries (above 4096 as two
+// sorted halves merged on the way out); LARGE = true: a few persistent 1024-thread blocks for the lists above 8192,
+// streamed through global memory.
 template <int THREADS, bool LARGE>
 __global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_kernel(const uint2* __restrict__ ranges,
                                                             const uint32_t* __restrict__ order, uint2* pairs,
@@ -577,7 +609,7 @@ __global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_
     extern __shared__ __align__(16) unsigned char ts_smem_raw[];
     TsSmem<THREADS>& s = *reinterpret_cast<TsSmem<THREADS>*>(ts_smem_raw);
     if (counters[1] > capacity) return;
-    constexpr uint32_t SMALL_CAP = 256 * TS_MAX_IPT;
+    constexpr uint32_t SMALL_CAP = TsSmem<256>::CAP;  // what the 256-thread blocks take (two halves + merge)
     // LARGE: a few persistent blocks walk the launch order and pick out the long lists (empty 1024-thread blocks with
     // 82 KB of shared memory cost ~6 us per wave to schedule, so one block per tile is not an option here)
     for (uint32_t slot = blockIdx.x; slot < (uint32_t)T; slot += gridDim.x) {
@@ -604,13 +636,27 @@ __global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_
         }
     }
     if constexpr (LARGE) {
-        ts_sort_in_smem<THREADS, TsSmem<THREADS>::MAXIPT>(s, src, n, out, id_bits);
+        ts_sort_in_smem<THREADS, TsSmem<THREADS>::MAXIPT>(s, s.items, src, n, out, id_bits);
     } else {
+        constexpr uint32_t HALF = TsSmem<THREADS>::HALF;
+        if (n > HALF) {
+            const uint32_t nA = n / 2, nB = n - nA;  // both <= HALF
+            ts_sort_in_smem<THREADS, 16>(s, s.items, src, nA, nullptr, id_bits);
+            __syncthreads();
+            if (threadIdx.x == 0) {   // fresh reduction state for the second half
+                s.red[0] = 0u; s.red[1] = 0xffffffffu; s.red[2] = 0u; s.red[3] = 0xffffffffu; s.red[4] = 0u; s.red[5] = 0u;
+            }
+            __syncthreads();
+            ts_sort_in_smem<THREADS, 16>(s, s.items + HALF, src + nA, nB, nullptr, id_bits);
+            __syncthreads();
+            ts_merge_out<THREADS>(s.items, nA, s.items + HALF, nB, out);
+            continue;
+        }
         const uint32_t per_thread = (n + THREADS - 1) / THREADS;
-        if (per_thread <= 2) ts_sort_in_smem<THREADS, 2>(s, src, n, out, id_bits);
-        else if (per_thread <= 4) ts_sort_in_smem<THREADS, 4>(s, src, n, out, id_bits);
-        else if (per_thread <= 8) ts_sort_in_smem<THREADS, 8>(s, src, n, out, id_bits);
-        else ts_sort_in_smem<THREADS, 16>(s, src, n, out, id_bits);
+        if (per_thread <= 2) ts_sort_in_smem<THREADS, 2>(s, s.items, src, n, out, id_bits);
+        else if (per_thread <= 4) ts_sort_in_smem<THREADS, 4>(s, s.items, src, n, out, id_bits);
+        else if (per_thread <= 8) ts_sort_in_smem<THREADS, 8>(s, s.items, src, n, out, id_bits);
+        else ts_sort_in_smem<THREADS, 16>(s, s.items, src, n, out, id_bits);
     }
     }
 }
@@ -658,7 +704,7 @@ int launch_binning(int P, int capacity, int W, int H, const GeometryState& g, co
     tile_sort_kernel<256, false><<<T, 256, smem_small, stream>>>(img.ranges, img.tile_order, b.pairs, b.pairs_alt,
                                                                 b.point_list, id_bits, img.counters, (uint32_t)capacity, T);
     LG_LAUNCH_CHECK(debug, stream);
-    if ((size_t)capacity > 256 * TS_MAX_IPT) {
+    if ((size_t)capacity > (size_t)TsSmem<256>::CAP) {
         tile_sort_kernel<1024, true><<<min(T, LG_NUM_SMS), 1024, smem_large, stream>>>(
             img.ranges, img.tile_order, b.pairs, b.pairs_alt, b.point_list, id_bits, img.counters, (uint32_t)capacity, T);
         LG_LAUNCH_CHECK(debug, stream);
