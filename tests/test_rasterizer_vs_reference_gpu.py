@@ -254,3 +254,14 @@ def test_very_long_tile_lists(P, expect_longer_than):
     cam = scenes.look_at_camera(96, 64, 0.6911, 0.6911 * 64 / 96, (0.0, 0.0, -4.03))
     longest, _ = _binning_case(sc, cam)
     assert longest > expect_longer_than, longest
+
+
+def test_image_wider_than_255_tiles():
+    """more than 255 tiles in x: the packed 8-bit tile rectangles do not apply (the scatter step recomputes them from the
+    projected centre and radius) and the block-aggregated scatter is bypassed"""
+    _need_ref()
+    sc = scenes.trained_like_scene(120_000, seed=23, sigma_xyz=0.9, clip=2.5, log_scale_mean=np.log(0.01))
+    W, H = 4144, 80                                   # 259 x 5 tiles
+    cam = scenes.look_at_camera(W, H, 1.2, 2 * math.atan(math.tan(0.6) * H / W), (0.0, 0.0, -3.0))
+    longest, ours = _binning_case(sc, cam)
+    assert ours["num_rendered"] > 50_000 and longest > 16
