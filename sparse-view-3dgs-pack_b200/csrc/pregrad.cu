@@ -470,9 +470,10 @@ __global__ void __launch_bounds__(256, PG_MIN_BLOCKS) preprocess_backward_kernel
     a.dL_dmean3D[3 * i + 0] = dmean[0];
     a.dL_dmean3D[3 * i + 1] = dmean[1];
     a.dL_dmean3D[3 * i + 2] = dmean[2];
+    if (a.dL_dcov3D) {  // only a cov3D_precomp caller needs it in memory
 #pragma unroll
-    if (a.dL_dcov3D)  // only a cov3D_precomp caller needs it in memory
         for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * i + k] = dcov[k];
+    }
     }  // idx < P
 
     if (STAGED == 1) {  // stream the warp's 32 x 3M gradient block out with coalesced stores

@@ -1,8 +1,8 @@
 // radix_sort.cu — stable LSD radix sort of (key, u32 value) pairs, onesweep style: one up-front histogram of
 // every digit place, then ONE read + ONE write of the pairs per 8-bit digit, with the per-tile digit offsets
 // resolved by a decoupled look-back chain instead of a separate scan pass.
-// Replaces cub::DeviceRadixSort::SortPairs at DGR/cuda_rasterizer/rasterizer_impl.cu:306-311 (u64 tile|depth keys)
-// and KNN/simple_knn.cu:211-214 (u32 Morton codes).
+// Replaces cub::DeviceRadixSort::SortPairs at KNN/simple_knn.cu:211-214 (u32 Morton codes of distCUDA2).  The
+// rasterizer's tile binning (DGR/cuda_rasterizer/rasterizer_impl.cu:306-311) no longer sorts globally: csrc/binning.cu.
 #include "common.cuh"
 
 namespace lg {
@@ -366,12 +366,9 @@ static int radix_sort_pairs_impl(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_
         rs_histogram_kernel<K><<<hist_blocks, 256, 0, stream>>>(keys_a, (uint32_t)n, begin_bit, end_bit, passes, hist);
         LG_LAUNCH_CHECK(debug, stream);
     }
-    static bool attr_set = false;
     const size_t smem = sizeof(RsSmem<K>);
-    if (!attr_set || true) {
-        LG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per call: the attribute belongs to the current device's context, and the call costs about a microsecond
+    LG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     K* src_k = keys_a;
     K* dst_k = keys_b;
     uint32_t* src_v = vals_a;
