@@ -23,32 +23,39 @@ namespace lg {
 #define LG_REC 12  // floats per packed gradient record: mean2D.xy, conic.xyw, opacity, invdepth, colour[C], pad
 
 // Sum N per-lane values over the 32 lanes of a warp.  On return lane L holds in `out` the warp total of value
-// `idx` (idx < N valid); lanes whose slot is padding get valid=false.
-template <int N>
-__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, float& out, int& idx, bool& valid) {
-    int n = N;        // padded slot count at this stage (compile-time after unrolling)
-    int cnt = N;      // true slot count of this lane's group
-    int base = 0;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-        if (n > 1) {
-            const int h = (n + 1) / 2;
+// `idx` (idx < N valid); lanes whose slot is padding get valid=false.  Halving butterfly: at every stage the two
+// partner lanes split the n live values between them (the upper lane keeps the upper half), so stage sizes are
+// ceil(n/2): 9 -> 5, 3, 2, 1, 1 = 12 shuffles; 18 -> 9, 5, 3, 2, 1 = 20.  Sizes are template parameters so that every
+// array index is a compile-time constant (a run-time `n` put the 18-value form into local memory).
+template <int NA, int N, int OFF>
+__device__ __forceinline__ void warp_multi_reduce_stage(float (&v)[NA], unsigned lane, int& base, int& cnt) {
+    if constexpr (OFF >= 1) {
+        const bool upper = (lane & OFF) != 0;
+        if constexpr (N > 1) {
+            constexpr int h = (N + 1) / 2;
 #pragma unroll
             for (int k = 0; k < h; k++) {
                 const float lo = v[k];
-                const float hi = (k + h < n) ? v[k + h] : 0.0f;
+                const float hi = (k + h < N) ? v[k + h] : 0.0f;
                 const float send = upper ? lo : hi;
                 const float keep = upper ? hi : lo;
-                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
             }
             if (upper) { base += h; cnt -= h; } else { cnt = min(cnt, h); }
-            n = h;
+            warp_multi_reduce_stage<NA, h, OFF / 2>(v, lane, base, cnt);
         } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
             if (upper) cnt = 0;  // both partners now hold the same total: the lower lane owns it
+            warp_multi_reduce_stage<NA, 1, OFF / 2>(v, lane, base, cnt);
         }
     }
+}
+
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, float& out, int& idx, bool& valid) {
+    int cnt = N;  // true slot count of this lane's group
+    int base = 0;
+    warp_multi_reduce_stage<N, N, 16>(v, lane, base, cnt);
     out = v[0];
     idx = base;
     valid = cnt >= 1;
@@ -60,6 +67,58 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, 
 // with w = G * dL/dalpha and (dx, dy) = mean2D - pixel.  The reference's dL/dmean2D, dL/dconic and dL/dopacity
 // (backward.cu:598-632) are linear in these moments with per-Gaussian coefficients (conic, opacity), so the
 // coefficients are applied once per Gaussian in the per-Gaussian kernel instead of once per (pixel, Gaussian) hit.
+//
+// Pixel state.  The reference carries accum_rec[c], last_color[c], last_alpha per pixel and forms
+//   dL/dalpha = T * sum_c (col_c - accum_rec_c) * g_c + bg_term / (1 - alpha)          (backward.cu:560-589, g = dL/dpixel)
+// Everything in it is linear in g, so the pixel only needs the scalar B = sum_c accum_rec_c * g_c *as the next hit will
+// see it*: after a hit with colour dot cg = sum_c col_c g_c,  B <- alpha * cg + (1 - alpha) * B.  Two registers of
+// state (T, B) instead of 2C + 2; the inverse-depth term is one more "colour" (1/depth, dL/dinvdepth_pix).
+//
+// No branch around the per-hit arithmetic: lanes whose pixel is not hit run it with alpha = G = 0, which leaves B
+// unchanged and makes every partial sum an exact zero (T is kept by a select); the 7+C zero-initialisations and the
+// divergent region of the earlier version cost more issue slots than the arithmetic they skipped.
+template <int C, bool INVD>
+struct BwdPixel {
+    float T, B;            // transmittance in front of the next hit; blended colour behind it, dotted with g
+    float g[C];            // dL/dpixel
+    float g_invd;          // dL/dinvdepth_pix
+    float bg_term;         // -T_final * sum_c bg_c g_c
+    float x, y;            // pixel centre
+};
+
+template <int C, bool INVD, int NVT>
+__device__ __forceinline__ void bwd_hit_values(BwdPixel<C, INVD>& px, const char* ent, bool hit, float dx, float dy,
+                                               float G, float alpha, float invd, float (&v)[NVT]) {
+    constexpr int VC = 6 + (INVD ? 1 : 0);
+    const float alpha_e = hit ? alpha : 0.0f;
+    const float G_e = hit ? G : 0.0f;
+    float rinv;  // 1 - alpha lies in [0.01, 1]: the bare MUFU.RCP needs no range fix-up
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(1.0f - alpha_e));
+    const float Tn = px.T * rinv;
+    px.T = hit ? Tn : px.T;
+    const float aT = alpha_e * px.T;
+    const float4 f4 = *reinterpret_cast<const float4*>(ent + 32);
+    const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+    float cg = fv[0] * px.g[0];
+#pragma unroll
+    for (int c = 1; c < C; c++) cg = fmaf(fv[c], px.g[c], cg);
+    if (INVD) cg = fmaf(invd, px.g_invd, cg);
+    const float d = cg - px.B;
+    const float dL_dalpha = fmaf(d, px.T, px.bg_term * rinv);
+    px.B = fmaf(alpha_e, d, px.B);
+    const float w = G_e * dL_dalpha;
+    const float wx = w * dx, wy = w * dy;
+    v[0] = wx;
+    v[1] = wy;
+    v[2] = wx * dx;
+    v[3] = wx * dy;
+    v[4] = wy * dy;
+    v[5] = w;
+    if (INVD) v[6] = aT * px.g_invd;
+#pragma unroll
+    for (int c = 0; c < C; c++) v[VC + c] = aT * px.g[c];
+}
+
 template <int C, bool INVD>
 __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
@@ -69,12 +128,13 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec,
     const uint32_t* __restrict__ tile_order) {
     constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
-    constexpr int VC = 6 + (INVD ? 1 : 0);      // first colour slot among the reduced values
+    constexpr int ENT = 48;                     // bytes per staged entry
     // one staged entry = three float4: (mean.x, mean.y, Gaussian id, 1/depth) (conic a, b, c, opacity) (colours, C <= 4),
-    // read as warp-wide broadcasts from a single base address
-    __shared__ float4 s_ent[BWD_BATCH * 3];
-    __shared__ uint8_t s_mask[BWD_BATCH];                    // per staged entry: which of the 8 patches it can touch
-    __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH];  // per warp: compacted slots it must evaluate
+    // read as warp-wide broadcasts from a single base address; entry BWD_BATCH is a sentinel that can never hit
+    // (opacity 0), which pads odd-length lists
+    __shared__ float4 s_ent[(BWD_BATCH + 1) * 3];
+    __shared__ uint8_t s_mask[BWD_BATCH];                        // per staged entry: which of the 8 patches it can touch
+    __shared__ __align__(4) lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH + 2];  // per warp: byte offsets into s_ent
     __shared__ uint32_t s_max;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -84,15 +144,18 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
-    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
     const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
     const uint2 range = ranges[tile];
 
     const float T_final = inside ? final_Ts[pix_id] : 0.0f;
-    float T = T_final;
     const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
 
-    if (tid == 0) s_max = 0;
+    if (tid == 0) {
+        s_max = 0;
+        s_ent[BWD_BATCH * 3 + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        s_ent[BWD_BATCH * 3 + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // opacity 0: alpha = 0 < 1/255
+        s_ent[BWD_BATCH * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     __syncthreads();
     const uint32_t warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0 && warp_max) atomicMax(&s_max, warp_max);
@@ -100,21 +163,22 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const uint32_t n_eff = s_max;  // entries [0, n_eff) of this tile's list can contribute to some pixel
     if (n_eff == 0) return;
 
-    float dL_dpixel[C];
-    float accum_rec[C], last_color[C];
+    BwdPixel<C, INVD> px;
+    px.T = T_final;
+    px.B = 0.0f;
+    px.x = (float)pix_x;
+    px.y = (float)pix_y;
     float bg_dot_dpixel = 0.0f;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        dL_dpixel[c] = inside ? dL_dpixels[(size_t)c * H * W + pix_id] : 0.0f;
-        accum_rec[c] = 0.0f;
-        last_color[c] = 0.0f;
-        bg_dot_dpixel += bg_color[c] * dL_dpixel[c];
+        px.g[c] = inside ? dL_dpixels[(size_t)c * H * W + pix_id] : 0.0f;
+        bg_dot_dpixel += bg_color[c] * px.g[c];
     }
-    const float bg_term = -T_final * bg_dot_dpixel;
-    float dL_invd = 0.0f, accum_invd_rec = 0.0f, last_invd = 0.0f;
-    if (INVD) dL_invd = inside ? dL_dinvdepth_pix[pix_id] : 0.0f;
-    float last_alpha = 0.0f;
+    px.bg_term = -T_final * bg_dot_dpixel;
+    px.g_invd = 0.0f;
+    if (INVD) px.g_invd = inside ? dL_dinvdepth_pix[pix_id] : 0.0f;
 
+    const char* const ent_base = reinterpret_cast<const char*>(s_ent);
     const int rounds = (int)((n_eff + BWD_BATCH - 1) / BWD_BATCH);
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
@@ -145,85 +209,80 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
         // position rel = n_eff-1-(batch_base+j) < warp_max  <=>  j >= n_eff - warp_max - batch_base
         const int first = (int)max((long long)n_eff - (long long)warp_max - (long long)batch_base, 0ll);
         if (first >= batch) continue;
-        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, first, batch);
-        // BWD_UNROLL list entries per trip: their power / exp / alpha evaluations are independent of each other and of
-        // the pixel state, so they are issued together; the hit paths then run in list order.
-        for (int k0 = 0; k0 < cnt; k0 += BWD_UNROLL) {
-          int js[BWD_UNROLL];
-          float dxs[BWD_UNROLL], dys[BWD_UNROLL], Gs[BWD_UNROLL], alphas[BWD_UNROLL], ids[BWD_UNROLL], invds[BWD_UNROLL];
-          bool hits[BWD_UNROLL];
-          unsigned any[BWD_UNROLL];
-#pragma unroll
-          for (int u = 0; u < BWD_UNROLL; u++) {
-            const bool has = k0 + u < cnt;
-            const int j = s_list[warp][has ? k0 + u : k0];
-            const uint32_t rel = n_eff - 1u - (batch_base + (uint32_t)j);  // 0-based position in the tile's list
-            const float4 xy = s_ent[j * 3 + 0];
-            const float4 co = s_ent[j * 3 + 1];
-            const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
-            const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
-            const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, F_MUL(co.w, G));
-            const bool hit = has && rel < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            js[u] = j; dxs[u] = dx; dys[u] = dy; Gs[u] = G; alphas[u] = alpha; ids[u] = xy.z; invds[u] = xy.w;
-            hits[u] = hit;
-            any[u] = __ballot_sync(0xffffffffu, hit);
-          }
-#pragma unroll
-          for (int u = 0; u < BWD_UNROLL; u++) {
-            if (any[u] == 0u) continue;
-            const int j = js[u];
-            const float dx = dxs[u], dy = dys[u], G = Gs[u], alpha = alphas[u];
-            const bool hit = hits[u];
-            float4 xy;
-            xy.z = ids[u];
-            xy.w = invds[u];
-
-            float v[NV];
-#pragma unroll
-            for (int n = 0; n < NV; n++) v[n] = 0.0f;
-            if (hit) {
-                float rinv;  // 1 - alpha lies in [0.01, 1]: the bare MUFU.RCP needs no range fix-up
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(1.0f - alpha));
-                T = T * rinv;
-                const float aT = alpha * T;
-                float dL_dalpha = 0.0f;
-                const float4 f4 = s_ent[j * 3 + 2];
-                const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const float col = fv[c];
-                    accum_rec[c] = fmaf(last_alpha, last_color[c] - accum_rec[c], accum_rec[c]);
-                    last_color[c] = col;
-                    dL_dalpha = fmaf(col - accum_rec[c], dL_dpixel[c], dL_dalpha);
-                    v[VC + c] = aT * dL_dpixel[c];
-                }
-                if (INVD) {
-                    const float invd = xy.w;
-                    accum_invd_rec = fmaf(last_alpha, last_invd - accum_invd_rec, accum_invd_rec);
-                    last_invd = invd;
-                    dL_dalpha = fmaf(invd - accum_invd_rec, dL_invd, dL_dalpha);
-                    v[6] = aT * dL_invd;
-                }
-                last_alpha = alpha;
-                dL_dalpha = fmaf(dL_dalpha, T, bg_term * rinv);
-                const float w = G * dL_dalpha;
-                const float wx = w * dx, wy = w * dy;
-                v[0] = wx;
-                v[1] = wy;
-                v[2] = wx * dx;
-                v[3] = wx * dy;
-                v[4] = wy * dy;
-                v[5] = w;
+        // compacted list of this warp's reachable entries as byte offsets into s_ent, padded to an even length
+        int cnt = 0;
+        {
+            lg_slot_t* list_w = s_list[warp];
+            const unsigned lt = (1u << lane) - 1u;
+            for (int base = first & ~31; base < batch; base += 32) {
+                const int slot = base + (int)lane;
+                const bool bit = slot >= first && slot < batch && ((s_mask[slot] >> warp) & 1u);
+                const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)(slot * ENT);
+                cnt += __popc(bal);
             }
+            if (lane == 0) list_w[cnt] = (lg_slot_t)(BWD_BATCH * ENT);
+            __syncwarp();
+        }
+        // this pixel is behind entry j of the batch  <=>  rel = n_eff-1-(batch_base+j) < last_contributor
+        //                                           <=>  j*ENT > ENT * (n_eff-1-batch_base-last_contributor)
+        const long long thr = (long long)n_eff - 1ll - (long long)batch_base - (long long)last_contributor;
+        const int thr_off = ENT * (int)max(min(thr, (long long)(2 * BWD_BATCH)), -1ll);
+        // two list entries per trip: their power / exp / alpha evaluations are independent of each other and of the
+        // pixel state, so they are issued together; the hit arithmetic then runs in list order and the partial sums of
+        // both entries go through ONE butterfly (20 shuffles for 2 x 9 values instead of 2 x 12)
+        for (int k0 = 0; k0 < cnt; k0 += 2) {
+            const uint32_t offs = *reinterpret_cast<const uint32_t*>(&s_list[warp][k0]);
+            const char* ents[2] = {ent_base + (offs & 0xffffu), ent_base + (offs >> 16)};
+            const int offv[2] = {(int)(offs & 0xffffu), (int)(offs >> 16)};
+            float dxs[2], dys[2], Gs[2], alphas[2], ids[2], invds[2];
+            bool hits[2];
+            unsigned any[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const float4 xy = *reinterpret_cast<const float4*>(ents[u]);
+                const float4 co = *reinterpret_cast<const float4*>(ents[u] + 16);
+                const float dx = F_SUB(xy.x, px.x), dy = F_SUB(xy.y, px.y);
+                const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
+                const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, F_MUL(co.w, G));
+                const bool hit = offv[u] > thr_off && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                dxs[u] = dx; dys[u] = dy; Gs[u] = G; alphas[u] = alpha; ids[u] = xy.z; invds[u] = xy.w;
+                hits[u] = hit;
+                any[u] = __ballot_sync(0xffffffffu, hit);
+            }
+            if ((any[0] | any[1]) == 0u) continue;
             float total;
             int slot;
             bool ok;
-            warp_multi_reduce<NV>(v, lane, total, slot, ok);
+            float idf;
+            if (any[0] != 0u && any[1] != 0u) {
+                float v0[NV], v1[NV], v[2 * NV];
+                bwd_hit_values<C, INVD, NV>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0], v0);
+                bwd_hit_values<C, INVD, NV>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1], v1);
+#pragma unroll
+                for (int n = 0; n < NV; n++) {
+                    v[n] = v0[n];
+                    v[NV + n] = v1[n];
+                }
+                warp_multi_reduce<2 * NV>(v, lane, total, slot, ok);
+                const bool second = slot >= NV;
+                idf = second ? ids[1] : ids[0];
+                slot -= second ? NV : 0;
+            } else if (any[0] != 0u) {
+                float v[NV];
+                bwd_hit_values<C, INVD, NV>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0], v);
+                warp_multi_reduce<NV>(v, lane, total, slot, ok);
+                idf = ids[0];
+            } else {
+                float v[NV];
+                bwd_hit_values<C, INVD, NV>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1], v);
+                warp_multi_reduce<NV>(v, lane, total, slot, ok);
+                idf = ids[1];
+            }
             if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
-            if (ok) atomicAdd(grad_rec + (size_t)__float_as_uint(xy.z) * LG_REC + slot, total);
-          }
+            if (ok) atomicAdd(grad_rec + (size_t)__float_as_uint(idf) * LG_REC + slot, total);
         }
     }
 }
