@@ -37,16 +37,25 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     // launch is void and the host queues the tail of the forward again.
     if (counters[1] > capacity) return;
     // one staged entry = three float4: (mean.x, mean.y, -, 1/depth) (conic a, b, c, opacity) (colours, C <= 4), read
-    // as warp-wide broadcasts from a single base address
-    __shared__ float4 s_ent[BLEND_BATCH * 3];
+    // as warp-wide broadcasts from a single base address; entry BLEND_BATCH is a sentinel that never passes the alpha
+    // test (opacity 0) and pads the per-warp lists to a multiple of FWD_UNROLL
+    constexpr int ENT = 48;  // bytes per staged entry
+    __shared__ float4 s_ent[(BLEND_BATCH + 1) * 3];
     __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
-    __shared__ lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH]; // per warp: compacted slots of the entries it must evaluate
+    // per warp: byte offsets into s_ent of the entries it must evaluate, FWD_UNROLL of them fetched by one load
+    __shared__ __align__(8) lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH + 4];
     __shared__ uint32_t s_neff;
+    static_assert(FWD_UNROLL == 4, "the list is read four offsets at a time");
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = tile_order[blockIdx.x];  // heaviest tiles first
     const uint32_t tile_x = tile % (uint32_t)grid_x, tile_y = tile / (uint32_t)grid_x;
-    if (tid == 0) s_neff = 0;
+    if (tid == 0) {
+        s_neff = 0;
+        s_ent[BLEND_BATCH * 3 + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        s_ent[BLEND_BATCH * 3 + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // opacity 0: alpha = 0 < 1/255
+        s_ent[BLEND_BATCH * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
@@ -65,6 +74,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
 #pragma unroll
     for (int c = 0; c < C; c++) acc[c] = 0.0f;
     float acc_invd = 0.0f;
+    const char* const ent_base = reinterpret_cast<const char*>(s_ent);
 
     for (int i = 0; i < rounds; i++, to_do -= BLEND_BATCH) {
         if (__syncthreads_count(done) == LG_TILE_PIX) break;
@@ -91,51 +101,65 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
         __syncthreads();
         const int batch = min(BLEND_BATCH, to_do);
         // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)
-        const int cnt = lg_compact_patch_list(s_mask, s_list[warp], warp, lane, 0, batch);
+        int cnt = 0;
+        {
+            lg_slot_t* list_w = s_list[warp];
+            const unsigned lt = (1u << lane) - 1u;
+            for (int base = 0; base < batch; base += 32) {
+                const int slot = base + (int)lane;
+                const bool bit = slot < batch && ((s_mask[slot] >> warp) & 1u);
+                const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)(slot * ENT);
+                cnt += __popc(bal);
+            }
+            if (lane < 3) list_w[cnt + lane] = (lg_slot_t)(BLEND_BATCH * ENT);
+            __syncwarp();
+        }
         const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
-        // Two list entries per trip: their power / exp / alpha chains are independent (only T couples the entries of
-        // a pixel), so evaluating both before applying either doubles the instruction-level parallelism of the loop
-        // and halves its overhead.  The decisions are the reference's, in the reference's order (forward.cu:349-381).
-        for (int k = 0; !done && k < cnt; k += FWD_UNROLL) {
-            int js[FWD_UNROLL];
-            float4 xys[FWD_UNROLL];
-            float alphas[FWD_UNROLL];
+        // Four list entries per trip: their power / exp / alpha chains are independent (only T couples the entries of
+        // a pixel), so all are evaluated before any is applied.  The decisions are the reference's, in the reference's
+        // order (forward.cu:349-381), applied without branches: an entry that does not pass, or a pixel that is done,
+        // blends with alpha = 0, which leaves T and the accumulators bit-for-bit unchanged (T * (1 - 0) = T,
+        // fma(T, 0 * f, acc) = acc), and since T never drops below 1e-4 such a step cannot trigger the stop test.
+        int last_off = -1;  // byte offset of the last entry of this batch that contributed to this pixel
+        for (int k = 0; k < cnt; k += FWD_UNROLL) {
+            const uint2 offs = *reinterpret_cast<const uint2*>(&s_list[warp][k]);
+            const int offv[FWD_UNROLL] = {(int)(offs.x & 0xffffu), (int)(offs.x >> 16), (int)(offs.y & 0xffffu),
+                                          (int)(offs.y >> 16)};
+            float invds[FWD_UNROLL], alphas[FWD_UNROLL];
             bool pass[FWD_UNROLL];
 #pragma unroll
             for (int u = 0; u < FWD_UNROLL; u++) {
-                const bool has = k + u < cnt;
-                const int j = s_list[warp][has ? k + u : k];
-                const float4 xy = s_ent[j * 3 + 0];
-                const float4 co = s_ent[j * 3 + 1];
+                const float4 xy = *reinterpret_cast<const float4*>(ent_base + offv[u]);
+                const float4 co = *reinterpret_cast<const float4*>(ent_base + offv[u] + 16);
                 const float dx = F_SUB(xy.x, pixf_x), dy = F_SUB(xy.y, pixf_y);
                 // power = -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy, reference contraction order
                 const float q = F_FMA(dx, F_MUL(dx, co.x), F_MUL(dy, F_MUL(dy, co.z)));
                 const float power = F_FMA(q, -0.5f, -F_MUL(dy, F_MUL(dx, co.y)));  // reference SASS: FFMA(q, -0.5, -m)
                 const float alpha = fminf(F_MUL(co.w, expf(power)), 0.99f);
-                js[u] = j;
-                xys[u] = xy;
+                invds[u] = xy.w;
                 alphas[u] = alpha;
-                pass[u] = has && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                pass[u] = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
             }
 #pragma unroll
             for (int u = 0; u < FWD_UNROLL; u++) {
-                if (pass[u] && !done) {
-                    const float alpha = alphas[u];
-                    const float test_T = F_MUL(T, F_SUB(1.0f, alpha));
-                    if (test_T < 0.0001f) {
-                        done = true;
-                    } else {
-                        const float4 f = s_ent[js[u] * 3 + 2];
-                        const float fv[4] = {f.x, f.y, f.z, f.w};
+                const bool live = pass[u] && !done;
+                const float a = live ? alphas[u] : 0.0f;
+                const float test_T = F_MUL(T, F_SUB(1.0f, a));
+                const bool stop = test_T < 0.0001f;  // only a live step can get here: T >= 1e-4 at all times
+                done = done || stop;
+                const float a2 = stop ? 0.0f : a;
+                const float4 f = *reinterpret_cast<const float4*>(ent_base + offv[u] + 32);
+                const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-                        for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(alpha, fv[c]), acc[c]);
-                        acc_invd = F_FMA(T, F_MUL(alpha, xys[u].w), acc_invd);
-                        T = test_T;
-                        last_contributor = batch_base + (uint32_t)js[u] + 1u;  // 1-based list position (forward.cu:345,381)
-                    }
-                }
+                for (int c = 0; c < C; c++) acc[c] = F_FMA(T, F_MUL(a2, fv[c]), acc[c]);
+                acc_invd = F_FMA(T, F_MUL(a2, invds[u]), acc_invd);
+                T = stop ? T : test_T;
+                last_off = (live && !stop) ? offv[u] : last_off;  // 1-based list position below (forward.cu:345,381)
             }
+            if (__all_sync(0xffffffffu, done)) break;
         }
+        if (last_off >= 0) last_contributor = batch_base + (uint32_t)last_off / (uint32_t)ENT + 1u;
     }
 
     // the backward's launch order key: how deep into the list this tile's pixels reached

@@ -70,10 +70,10 @@ def test_baseline_config_full_size_vs_reference(name):
     assert float((ours["invdepth"] - ref["invdepth"]).abs().max()) <= IMG_ATOL
     R, n_vis = ours["num_rendered"], int(vis.sum())
     for k in list(ours):
-        if k not in ("radii", "num_rendered", "geom", "binning", "img", "C", "M"):
+        if k not in ("radii", "num_rendered", "binning_capacity", "geom", "binning", "img", "C", "M"):
             del ours[k]
     for k in list(ref):
-        if k not in ("radii", "num_rendered", "geom", "binning", "img", "C", "M"):
+        if k not in ("radii", "num_rendered", "binning_capacity", "geom", "binning", "img", "C", "M"):
             del ref[k]
     torch.cuda.empty_cache()
     gen = torch.Generator(device="cuda").manual_seed(3)
