@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, uint32_t* __rest
         counters[4] = 0;          // tile-sort overflow / error word
     }
     __syncthreads();
+    if (tid == 0) counters[5] = s_max;  // longest list: tells the large-list sort launch whether it has any work
     const float scale = 1023.0f / (float)s_max;
     for (int t = tid; t < T; t += 1024) atomicAdd(&s_cnt[1023 - min((int)((float)(ranges[t].y - ranges[t].x) * scale), 1023)], 1u);
     __syncthreads();
@@ -610,6 +611,7 @@ __global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_
     TsSmem<THREADS>& s = *reinterpret_cast<TsSmem<THREADS>*>(ts_smem_raw);
     if (counters[1] > capacity) return;
     constexpr uint32_t SMALL_CAP = TsSmem<256>::CAP;  // what the 256-thread blocks take (two halves + merge)
+    if (LARGE && counters[5] <= SMALL_CAP) return;    // no list for this launch (the usual case): nothing to walk
     // LARGE: a few persistent blocks walk the launch order and pick out the long lists (empty 1024-thread blocks with
     // 82 KB of shared memory cost ~6 us per wave to schedule, so one block per tile is not an option here)
     for (uint32_t slot = blockIdx.x; slot < (uint32_t)T; slot += gridDim.x) {

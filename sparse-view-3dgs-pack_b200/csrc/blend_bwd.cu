@@ -126,14 +126,16 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec,
-    const uint32_t* __restrict__ tile_order) {
+    const uint32_t* __restrict__ tile_order, const uint8_t* __restrict__ entry_masks) {
     constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
     constexpr int ENT = 48;                     // bytes per staged entry
     // one staged entry = three float4: (mean.x, mean.y, Gaussian id, 1/depth) (conic a, b, c, opacity) (colours, C <= 4),
     // read as warp-wide broadcasts from a single base address; entry BWD_BATCH is a sentinel that can never hit
     // (opacity 0), which pads odd-length lists
     __shared__ float4 s_ent[(BWD_BATCH + 1) * 3];
-    __shared__ uint8_t s_mask[BWD_BATCH];                        // per staged entry: which of the 8 patches it can touch
+    // per 32 staged entries and patch: which of them can touch the patch at all (ballots of the staging warps over the
+    // mask bytes the forward pass left per list entry)
+    __shared__ uint32_t s_reach[BWD_BATCH / 32][LG_TILE_PIX / 32];
     __shared__ __align__(4) lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH + 2];  // per warp: byte offsets into s_ent
     __shared__ uint32_t s_max;
 
@@ -144,7 +146,6 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
-    const float tile_x0 = (float)(tile_x * LG_TILE_X), tile_y0 = (float)(tile_y * LG_TILE_Y);
     const uint2 range = ranges[tile];
 
     const float T_final = inside ? final_Ts[pix_id] : 0.0f;
@@ -190,10 +191,11 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
             const uint32_t progress = batch_base + slot;
             unsigned mask = 0;
             if (progress < n_eff) {
-                const uint32_t id = point_list[range.x + (n_eff - 1u - progress)];
+                const uint32_t pos = range.x + (n_eff - 1u - progress);
+                const uint32_t id = point_list[pos];
+                mask = entry_masks[pos];
                 const float2 m = means2D[id];
                 const float4 cq = conic_opacity[id];
-                mask = lg_patch_mask(m.x, m.y, cq, tile_x0, tile_y0);
                 float fv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int c = 0; c < C; c++) fv[c] = colors[(size_t)id * C + c];
@@ -201,7 +203,13 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
                 s_ent[slot * 3 + 1] = cq;
                 s_ent[slot * 3 + 2] = make_float4(fv[0], fv[1], fv[2], fv[3]);
             }
-            s_mask[slot] = (uint8_t)mask;
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < LG_TILE_PIX / 32; b++) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (mask >> b) & 1u);
+                word = lane == (unsigned)b ? bal : word;
+            }
+            if (lane < LG_TILE_PIX / 32) s_reach[slot >> 5][lane] = word;
         }
         __syncthreads();
         const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - batch_base);
@@ -210,19 +218,26 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
         const int first = (int)max((long long)n_eff - (long long)warp_max - (long long)batch_base, 0ll);
         if (first >= batch) continue;
         // compacted list of this warp's reachable entries as byte offsets into s_ent, padded to an even length
+        // (words of chunks past the end of the list are zero: the staging loop covers all BWD_BATCH slots)
         int cnt = 0;
         {
-            lg_slot_t* list_w = s_list[warp];
+            const uint32_t list_addr = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
             const unsigned lt = (1u << lane) - 1u;
-            for (int base = first & ~31; base < batch; base += 32) {
-                const int slot = base + (int)lane;
-                const bool bit = slot >= first && slot < batch && ((s_mask[slot] >> warp) & 1u);
-                const unsigned bal = __ballot_sync(0xffffffffu, bit);
-                if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)(slot * ENT);
+            const uint32_t my_off = lane * ENT;
+#pragma unroll
+            for (int c = 0; c < BWD_BATCH / 32; c++) {
+                const int drop = min(max(first - c * 32, 0), 32);  // leading slots of this chunk behind `first`
+                const uint32_t bal = s_reach[c][warp] & (uint32_t)(0xffffffffull << drop);
+                if ((bal >> lane) & 1u)
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)(cnt + __popc(bal & lt))),
+                                 "h"((unsigned short)(my_off + c * 32 * ENT)) : "memory");
                 cnt += __popc(bal);
             }
-            if (lane == 0) list_w[cnt] = (lg_slot_t)(BWD_BATCH * ENT);
+            if (lane == 0)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)cnt),
+                             "h"((unsigned short)(BWD_BATCH * ENT)) : "memory");
             __syncwarp();
+            cnt = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);  // same in every lane; tells the compiler so
         }
         // this pixel is behind entry j of the batch  <=>  rel = n_eff-1-(batch_base+j) < last_contributor
         //                                           <=>  j*ENT > ENT * (n_eff-1-batch_base-last_contributor)
@@ -297,7 +312,8 @@ int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, co
 #define LG_LAUNCH_BWD(CH, INVD)                                                                                    \
     blend_backward_kernel<CH, INVD><<<grid, block, 0, stream>>>(                                                     \
         img.ranges, b.point_list, W, H, gx, background, g.means2D, g.conic_opacity, features, g.depths,              \
-        img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch, img.tile_order_bwd)
+        img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch, img.tile_order_bwd,                  \
+        reinterpret_cast<const uint8_t*>(b.pairs))
     const bool invd = dL_dinvdepth_pix != nullptr;
     switch (C) {
         case 1: if (invd) LG_LAUNCH_BWD(1, true); else LG_LAUNCH_BWD(1, false); break;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth,
     const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff, uint32_t* __restrict__ counters,
-    uint32_t capacity, uint32_t* __restrict__ tile_order_bwd) {
+    uint32_t capacity, uint32_t* __restrict__ tile_order_bwd, uint8_t* __restrict__ entry_masks) {
     // The list was only built if it fits the binning buffer the caller sized speculatively (abi.cu); otherwise this
     // launch is void and the host queues the tail of the forward again.
     if (counters[1] > capacity) return;
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     // test (opacity 0) and pads the per-warp lists to a multiple of FWD_UNROLL
     constexpr int ENT = 48;  // bytes per staged entry
     __shared__ float4 s_ent[(BLEND_BATCH + 1) * 3];
-    __shared__ uint8_t s_mask[BLEND_BATCH];                   // per staged entry: which of the 8 patches it can touch
+    // per 32 staged entries and patch: which of them can touch the patch at all (ballots of the staging warps)
+    __shared__ uint32_t s_reach[BLEND_BATCH / 32][LG_TILE_PIX / 32];
     // per warp: byte offsets into s_ent of the entries it must evaluate, FWD_UNROLL of them fetched by one load
     __shared__ __align__(8) lg_slot_t s_list[LG_TILE_PIX / 32][BLEND_BATCH + 4];
     __shared__ uint32_t s_neff;
@@ -96,24 +97,38 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
                 s_ent[slot * 3 + 1] = co;
                 s_ent[slot * 3 + 2] = make_float4(fv[0], fv[1], fv[2], fv[3]);
             }
-            s_mask[slot] = (uint8_t)mask;
+            // the staging warp votes once per patch; lane b keeps the word of patch b.  The mask byte also goes to
+            // global memory for the backward pass, which stages the same entries (it never goes past a batch staged here)
+            if (range.x + progress < range.y) entry_masks[range.x + progress] = (uint8_t)mask;
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < LG_TILE_PIX / 32; b++) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (mask >> b) & 1u);
+                word = lane == (unsigned)b ? bal : word;
+            }
+            if (lane < LG_TILE_PIX / 32) s_reach[slot >> 5][lane] = word;
         }
         __syncthreads();
-        const int batch = min(BLEND_BATCH, to_do);
         // ---- each warp keeps only the entries that can reach its 8x4 patch (order preserved)
+        // (words of chunks past the end of the list are zero: the staging loop covers all BLEND_BATCH slots)
         int cnt = 0;
         {
-            lg_slot_t* list_w = s_list[warp];
+            const uint32_t list_addr = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
             const unsigned lt = (1u << lane) - 1u;
-            for (int base = 0; base < batch; base += 32) {
-                const int slot = base + (int)lane;
-                const bool bit = slot < batch && ((s_mask[slot] >> warp) & 1u);
-                const unsigned bal = __ballot_sync(0xffffffffu, bit);
-                if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)(slot * ENT);
+            const uint32_t my_off = lane * ENT;
+#pragma unroll
+            for (int c = 0; c < BLEND_BATCH / 32; c++) {
+                const uint32_t bal = s_reach[c][warp];
+                if ((bal >> lane) & 1u)
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)(cnt + __popc(bal & lt))),
+                                 "h"((unsigned short)(my_off + c * 32 * ENT)) : "memory");
                 cnt += __popc(bal);
             }
-            if (lane < 3) list_w[cnt + lane] = (lg_slot_t)(BLEND_BATCH * ENT);
+            if (lane < 3)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)(cnt + (int)lane)),
+                             "h"((unsigned short)(BLEND_BATCH * ENT)) : "memory");
             __syncwarp();
+            cnt = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);  // same in every lane; tells the compiler so
         }
         const uint32_t batch_base = (uint32_t)i * BLEND_BATCH;
         // Four list entries per trip: their power / exp / alpha chains are independent (only T couples the entries of
@@ -254,7 +269,8 @@ int launch_blend_forward(int C, int W, int H, int capacity, const GeometryState&
                                                          features, g.conic_opacity, g.depths, img.accum_alpha,       \
                                                          img.n_contrib, background, out_color, out_invdepth,         \
                                                          img.tile_order, img.tile_neff, img.counters,                \
-                                                         (uint32_t)capacity, img.tile_order_bwd)
+                                                         (uint32_t)capacity, img.tile_order_bwd,                     \
+                                                         reinterpret_cast<uint8_t*>(b.pairs))
     switch (C) {
         case 1: LG_LAUNCH_FWD(1); break;
         case 2: LG_LAUNCH_FWD(2); break;

@@ -74,7 +74,8 @@ struct ImageState {
     uint32_t* tile_neff;       // T: entries that reached some pixel of the tile (max n_contrib), written by the forward
     uint32_t* tile_order_bwd;  // T: backward, by tile_neff
     uint32_t* counters;        // [1] num_rendered (total list length, written by the tile scan), [3] blend-forward
-                               // completion ticket (the last block derives the backward's launch order)
+                               // completion ticket (the last block derives the backward's launch order),
+                               // [4] tile-sort error word, [5] longest tile list (tile scan)
     // Per-tile binning counters, one 128-byte line per tile (atomics on one line serialise in its L2 slice: with the
     // counters packed, 3.6 M increments on 80 lines took 160 us; one line per tile spreads them over all slices).
     // word 0 = list length (counted by the preprocess kernel), word 1 = write cursor of the scatter step.
