@@ -28,6 +28,7 @@ against NCCL and the bit-identity of the replicas.  `image_loss` / `train_iterat
 The reference arm imports nothing of this repo's package: its process maps only the reference's own libraries.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -264,18 +265,36 @@ class Stepper:
         return self.last_loss
 
 
-def timed_loop(fn, steps, world, device):
+STEP_MS = {}   # label -> per-step device times of the last timed_loop with that label (diagnostic: median vs mean)
+
+
+def timed_loop(fn, steps, world, device, label=None):
+    """K steps between two CUDA events, barrier + synchronize on both sides, max over ranks.  The Python garbage
+    collector is parked for the duration (a generation-2 collection in the middle of an 80 ms region costs milliseconds;
+    a trainer does the same with gc.freeze()); one extra event per step records the per-step times for `label`."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(device)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(steps):
-        fn(i)
-    b.record()
-    torch.cuda.synchronize(device)
+    gc.collect()
+    gc.disable()
+    try:
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)] if label else None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            if marks:
+                marks[i].record()
+            fn(i)
+        if marks:
+            marks[steps].record()
+        b.record()
+        torch.cuda.synchronize(device)
+    finally:
+        gc.enable()
     if world > 1:
         dist.barrier()
+    if marks:
+        STEP_MS[label] = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
     ms = torch.tensor([a.elapsed_time(b)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -606,6 +625,9 @@ def cfg5_section(device, rank, world, steps=3):
     return out
 
 
+STAGE_TIMING_EVERY = 3   # rasterizer calls per timed one (co-prime with the 4 views of a step: all positions sampled)
+
+
 def measure(stepper, cam_devs, host_cams, host_gts, K, W, world, rank, device, sampler=None, stage_timing=None,
             launch_counter=None):
     """(ms per resident step, ms per end-to-end step, kernels launched in the timed resident region) of one Stepper:
@@ -615,17 +637,21 @@ def measure(stepper, cam_devs, host_cams, host_gts, K, W, world, rank, device, s
     for i in range(W):
         stepper.step_resident(pick(i))
     if stage_timing is not None:
-        stage_timing(min(K * V, 256))
+        # CUDA events around the kernels of every third rasterizer call of the timed region (an event record between two
+        # kernels serialises the stream for ~3 us; ten per call on every call cost 3 % of the step)
+        stage_timing[0](min(K * V, 256), STAGE_TIMING_EVERY)
     if sampler is not None:
         sampler.mark()
     n0 = launch_counter() if launch_counter is not None else 0
-    ms_res = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device) / K
+    ms_res = timed_loop(lambda i: stepper.step_resident(pick(i)), K, world, device, stepper.mode + "/resident") / K
     launches = (launch_counter() - n0) if launch_counter is not None else None
+    if stage_timing is not None:
+        stage_timing[1]()   # read the ring and disarm it: the end-to-end loop below runs without stage events
     ring = lambda i: [((i * world + rank) * V + v) % len(host_cams) for v in range(V)]
     e2e_fn = lambda i: stepper.step_e2e([host_cams[j] for j in ring(i)], [host_gts[j] for j in ring(i)])
     for i in range(W):
         e2e_fn(i)
-    ms_e2e = timed_loop(e2e_fn, K, world, device) / K
+    ms_e2e = timed_loop(e2e_fn, K, world, device, stepper.mode + "/e2e") / K
     return ms_res, ms_e2e, launches
 
 
@@ -681,14 +707,19 @@ def main():
     stepper = Stepper("sinks", params, device, world)
     sampler = ClockSampler(local)
     sampler.start()
+    rows = []
+
+    def read_stage_rows():
+        n_timed = (K * V + STAGE_TIMING_EVERY - 1) // STAGE_TIMING_EVERY
+        rows.extend(_lib.read_stage_times(s) for s in range(min(n_timed, 256)))
+        _lib.stage_timing(0)
+
     ms_step, ms_e2e, launches = measure(stepper, cam_devs, host_cams, host_gts, K, W, world, rank, device, sampler,
-                                        _lib.stage_timing, _lib.lib.lg_launch_count)
+                                        (_lib.stage_timing, read_stage_rows), _lib.lib.lg_launch_count)
     clocks = sampler.stop()
     value = world * V / (ms_step / 1e3)
 
-    # ---- per-stage times recorded during the timed resident region
-    rows = [_lib.read_stage_times(s) for s in range(min(K * V, 256))]
-    _lib.stage_timing(0)
+    # ---- per-stage times recorded during the timed resident region (rows)
     mean_ms = {k: float(np.mean([r[k] for r in rows if r[k] >= 0])) for k in _lib.STAGES}
     import diff_gaussian_rasterization as dgr
     seen = []   # work terms of the metric camera (step 0's view on rank 0)
@@ -749,7 +780,9 @@ def main():
                 break
         except Exception:
             pass
-    roofline.update({"kernel": dom, "traffic": traffic, "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
+    roofline.update({"kernel": dom, "traffic": traffic,
+                     "timing": "CUDA events on the launching stream around this kernel in every %d-th rasterizer call of "
+                               "the timed region (mean of %d launches)" % (STAGE_TIMING_EVERY, len(rows)), "share_of_step": round(mean_ms[dom] * V / ms_step, 3),
                      "peak_source": hbm_src if roofline["bound"] == "hbm" else
                      "FFMA rate measured on this box by csrc/microbench.cu (lg_simt_peaks) at the start of this run; "
                      "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s" % FP32_SIMT_NOMINAL_TFLOPS,
@@ -779,6 +812,9 @@ def main():
                    "l2_policy": "inputs larger than L2 (236 MB of Gaussian parameters + 72 MB of binning state per view)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "stages": stages,
     }
+    # diagnostic only: per-step device times of the two timed regions (a mean far above the median = a host hiccup)
+    line["step_ms"] = {k: {"median": round(float(np.median(v)), 4), "min": round(min(v), 4), "max": round(max(v), 4)}
+                       for k, v in STEP_MS.items()}
     if exchange is not None:
         line["exchange"] = exchange
     if world == 1:
@@ -833,7 +869,8 @@ def reference_arm(args, K, W, local):
     host_cams, host_gts = host_inputs(cams)
     stepper = Stepper(mode, params, device, 1)
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("BENCH_NO_SAMPLER"):   # debugging aid only: the driver's runs always sample
+        sampler.start()
     ms_step, ms_e2e, _ = measure(stepper, cam_devs, host_cams, host_gts, K, W, 1, 0, device, sampler)
     clocks = sampler.stop()
     del stepper, params

@@ -238,6 +238,9 @@ unsigned long long lg_launch_count(void);
  * G warp-instructions/s, [4] SHFL.BFLY G warp-instructions/s, [5] integer ALU (add / logic) G warp-instructions/s. */
 int lg_simt_peaks(float* peaks_out, int n, void* stream);
 int lg_stage_timing_enable(int slots);
+/* time only one rasterizer call in `every` (default 1): an event record between two kernels costs ~3 us of stream
+ * serialisation, ten per call; sampling keeps the measurement inside a timed region without paying that on every call */
+int lg_stage_timing_sample(int every);
 int lg_stage_timing_read(int slot, float* ms_out, int n);
 
 /* Replaces SimpleKNN::knn (KNN/simple_knn.cu:186-222) as bound by distCUDA2 (KNN/spatial.cu:16-26):

@@ -85,18 +85,24 @@ void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 #define LG_TIMING_SLOTS 256
 static int g_timing_slots = 0;
 static int g_slot = -1;
+static int g_timing_every = 1;    // time one forward(+backward) call in `every` (lg_stage_timing_sample)
+static long long g_timing_calls = 0;
+static bool g_timing_active = false;
 static cudaEvent_t g_ev[LG_TIMING_SLOTS][ST_COUNT][2];
 static bool g_ev_used[LG_TIMING_SLOTS][ST_COUNT];
 void stage_begin(int stage, cudaStream_t stream) {
     if (g_timing_slots <= 0) return;
     if (stage == ST_PREPROCESS) {
-        g_slot = (g_slot + 1) % g_timing_slots;
-        for (int s = 0; s < ST_COUNT; s++) g_ev_used[g_slot][s] = false;
+        g_timing_active = (g_timing_calls++ % g_timing_every) == 0;
+        if (g_timing_active) {
+            g_slot = (g_slot + 1) % g_timing_slots;
+            for (int s = 0; s < ST_COUNT; s++) g_ev_used[g_slot][s] = false;
+        }
     }
-    if (g_slot >= 0) cudaEventRecord(g_ev[g_slot][stage][0], stream);
+    if (g_timing_active && g_slot >= 0) cudaEventRecord(g_ev[g_slot][stage][0], stream);
 }
 void stage_end(int stage, cudaStream_t stream) {
-    if (g_timing_slots <= 0 || g_slot < 0) return;
+    if (g_timing_slots <= 0 || g_slot < 0 || !g_timing_active) return;
     cudaEventRecord(g_ev[g_slot][stage][1], stream);
     g_ev_used[g_slot][stage] = true;
 }
@@ -367,12 +373,19 @@ int lg_stage_timing_enable(int slots) {
             for (int k = 0; k < 2; k++) cudaEventDestroy(lg::g_ev[i][s][k]);
     lg::g_timing_slots = 0;
     lg::g_slot = -1;
+    lg::g_timing_calls = 0;
+    lg::g_timing_active = false;
     for (int i = 0; i < slots; i++)
         for (int s = 0; s < ST_COUNT; s++) {
             for (int k = 0; k < 2; k++) LG_CUDA(cudaEventCreate(&lg::g_ev[i][s][k]));
             lg::g_ev_used[i][s] = false;
         }
     lg::g_timing_slots = slots;
+    return LG_OK;
+}
+
+int lg_stage_timing_sample(int every) {
+    lg::g_timing_every = every < 1 ? 1 : every;
     return LG_OK;
 }
 

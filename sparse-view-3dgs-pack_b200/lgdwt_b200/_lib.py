@@ -142,6 +142,8 @@ def _load():
     lib.lg_launch_count.restype = ctypes.c_ulonglong
     lib.lg_stage_timing_enable.restype = i
     lib.lg_stage_timing_enable.argtypes = [i]
+    lib.lg_stage_timing_sample.restype = i
+    lib.lg_stage_timing_sample.argtypes = [i]
     lib.lg_stage_timing_read.restype = i
     lib.lg_stage_timing_read.argtypes = [i, ctypes.POINTER(f), i]
     lib.lg_simt_peaks.restype = i
@@ -175,8 +177,9 @@ def stream_ptr(device=None):
 STAGES = ("preprocess", "binning", "blend_forward", "blend_backward", "preprocess_backward")
 
 
-def stage_timing(slots):
-    """arm (slots > 0) or disarm (0) the per-stage CUDA-event ring"""
+def stage_timing(slots, every=1):
+    """arm (slots > 0) or disarm (0) the per-stage CUDA-event ring; `every` = time one rasterizer call in that many"""
+    check(lib.lg_stage_timing_sample(int(every)))
     check(lib.lg_stage_timing_enable(int(slots)))
 
 
