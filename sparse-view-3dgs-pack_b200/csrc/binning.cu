@@ -137,11 +137,19 @@ __global__ void __launch_bounds__(SCATTER_BLOCK) scatter_pairs_kernel(int P, con
     const uint32_t n = (x1 - x0) * (y1 - y0);
     if (n > 0) key = __float_as_uint(depths[idx]);
     if (n > 0 && n <= SCATTER_COOP) {
-        for (uint32_t y = y0; y < y1; y++)
-            for (uint32_t x = x0; x < x1; x++) {
-                const uint32_t slot = atomicAdd(&tile_ctr[(size_t)(y * (uint32_t)grid_x + x) * LG_CTR_STRIDE + 1], 1u);
-                pairs[slot] = make_uint2(key, (uint32_t)idx);
-            }
+        // all of the rectangle's cursor atomics are issued before the first result is used: up to SCATTER_COOP L2 round
+        // trips in flight per thread instead of one after the other
+        uint32_t slot[SCATTER_COOP];
+        uint32_t x = x0, y = y0;
+#pragma unroll
+        for (int k = 0; k < SCATTER_COOP; k++) {
+            slot[k] = 0xffffffffu;
+            if ((uint32_t)k < n) slot[k] = atomicAdd(&tile_ctr[(size_t)(y * (uint32_t)grid_x + x) * LG_CTR_STRIDE + 1], 1u);
+            if (++x == x1) { x = x0; y++; }
+        }
+#pragma unroll
+        for (int k = 0; k < SCATTER_COOP; k++)
+            if ((uint32_t)k < n) pairs[slot[k]] = make_uint2(key, (uint32_t)idx);
     }
     unsigned big = __ballot_sync(0xffffffffu, n > SCATTER_COOP);
     while (big) {
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(SCATTER_AGG_BLOCK) scatter_pairs_agg_kernel(
 
 // ------------------------------------------------------------------------------------------------ 4. SORT
 #ifndef TS_MIN_BLOCKS
-#define TS_MIN_BLOCKS 3
+#define TS_MIN_BLOCKS 4
 #endif
 constexpr int TS_RADIX = 256;
 constexpr int TS_MAX_IPT = 16;
@@ -246,8 +254,11 @@ template <int THREADS>
 struct TsSmem {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int MAXIPT = THREADS >= 1024 ? 8 : TS_MAX_IPT;  // entries per thread held in registers
-    static constexpr int HALF = THREADS * MAXIPT;                    // longest list sorted in one go
-    static constexpr int CAP = THREADS >= 1024 ? HALF : 2 * HALF;    // 256 threads: two sorted halves + a merge
+    static constexpr int HALF = THREADS * MAXIPT;                    // longest list sorted in one go (= items held)
+    // longest list the block takes: 256 threads sort two halves one after the other — the first goes back to global
+    // memory sorted, the second stays in shared memory — and merge them on the way out.  Holding both halves in shared
+    // memory (64 KB of items) limited the kernel to 2 blocks per SM; 32 KB gives 3 (then registers limit).
+    static constexpr int CAP = THREADS >= 1024 ? HALF : 2 * HALF;
     uint32_t warp_hist[WARPS][TS_RADIX];  // per warp and digit: running count, then exclusive prefix over warps
     uint32_t excl[TS_RADIX];              // per digit: first slot inside the chunk
     uint32_t base[TS_RADIX];              // multi-chunk passes: running global offset of every digit
@@ -255,7 +266,7 @@ struct TsSmem {
     uint32_t red[8];                      // [0] OR, [1] AND of the keys, [2] full-sort fallback, [3] min, [4] max, [5] #groups
     uint32_t grp_start[TS_MAX_GROUPS];    // long groups left to the whole block (ts_fix_groups)
     uint32_t grp_len[TS_MAX_GROUPS];
-    uint2 items[CAP];
+    uint2 items[HALF];
 };
 
 template <int SEL>
@@ -494,14 +505,16 @@ __device__ __noinline__ void ts_sort_in_smem(TsSmem<THREADS>& s, uint2* items, c
 }
 
 // Lists of HALF < n <= 2 * HALF entries (256-thread blocks): the two halves of the scattered list are sorted one
-// after the other into the two halves of the shared item buffer and merged on the way out.  Every thread produces a
+// after the other; the first goes back, sorted, to the tile's slice of the second pair buffer (plain global loads and
+// stores of the same block, ordered by the block barrier; it stays in L2), the second remains in shared memory, and
+// the two are merged on the way out.  Every thread produces a
 // run of consecutive output slots: a merge-path binary search finds how many entries of each half precede its run,
 // then it merges serially (keys are (depth bits, id) pairs: distinct, so the merge is unambiguous).
 __device__ __forceinline__ bool ts_pair_less(const uint2& a, const uint2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
 
 template <int THREADS>
-__device__ __forceinline__ void ts_merge_out(const uint2* __restrict__ A, uint32_t nA, const uint2* __restrict__ B,
-                                             uint32_t nB, uint32_t* __restrict__ out) {
+__device__ __forceinline__ void ts_merge_out(const uint2* A, uint32_t nA, const uint2* B, uint32_t nB,
+                                             uint32_t* out) {
     const uint32_t n = nA + nB;
     const uint32_t per = (n + THREADS - 1) / THREADS;
     const uint32_t d0 = min(threadIdx.x * per, n), d1 = min(d0 + per, n);
@@ -645,13 +658,15 @@ __global__ void __launch_bounds__(THREADS, LARGE ? 1 : TS_MIN_BLOCKS) tile_sort_
             const uint32_t nA = n / 2, nB = n - nA;  // both <= HALF
             ts_sort_in_smem<THREADS, 16>(s, s.items, src, nA, nullptr, id_bits);
             __syncthreads();
+            uint2* sortedA = pairs_alt + range.x;   // this tile's slice of the second pair buffer (L2-resident)
+            for (uint32_t q = threadIdx.x; q < nA; q += THREADS) sortedA[q] = s.items[q];
             if (threadIdx.x == 0) {   // fresh reduction state for the second half
                 s.red[0] = 0u; s.red[1] = 0xffffffffu; s.red[2] = 0u; s.red[3] = 0xffffffffu; s.red[4] = 0u; s.red[5] = 0u;
             }
             __syncthreads();
-            ts_sort_in_smem<THREADS, 16>(s, s.items + HALF, src + nA, nB, nullptr, id_bits);
-            __syncthreads();
-            ts_merge_out<THREADS>(s.items, nA, s.items + HALF, nB, out);
+            ts_sort_in_smem<THREADS, 16>(s, s.items, src + nA, nB, nullptr, id_bits);
+            __syncthreads();   // also orders the block's global writes of sortedA before the reads below
+            ts_merge_out<THREADS>(sortedA, nA, s.items, nB, out);
             continue;
         }
         const uint32_t per_thread = (n + THREADS - 1) / THREADS;

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout -s KILL 400 python -m pytest tests/test_ops_gpu.py tests/test_trainer_gpu.py tests/test_rasterizer_vs_reference_gpu.py -x -q --timeout 300 > gpurun_out/r2_t9.log 2>&1
+timeout -s KILL 400 python -m pytest tests/test_ops_gpu.py tests/test_trainer_gpu.py tests/test_rasterizer_vs_reference_gpu.py tests/test_configs_gpu.py -x -q --timeout 300 > gpurun_out/r2_t9.log 2>&1
 tail -4 gpurun_out/r2_t9.log
 for L in ${LIBS:-liblgdwt_b200.so libv_nobulk.so}; do
 export LGDWT_LIBNAME=$L
