@@ -63,6 +63,7 @@ P_GAUSSIANS = 1_000_000
 WIDTH = HEIGHT = 800
 SH_DEGREE = 3
 N_CAMERAS = 8
+VIEW_STREAMS_DEFAULT = 1  # 2: consecutive views of a step alternate between two CUDA streams (Stepper.overlap)
 VIEWS_PER_RANK = 4  # views per rank per step (gradient accumulation); x 8 ranks = the 32-view batch of config 5
 FP32_SIMT_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # only a fallback: the FFMA peak is measured on the box
 
@@ -153,6 +154,12 @@ class Stepper:
         self.host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.loss_ready = [torch.cuda.Event() for _ in range(2)]
         self.e2e_steps, self.last_loss = 0, float("nan")
+        # view overlap (this repo's "sinks" arm only): consecutive views of a step alternate between two streams, so that
+        # the latency-bound head of view v+1 (preprocess, tile scan, scatter, tile sort) runs under the issue-bound
+        # blend backward of view v.  The backward kernels that add into the shared bucket stay in view order (each
+        # backward waits for the previous view's), so the step's result is the single-stream one bit for bit.
+        self.overlap = mode == "sinks" and env_int("LGDWT_VIEW_STREAMS", VIEW_STREAMS_DEFAULT) > 1
+        self.view_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if self.overlap else None
         # the flat gradient bucket (what a data-parallel step all-reduces): means3D 3 | shs 48 | opacity 1 | scales 3 | rot 4
         self.peer, self.peer_unavailable = None, ""
         if mode == "sinks" and world > 1:
@@ -220,9 +227,23 @@ class Stepper:
 
     def step_resident(self, cams):
         self.begin_step()
-        for v, cam in enumerate(cams):
-            color, radii, invd = self.render(cam, v == 0)
-            color.backward(self.dL)
+        if self.overlap:
+            main = torch.cuda.current_stream(self.device)
+            for s in self.view_streams:
+                s.wait_stream(main)
+            for v, cam in enumerate(cams):
+                s = self.view_streams[v % 2]
+                with torch.cuda.stream(s):
+                    color, radii, invd = self.render(cam, v == 0)
+                    if v > 0:  # bucket order: this view's backward after the previous view's
+                        s.wait_stream(self.view_streams[(v - 1) % 2])
+                    color.backward(self.dL)
+            for s in self.view_streams:
+                main.wait_stream(s)
+        else:
+            for v, cam in enumerate(cams):
+                color, radii, invd = self.render(cam, v == 0)
+                color.backward(self.dL)
         self.exchange()
 
     def step_e2e(self, host_cams, host_gts):
@@ -233,24 +254,34 @@ class Stepper:
         self.begin_step()
         main = torch.cuda.current_stream(self.device)
         total = torch.zeros((), device=self.device)
+        if self.overlap:
+            for s in self.view_streams:
+                s.wait_stream(main)
         for v, (host_cam, host_gt) in enumerate(zip(host_cams, host_gts)):
-            cam = dict(host_cam)
-            pk = host_cam["packed"].to(self.device, non_blocking=True)  # one 140-byte upload per view
-            cam["viewmatrix"], cam["projmatrix"], cam["campos"] = pk[:16].view(4, 4), pk[16:32].view(4, 4), pk[32:35]
-            gt_buf = self.dev_gt[self.e2e_steps % 2][v]
-            with torch.cuda.stream(self.copy_stream):
-                # double-buffered: the readers of this buffer belong to the step before the previous one, whose loss
-                # has been read back (so it has completed) before this step was started
-                gt_buf.copy_(host_gt, non_blocking=True)
-                self.copy_done[v].record(self.copy_stream)
-            color, radii, invd = self.render(cam, v == 0)
-            main.wait_event(self.copy_done[v])
-            if self.mode in ("sinks", "dropin"):   # this repo's public loss op; the reference arm keeps the stock torch expression
-                loss = self.l1(color, gt_buf)
-            else:
-                loss = (color - gt_buf).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
-            loss.backward()
-            total += loss.detach()
+            s = self.view_streams[v % 2] if self.overlap else main
+            with torch.cuda.stream(s):
+                cam = dict(host_cam)
+                pk = host_cam["packed"].to(self.device, non_blocking=True)  # one 140-byte upload per view
+                cam["viewmatrix"], cam["projmatrix"], cam["campos"] = pk[:16].view(4, 4), pk[16:32].view(4, 4), pk[32:35]
+                gt_buf = self.dev_gt[self.e2e_steps % 2][v]
+                with torch.cuda.stream(self.copy_stream):
+                    # double-buffered: the readers of this buffer belong to the step before the previous one, whose loss
+                    # has been read back (so it has completed) before this step was started
+                    gt_buf.copy_(host_gt, non_blocking=True)
+                    self.copy_done[v].record(self.copy_stream)
+                color, radii, invd = self.render(cam, v == 0)
+                s.wait_event(self.copy_done[v])
+                if self.mode in ("sinks", "dropin"):   # this repo's public loss op; the reference arm keeps the stock torch expression
+                    loss = self.l1(color, gt_buf)
+                else:
+                    loss = (color - gt_buf).abs().mean()      # l1_loss, LG/utils/loss_utils.py:40-41
+                if self.overlap and v > 0:  # bucket (and `total`) order: after the previous view's backward
+                    s.wait_stream(self.view_streams[(v - 1) % 2])
+                loss.backward()
+                total += loss.detach()
+        if self.overlap:
+            for s in self.view_streams:
+                main.wait_stream(s)
         self.exchange()
         # device -> host read of the step's loss: an asynchronous copy into pinned memory, waited for only after the NEXT
         # step has been queued (a trainer logs the loss one step late rather than draining the GPU every step; the

@@ -25,6 +25,7 @@ flat bucket (`GradSinks(raw_rot_norm=...)`), `lg_densify_stats`, `lg_adam_step_s
 protocol can be tested on CPU with the gloo backend (tests/test_host_cpu.py).
 """
 import ctypes
+import contextlib
 import math
 from typing import Callable, NamedTuple, Optional, Sequence
 
@@ -287,12 +288,14 @@ def default_render(act, cam, bg, sh_degree=3, antialiasing=False):
     return color.clamp(0, 1), radii, means2D
 
 
-def fused_render(g: FlatGaussians, cam, bg, accumulate, antialiasing=False, with_depth=False):
+def fused_render(g: FlatGaussians, cam, bg, accumulate, antialiasing=False, with_depth=False, act=None):
     """One view of the fused path: raw parameters -> lg_activate_forward -> rasterizer at the active SH degree; the
     backward adds the RAW-parameter gradients into g.grad.  Returns (image, radii, means2D[, invdepth]) like the
-    reference's render() (LG/gaussian_renderer/__init__.py:119-128)."""
+    reference's render() (LG/gaussian_renderer/__init__.py:119-128).  `act`: the result of an earlier g.activate() of
+    the same step (the parameters do not change between the views of a step)."""
     from diff_gaussian_rasterization import GaussianRasterizer
-    act = g.activate()
+    if act is None:
+        act = g.activate()
     means2D = torch.zeros((g.P, 3), dtype=torch.float32, device=g.device, requires_grad=True)
     color, radii, invdepth = GaussianRasterizer(_raster_settings(cam, bg, g.active_sh_degree, antialiasing))(
         means3D=act["means3D"], means2D=means2D, shs=act["shs"], colors_precomp=None, opacities=act["opacities"],
@@ -355,14 +358,23 @@ class ViewParallelTrainer:
                  group: Optional[dist.ProcessGroup] = None, densify: Optional[DensifyConfig] = None,
                  densify_fn: Optional[Callable] = None, stats_fn: Optional[Callable] = None,
                  reset_opacity_fn: Optional[Callable] = None, seed: int = 0, exchange: str = "nccl",
-                 schedule: Optional[TrainSchedule] = None):
+                 schedule: Optional[TrainSchedule] = None, view_streams: int = 1):
         """render_fn=None selects the fused CUDA path (`fused_render`); a custom render_fn(act, cam, bg) ->
         (image, radii[, viewspace_points]) runs through autograd leaves.  densify=None disables density control.
         exchange="nccl": all-reduce of the bucket + the same full Adam pass on every rank; exchange="peer": the
         fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory (lgdwt_b200.peer), falling back to
         "nccl" (with `peer_unavailable` saying why) when the ranks cannot map each other's memory.
         schedule: a TrainSchedule turns on what LG/train.py varies per iteration (active SH degree from 0, position
-        learning rate decay, depth-L1 weight); loss_fn may be a RunningMeanLoss (stateful DWT scale)."""
+        learning rate decay, depth-L1 weight); loss_fn may be a RunningMeanLoss (stateful DWT scale).
+        view_streams=2 (fused path): consecutive views of a step alternate between two CUDA streams, so that the
+        latency-bound head of view k+1 (activation is done once per step; preprocess, tile scan, scatter, tile sort)
+        runs under the issue-bound blend backward of view k.  Everything with state stays in view order — the loss
+        (running mean) waits for the previous view's loss, the backward (bucket, densification statistics) for the
+        previous view's backward — so a step computes exactly what the single-stream step computes."""
+        if view_streams not in (1, 2):
+            raise ValueError("view_streams must be 1 or 2")
+        self.view_streams = ([torch.cuda.Stream(device=gaussians.device) for _ in range(2)]
+                             if view_streams == 2 and render_fn is None and gaussians.data.is_cuda else None)
         self.g, self.adam, self.render_fn, self.loss_fn, self.group = gaussians, adam, render_fn, loss_fn, group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -435,31 +447,52 @@ class ViewParallelTrainer:
         if not fused or not mine:
             self.g.grad.zero_()
         depth_w = self.schedule.depth_l1_weight(self.iteration) if self.schedule is not None else 0.0
+        overlap = fused and self.view_streams is not None and len(mine) > 1
+        act, prev, prev_loss_done = None, None, None
+        if overlap:
+            main = torch.cuda.current_stream(self.g.device)
+            act = self.g.activate()
+            for s in self.view_streams:
+                s.wait_stream(main)
         for k, v in enumerate(mine):
-            target = depths[v] if depths is not None else None
-            invdepth = None
-            if fused:  # the first view of the step overwrites the bucket: no zero-fill pass
-                if target is not None and depth_w > 0.0:
-                    image, radii, viewspace, invdepth = fused_render(self.g, cams[v], bg, accumulate=k > 0, with_depth=True)
+            stream = self.view_streams[k % 2] if overlap else None
+            with (torch.cuda.stream(stream) if overlap else contextlib.nullcontext()):
+                target = depths[v] if depths is not None else None
+                invdepth = None
+                if fused:  # the first view of the step overwrites the bucket: no zero-fill pass
+                    if target is not None and depth_w > 0.0:
+                        image, radii, viewspace, invdepth = fused_render(self.g, cams[v], bg, accumulate=k > 0,
+                                                                         with_depth=True, act=act)
+                    else:
+                        image, radii, viewspace = fused_render(self.g, cams[v], bg, accumulate=k > 0, act=act)
+                    leaves = None
                 else:
-                    image, radii, viewspace = fused_render(self.g, cams[v], bg, accumulate=k > 0)
-                leaves = None
-            else:
-                leaves = self.g.leaves()
-                out = self.render_fn(self.g.activated(leaves), cams[v], bg)
-                image, radii = out[0], out[1]
-                viewspace = out[2] if len(out) > 2 else None
-                invdepth = out[3] if len(out) > 3 else None
-            if target is not None and depth_w > 0.0 and invdepth is not None:
-                loss = self.loss_fn(image, gts[v], invdepth=invdepth, depth_target=target, depth_weight=depth_w)
-            else:
-                loss = self.loss_fn(image, gts[v])
-            loss.backward()
-            if leaves is not None:
-                self.g.accumulate(leaves)
-            if self.densify_cfg is not None and self.iteration < self.densify_cfg.densify_until_iter:
-                self._add_stats(viewspace, radii)
-            total += loss.detach()
+                    leaves = self.g.leaves()
+                    out = self.render_fn(self.g.activated(leaves), cams[v], bg)
+                    image, radii = out[0], out[1]
+                    viewspace = out[2] if len(out) > 2 else None
+                    invdepth = out[3] if len(out) > 3 else None
+                if prev_loss_done is not None:  # a stateful loss (running mean) advances view by view
+                    stream.wait_event(prev_loss_done)
+                if target is not None and depth_w > 0.0 and invdepth is not None:
+                    loss = self.loss_fn(image, gts[v], invdepth=invdepth, depth_target=target, depth_weight=depth_w)
+                else:
+                    loss = self.loss_fn(image, gts[v])
+                if overlap:
+                    prev_loss_done = torch.cuda.Event()
+                    prev_loss_done.record(stream)
+                    if prev is not None:  # bucket / statistics / `total` order
+                        stream.wait_stream(prev)
+                loss.backward()
+                if leaves is not None:
+                    self.g.accumulate(leaves)
+                if self.densify_cfg is not None and self.iteration < self.densify_cfg.densify_until_iter:
+                    self._add_stats(viewspace, radii)
+                total += loss.detach()
+                prev = stream
+        if overlap:
+            for s in self.view_streams:
+                main.wait_stream(s)
         return total
 
     def reduce_gradients(self):

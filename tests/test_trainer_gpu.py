@@ -185,6 +185,33 @@ def test_trainer_single_gpu_with_density_control():
     assert float(torch.sigmoid(g.slab("opacity")).max()) < 0.05
 
 
+def test_two_stream_view_overlap_computes_the_single_stream_step():
+    """view_streams=2 (consecutive views of a step on alternating CUDA streams, the head of view k+1 under the blend
+    backward of view k) keeps the loss state, the bucket and the densification statistics in view order: six steps of
+    four views incl. the running-mean loss give the single-stream losses, parameters and statistics (to the run-to-run
+    spread of the backward's atomics)"""
+    results = []
+    for streams in (1, 2):
+        g, cams, gts = _small_training_set(P=25_000, n_views=4)
+        cfg = dp.DensifyConfig(densify_from_iter=100, densify_until_iter=200)  # statistics only, no edit
+        tr = dp.ViewParallelTrainer(g, loss_fn=dp.RunningMeanLoss(torch.device(dev)), densify=cfg, view_streams=streams)
+        assert (tr.view_streams is not None) == (streams == 2)
+        bg = torch.zeros(3, device=dev)
+        losses = [float(tr.step(cams, gts, bg)) for _ in range(6)]
+        torch.cuda.synchronize()
+        results.append((losses, g.data.clone(), g.grad.clone(), tr.stats.xyz_gradient_accum.clone(), tr.stats.denom.clone(),
+                        float(tr.loss_fn.running_mean)))
+    (l1, p1, g1, a1, d1, r1), (l2, p2, g2, a2, d2, r2) = results
+    np.testing.assert_allclose(l2, l1, rtol=2e-5)
+    assert abs(r1 - r2) <= 2e-5 * abs(r1)
+    assert torch.equal(d1, d2)
+    torch.testing.assert_close(a2, a1, rtol=1e-3, atol=1e-3 * float(a1.abs().max()))
+    assert float((g2 - g1).abs().max()) <= 1e-3 * float(g1.abs().max())
+    # Adam's sign-like first steps amplify last-bit gradient differences of near-zero gradients: compare the bulk
+    close = ((p2 - p1).abs() <= 1e-4 + 1e-4 * p1.abs()).float().mean()
+    assert float(close) >= 0.999, float(close)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink / PCIe peer access")
 def test_peer_exchange_two_gpus():
     """fused reduce-scatter + Adam + all-gather over peer memory == NCCL all-reduce + local Adam (tests/peer_worker.py)"""
