@@ -394,6 +394,30 @@ int lg_image_loss_combine(const float* photometric_out, const float* dwt_out, fl
 int lg_image_loss_backward_coefs(const float* coef, const float* g, float* out4, void* stream);
 int lg_image_loss_add(float* a, const float* b, long long n, void* stream);
 
+/* The same iteration loss (LG/train.py:128-202) entered ONCE per direction: lg_image_loss_forward = the photometric and
+ * wavelet forward kernels + lg_image_loss_combine; lg_image_loss_backward = the two gradient kernels, the second one
+ * adding in place, each scaling its coefficient by the upstream gradient g_up (device scalar) itself.
+ *   terms (device, 24 floats, written by the forward, read by the backward): [0] L1, [1] SSIM, [2..13] the out_losses of
+ *   lg_dwt_loss_forward, [14] loss, [15] base, [16..19] d(loss)/d(L1, SSIM, dwt, patch), [20..23] spare.
+ *   patch_mask / workspaces: as for the separate entry points; the photometric workspace, terms and patch_mask must be
+ *   kept until the backward.  The *_scaled forms are the two backward kernels with the upstream factor and (wavelet)
+ *   the accumulate switch exposed. */
+int lg_image_loss_forward(const float* pred, const float* gt, int C, int H, int W, const float* band_weights_host,
+                          int patch_size, double percentile, float patch_w_lh, float patch_w_hl, float* running_mean,
+                          float lambda_dssim, float patch_weight, int update_running_mean, float* terms,
+                          uint8_t* patch_mask, size_t patch_mask_bytes, char* photometric_workspace,
+                          size_t photometric_bytes, char* dwt_workspace, size_t dwt_bytes, int want_backward, void* stream);
+int lg_image_loss_backward(const float* pred, const float* gt, int C, int H, int W, const float* band_weights_host,
+                           int patch_size, float patch_w_lh, float patch_w_hl, const float* terms, const float* g_up,
+                           const uint8_t* patch_mask, const char* photometric_workspace, float* dL_dpred, void* stream);
+int lg_photometric_loss_backward_scaled(const float* pred, const float* gt, int C, int H, int W, const char* workspace,
+                                        const float* g_l1, const float* g_ssim, const float* g_up, float* dL_dpred,
+                                        void* stream);
+int lg_dwt_loss_backward_scaled(const float* pred, const float* gt, int C, int H, int W, const float* band_weights_host,
+                                int patch_size, float patch_w_lh, float patch_w_hl, const float* g_dwt_dev,
+                                const float* g_patch_dev, const float* g_up, const uint8_t* patch_mask,
+                                const float* out_losses, float* dL_dpred, int accumulate, void* stream);
+
 /* Single-level Haar analysis (the pytorch_wavelets.DWTForward(J=1,'symmetric','db1') call sites at
  * LG/utils/loss_utils.py:140-148).  x (N*C,H,W) -> ll (N*C,H2,W2), yh (N*C,3,H2,W2) with H2=(H+1)/2.
  * and its adjoint (for autograd through the compat module).                                              */

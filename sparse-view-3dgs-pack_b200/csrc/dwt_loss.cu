@@ -293,13 +293,15 @@ __global__ void __launch_bounds__(DWT_TB * DWT_TB) dwt_backward_kernel(const flo
                                                                        const float* __restrict__ g_patch_p,
                                                                        const uint8_t* __restrict__ mask,
                                                                        const float* __restrict__ out_losses,
+                                                                       const float* __restrict__ g_up, int accumulate,
                                                                        float* __restrict__ dpred) {
     const int H = a.H, W = a.W, C = a.C;
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2, H4 = (H2 + 1) / 2, W4 = (W2 + 1) / 2;
     const int tx = threadIdx.x % DWT_TB, ty = threadIdx.x / DWT_TB;
     const int j2 = blockIdx.x * DWT_TB + tx, i2 = blockIdx.y * DWT_TB + ty;
     if (i2 >= H4 || j2 >= W4) return;
-    const float g_dwt = g_dwt_p ? *g_dwt_p : 1.f, g_patch = g_patch_p ? *g_patch_p : 0.f;
+    const float up = g_up ? *g_up : 1.f;  // upstream gradient of the combined loss (device scalar)
+    const float g_dwt = (g_dwt_p ? *g_dwt_p : 1.f) * up, g_patch = (g_patch_p ? *g_patch_p : 0.f) * up;
     const float n1 = (float)C * H2 * W2, n2 = (float)C * H4 * W4;
     float k1[4], k2[4];
 #pragma unroll
@@ -367,13 +369,20 @@ __global__ void __launch_bounds__(DWT_TB * DWT_TB) dwt_backward_kernel(const flo
         for (int r = 0; r < 4; r++) {
             const int y = 4 * i2 + r;
             if (y >= H) continue;
+            // accumulate: the image already holds the photometric gradient (lg_image_loss_backward); sum = held + ours
             if (fast) {
-                *reinterpret_cast<float4*>(out + (size_t)y * W + 4 * j2) = make_float4(dx[r][0], dx[r][1], dx[r][2], dx[r][3]);
+                float4* o4 = reinterpret_cast<float4*>(out + (size_t)y * W + 4 * j2);
+                float4 v = make_float4(dx[r][0], dx[r][1], dx[r][2], dx[r][3]);
+                if (accumulate) {
+                    const float4 h = *o4;
+                    v = make_float4(h.x + v.x, h.y + v.y, h.z + v.z, h.w + v.w);
+                }
+                *o4 = v;
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int x = 4 * j2 + q;
-                    if (x < W) out[(size_t)y * W + x] = dx[r][q];
+                    if (x < W) out[(size_t)y * W + x] = accumulate ? out[(size_t)y * W + x] + dx[r][q] : dx[r][q];
                 }
             }
         }
@@ -498,6 +507,15 @@ extern "C" int lg_dwt_loss_backward(const float* pred, const float* gt, int C, i
                                     const float* band_weights_host, int patch_size, float patch_w_lh, float patch_w_hl,
                                     const float* g_dwt_dev, const float* g_patch_dev, const uint8_t* patch_mask,
                                     const float* out_losses, float* dL_dpred, void* stream_v) {
+    return lg_dwt_loss_backward_scaled(pred, gt, C, H, W, band_weights_host, patch_size, patch_w_lh, patch_w_hl, g_dwt_dev,
+                                       g_patch_dev, nullptr, patch_mask, out_losses, dL_dpred, 0, stream_v);
+}
+
+extern "C" int lg_dwt_loss_backward_scaled(const float* pred, const float* gt, int C, int H, int W,
+                                           const float* band_weights_host, int patch_size, float patch_w_lh,
+                                           float patch_w_hl, const float* g_dwt_dev, const float* g_patch_dev,
+                                           const float* g_up_dev, const uint8_t* patch_mask, const float* out_losses,
+                                           float* dL_dpred, int accumulate, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     int rc = dwt_check("lg_dwt_loss_backward", pred, gt, C, H, W, patch_size);
     if (rc != LG_OK) return rc;
@@ -519,7 +537,7 @@ extern "C" int lg_dwt_loss_backward(const float* pred, const float* gt, int C, i
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2, H4 = (H2 + 1) / 2, W4 = (W2 + 1) / 2;
     const dim3 grid((W4 + DWT_TB - 1) / DWT_TB, (H4 + DWT_TB - 1) / DWT_TB);
     dwt_backward_kernel<<<grid, DWT_TB * DWT_TB, 0, stream>>>(pred, gt, a, g_dwt_dev, g_patch_dev, patch_mask, out_losses,
-                                                              dL_dpred);
+                                                              g_up_dev, accumulate, dL_dpred);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }

@@ -166,3 +166,47 @@ extern "C" int lg_image_loss_add(float* a, const float* b, long long n, void* st
     LG_LAUNCH_CHECK(false, (cudaStream_t)stream_v);
     return LG_OK;
 }
+
+// The whole iteration loss in ONE library call each way (LG/train.py:128-202): the host enters the library once per
+// direction instead of seven times (at 3x800x800 the seven calls and their temporaries cost more host time than the
+// kernels take on the GPU).  `terms` (24 floats): [0:2] L1, SSIM | [2:14] lg_dwt_loss_forward's out_losses |
+// [14:16] loss, base | [16:20] d(loss)/d(L1, SSIM, dwt, patch) | [20:24] spare.
+extern "C" int lg_image_loss_forward(const float* pred, const float* gt, int C, int H, int W,
+                                     const float* band_weights_host, int patch_size, double percentile, float patch_w_lh,
+                                     float patch_w_hl, float* running_mean, float lambda_dssim, float patch_weight,
+                                     int update_running_mean, float* terms, uint8_t* patch_mask, size_t patch_mask_bytes,
+                                     char* photometric_workspace, size_t photometric_bytes, char* dwt_workspace,
+                                     size_t dwt_bytes, int want_backward, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (!terms || !running_mean) {
+        set_error("lg_image_loss_forward: null pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    LG_CUDA(cudaMemsetAsync(terms, 0, 24 * sizeof(float), stream));
+    if (patch_mask && patch_mask_bytes) LG_CUDA(cudaMemsetAsync(patch_mask, 0, patch_mask_bytes, stream));
+    int rc = lg_photometric_loss_forward(pred, gt, C, H, W, terms, photometric_workspace, photometric_bytes, want_backward,
+                                         stream_v);
+    if (rc != LG_OK) return rc;
+    rc = lg_dwt_loss_forward(pred, gt, C, H, W, band_weights_host, patch_size, percentile, patch_w_lh, patch_w_hl,
+                             terms + 2, patch_mask, dwt_workspace, dwt_bytes, stream_v);
+    if (rc != LG_OK) return rc;
+    return lg_image_loss_combine(terms, terms + 2, running_mean, lambda_dssim, patch_weight, update_running_mean,
+                                 terms + 14, terms + 16, stream_v);
+}
+
+// dL/dpred of the combined loss: the photometric kernel writes the image, the wavelet kernel adds its part in place;
+// both scale their coefficient (terms[16:20]) by the upstream gradient `g_up` (device scalar) themselves.
+extern "C" int lg_image_loss_backward(const float* pred, const float* gt, int C, int H, int W,
+                                      const float* band_weights_host, int patch_size, float patch_w_lh, float patch_w_hl,
+                                      const float* terms, const float* g_up, const uint8_t* patch_mask,
+                                      const char* photometric_workspace, float* dL_dpred, void* stream_v) {
+    if (!terms || !g_up) {
+        set_error("lg_image_loss_backward: null pointer");
+        return LG_ERR_INVALID_ARGUMENT;
+    }
+    int rc = lg_photometric_loss_backward_scaled(pred, gt, C, H, W, photometric_workspace, terms + 16, terms + 17, g_up,
+                                                 dL_dpred, stream_v);
+    if (rc != LG_OK) return rc;
+    return lg_dwt_loss_backward_scaled(pred, gt, C, H, W, band_weights_host, patch_size, patch_w_lh, patch_w_hl, terms + 18,
+                                       terms + 19, g_up, patch_mask, terms + 2, dL_dpred, 1, stream_v);
+}

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(PH_THREADS) photometric_backward_kernel(const 
                                                                           const float* __restrict__ dmaps,
                                                                           size_t plane_stride_maps,
                                                                           const float* __restrict__ g_l1,
-                                                                          const float* __restrict__ g_ssim, float inv_n,
+                                                                          const float* __restrict__ g_ssim,
+                                                                          const float* __restrict__ g_up, float inv_n,
                                                                           float* __restrict__ dL_dpred) {
     __shared__ float s_m[3][PH_SY][PH_SX + 1];
     __shared__ float s_h[3][PH_SY][PH_BX + 1];
@@ -181,8 +182,9 @@ __global__ void __launch_bounds__(PH_THREADS) photometric_backward_kernel(const 
         }
         const size_t o = pbase + (size_t)gy * W + gx;
         const float x = pred[o], y = gt[o];
-        const float gs = g_ssim ? *g_ssim * inv_n : 0.0f;
-        const float gl = g_l1 ? *g_l1 * inv_n : 0.0f;
+        const float up = g_up ? *g_up : 1.0f;  // upstream gradient of the combined loss (device scalar)
+        const float gs = g_ssim ? (*g_ssim * up) * inv_n : 0.0f;
+        const float gl = g_l1 ? (*g_l1 * up) * inv_n : 0.0f;
         const float d = x - y;
         const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
         dL_dpred[o] = gs * (m0 + 2.f * x * m1 + y * m2) + gl * sgn;
@@ -247,6 +249,14 @@ extern "C" int lg_photometric_loss_forward(const float* pred, const float* gt, i
 extern "C" int lg_photometric_loss_backward(const float* pred, const float* gt, int C, int H, int W,
                                             const char* workspace, const float* g_l1_dev, const float* g_ssim_dev,
                                             float* dL_dpred, void* stream_v) {
+    return lg_photometric_loss_backward_scaled(pred, gt, C, H, W, workspace, g_l1_dev, g_ssim_dev, nullptr, dL_dpred,
+                                               stream_v);
+}
+
+extern "C" int lg_photometric_loss_backward_scaled(const float* pred, const float* gt, int C, int H, int W,
+                                                   const char* workspace, const float* g_l1_dev,
+                                                   const float* g_ssim_dev, const float* g_up_dev, float* dL_dpred,
+                                                   void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (!pred || !gt || !workspace || !dL_dpred || C <= 0 || H <= 0 || W <= 0 || C > 65535) {
         set_error("lg_photometric_loss_backward: invalid arguments");
@@ -256,7 +266,7 @@ extern "C" int lg_photometric_loss_backward(const float* pred, const float* gt, 
     PhotoWorkspace w = PhotoWorkspace::from_chunk(p, C, H, W);
     const dim3 grid((W + PH_BX - 1) / PH_BX, (H + PH_BY - 1) / PH_BY, C);
     photometric_backward_kernel<<<grid, PH_THREADS, 0, stream>>>(pred, gt, H, W, w.dmaps, (size_t)C * H * W, g_l1_dev,
-                                                                 g_ssim_dev, (float)(1.0 / ((double)C * H * W)),
+                                                                 g_ssim_dev, g_up_dev, (float)(1.0 / ((double)C * H * W)),
                                                                  dL_dpred);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;

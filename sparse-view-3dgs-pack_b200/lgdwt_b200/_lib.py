@@ -133,6 +133,15 @@ def _load():
     lib.lg_image_loss_backward_coefs.argtypes = [_P, _P, _P, _P]
     lib.lg_image_loss_add.restype = i
     lib.lg_image_loss_add.argtypes = [_P, _P, ctypes.c_longlong, _P]
+    lib.lg_image_loss_forward.restype = i
+    lib.lg_image_loss_forward.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, ctypes.c_double, f, f, _P, f, f, i, _P,
+                                          _P, ctypes.c_size_t, _P, ctypes.c_size_t, _P, ctypes.c_size_t, i, _P]
+    lib.lg_image_loss_backward.restype = i
+    lib.lg_image_loss_backward.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, f, f, _P, _P, _P, _P, _P, _P]
+    lib.lg_photometric_loss_backward_scaled.restype = i
+    lib.lg_photometric_loss_backward_scaled.argtypes = [_P, _P, i, i, i, _P, _P, _P, _P, _P, _P]
+    lib.lg_dwt_loss_backward_scaled.restype = i
+    lib.lg_dwt_loss_backward_scaled.argtypes = [_P, _P, i, i, i, ctypes.POINTER(f), i, f, f, _P, _P, _P, _P, _P, _P, i, _P]
     lib.lg_haar_dwt2_forward.restype = i
     lib.lg_haar_dwt2_forward.argtypes = [_P, i, i, i, _P, _P, _P]
     lib.lg_haar_dwt2_backward.restype = i

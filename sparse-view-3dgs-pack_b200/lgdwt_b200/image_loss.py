@@ -5,9 +5,9 @@
     loss = base + scale * dwt + patch_weight * patch                     (:196-202)
 
 with dwt = the weighted 2-level global sub-band L1 (:131-164) and patch = the ELF-selected 128-px patch loss (:166-180).
-One autograd node: the photometric and wavelet forward kernels, a one-thread assembly kernel that also advances the
-running mean on the device (the reference does it on the host after an `.item()`), and in the backward the two
-gradient kernels plus one add.  The reference runs ~100 PyTorch launches and two autograd graphs for the same value.
+One autograd node and ONE library call per direction (lg_image_loss_forward / lg_image_loss_backward): the photometric
+and wavelet forward kernels, a one-thread assembly kernel that also advances the running mean on the device (the
+reference does it on the host after an `.item()`), and in the backward two gradient kernels, the second adding in place.  The reference runs ~100 PyTorch launches and two autograd graphs for the same value.
 """
 import ctypes
 
@@ -33,56 +33,47 @@ class _FusedImageLoss(torch.autograd.Function):
             raise RuntimeError("fused_image_loss: running_mean must be a float32 scalar tensor on the image's device")
         C, H, W = pred_c.shape
         dev = pred_c.device
-        lib, sp = _lib.lib, _lib.stream_ptr(dev)
+        lib = _lib.lib
         ps = int(cfg.patch_size) if cfg.patch_enable else 0
         L = (H // ps) * (W // ps) if ps > 0 else 0
-        # one allocation for the small device results: photometric 2 | dwt 12 | loss 2 | coefficients 4 | scaled 4
-        small = torch.zeros(24, dtype=torch.float32, device=dev)
-        ph_out, dwt_out, loss_out, coef, coef_g = small[0:2], small[2:14], small[14:16], small[16:20], small[20:24]
-        mask = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
+        # ONE library call (lg_image_loss_forward) and two allocations: the small device results
+        # [photometric 2 | dwt 12 | loss 2 | coefficients 4 | spare 4] followed by the ELF patch mask (zeroed by the
+        # library), and one block for both workspaces (the photometric part holds the derivative maps for the backward)
+        small_mask = torch.empty(96 + max(L, 1), dtype=torch.uint8, device=dev)
+        small, mask = small_mask[:96].view(torch.float32), small_mask[96:]
         ph_bytes = lib.lg_photometric_workspace_bytes(C, H, W)
         dwt_bytes = lib.lg_dwt_workspace_bytes(C, H, W, ps)
-        ph_ws = torch.empty(ph_bytes, dtype=torch.uint8, device=dev)
-        dwt_ws = torch.empty(dwt_bytes, dtype=torch.uint8, device=dev)
+        ph_pad = (ph_bytes + 255) // 256 * 256
+        ws = torch.empty(ph_pad + dwt_bytes, dtype=torch.uint8, device=dev)
         weights = (ctypes.c_float * 8)(*[float(w) for w in cfg.band_weights])
         need_grad = bool(ctx.needs_input_grad[0])
         with torch.cuda.device(dev):
-            _lib.check(lib.lg_photometric_loss_forward(pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, ph_out.data_ptr(),
-                                                       ph_ws.data_ptr(), ph_bytes, int(need_grad), sp), RuntimeError)
-            _lib.check(lib.lg_dwt_loss_forward(pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, weights, ps,
-                                               float(cfg.patch_percentile), float(cfg.patch_lh1_weight),
-                                               float(cfg.patch_hl1_weight), dwt_out.data_ptr(), mask.data_ptr(),
-                                               dwt_ws.data_ptr(), dwt_bytes, sp), RuntimeError)
-            _lib.check(lib.lg_image_loss_combine(ph_out.data_ptr(), dwt_out.data_ptr(), running_mean.data_ptr(),
-                                                 float(lambda_dssim), float(patch_weight), int(update_running_mean),
-                                                 loss_out.data_ptr(), coef.data_ptr(), sp), RuntimeError)
-        ctx.save_for_backward(pred_c, gt_c, small, mask, ph_ws)
+            _lib.check(lib.lg_image_loss_forward(
+                pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, weights, ps, float(cfg.patch_percentile),
+                float(cfg.patch_lh1_weight), float(cfg.patch_hl1_weight), running_mean.data_ptr(), float(lambda_dssim),
+                float(patch_weight), int(update_running_mean), small.data_ptr(), mask.data_ptr(), mask.numel(),
+                ws.data_ptr(), ph_bytes, ws.data_ptr() + ph_pad, dwt_bytes, int(need_grad), _lib.stream_ptr(dev)),
+                RuntimeError)
+        ctx.save_for_backward(pred_c, gt_c, small, mask, ws)
         ctx.cfg, ctx.ps, ctx.in_shape = cfg, ps, pred.shape
         ctx.mark_non_differentiable(small)
-        return loss_out[0], small
+        return small[14], small
 
     @staticmethod
     def backward(ctx, g_loss, _g_small):
-        pred_c, gt_c, small, mask, ph_ws = ctx.saved_tensors
+        pred_c, gt_c, small, mask, ws = ctx.saved_tensors
         cfg = ctx.cfg
         C, H, W = pred_c.shape
         dev = pred_c.device
-        lib, sp = _lib.lib, _lib.stream_ptr(dev)
-        ph_out, dwt_out, coef, coef_g = small[0:2], small[2:14], small[16:20], small[20:24]
         g = g_loss.reshape(()).float().contiguous()
         grad = torch.empty_like(pred_c)
-        grad2 = torch.empty_like(pred_c)
         weights = (ctypes.c_float * 8)(*[float(w) for w in cfg.band_weights])
         with torch.cuda.device(dev):
-            _lib.check(lib.lg_image_loss_backward_coefs(coef.data_ptr(), g.data_ptr(), coef_g.data_ptr(), sp), RuntimeError)
-            _lib.check(lib.lg_photometric_loss_backward(pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, ph_ws.data_ptr(),
-                                                        coef_g[0:1].data_ptr(), coef_g[1:2].data_ptr(), grad.data_ptr(),
-                                                        sp), RuntimeError)
-            _lib.check(lib.lg_dwt_loss_backward(pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, weights, ctx.ps,
-                                                float(cfg.patch_lh1_weight), float(cfg.patch_hl1_weight),
-                                                coef_g[2:3].data_ptr(), coef_g[3:4].data_ptr(), mask.data_ptr(),
-                                                dwt_out.data_ptr(), grad2.data_ptr(), sp), RuntimeError)
-            _lib.check(lib.lg_image_loss_add(grad.data_ptr(), grad2.data_ptr(), grad.numel(), sp), RuntimeError)
+            # two launches: the photometric gradient, then the wavelet gradient added in place
+            _lib.check(_lib.lib.lg_image_loss_backward(
+                pred_c.data_ptr(), gt_c.data_ptr(), C, H, W, weights, ctx.ps, float(cfg.patch_lh1_weight),
+                float(cfg.patch_hl1_weight), small.data_ptr(), g.data_ptr(), mask.data_ptr(), ws.data_ptr(),
+                grad.data_ptr(), _lib.stream_ptr(dev)), RuntimeError)
         return grad.reshape(ctx.in_shape), None, None, None, None, None, None
 
 

@@ -187,29 +187,40 @@ def test_trainer_single_gpu_with_density_control():
 
 def test_two_stream_view_overlap_computes_the_single_stream_step():
     """view_streams=2 (consecutive views of a step on alternating CUDA streams, the head of view k+1 under the blend
-    backward of view k) keeps the loss state, the bucket and the densification statistics in view order: six steps of
-    four views incl. the running-mean loss give the single-stream losses, parameters and statistics (to the run-to-run
-    spread of the backward's atomics)"""
-    results = []
-    for streams in (1, 2):
+    backward of view k) keeps the loss state, the bucket and the densification statistics in view order.  The first
+    step (nothing amplified by Adam yet) must give the single-stream loss, running mean and gradient bucket to the
+    last-bit spread of the backward's atomics; six steps of four views must stay as close to a single-stream run as a
+    second single-stream run does (the backward adds with atomics, so two runs of the SAME schedule differ too)."""
+    def run(streams):
+        torch.manual_seed(11)  # _small_training_set scales the raw quaternions with torch.rand
         g, cams, gts = _small_training_set(P=25_000, n_views=4)
         cfg = dp.DensifyConfig(densify_from_iter=100, densify_until_iter=200)  # statistics only, no edit
         tr = dp.ViewParallelTrainer(g, loss_fn=dp.RunningMeanLoss(torch.device(dev)), densify=cfg, view_streams=streams)
         assert (tr.view_streams is not None) == (streams == 2)
         bg = torch.zeros(3, device=dev)
-        losses = [float(tr.step(cams, gts, bg)) for _ in range(6)]
+        tr.begin_iteration()
+        first_loss = float(tr.accumulate_views(cams, gts, bg))
+        first = (first_loss, g.grad.clone(), float(tr.loss_fn.running_mean), tr.stats.denom.clone())
+        tr.exchange_and_update(0.25)
+        losses = [float(tr.step(cams, gts, bg)) for _ in range(5)]
         torch.cuda.synchronize()
-        results.append((losses, g.data.clone(), g.grad.clone(), tr.stats.xyz_gradient_accum.clone(), tr.stats.denom.clone(),
-                        float(tr.loss_fn.running_mean)))
-    (l1, p1, g1, a1, d1, r1), (l2, p2, g2, a2, d2, r2) = results
-    np.testing.assert_allclose(l2, l1, rtol=2e-5)
-    assert abs(r1 - r2) <= 2e-5 * abs(r1)
+        return first, losses, g.data.clone(), tr.stats.xyz_gradient_accum.clone(), tr.stats.denom.clone()
+
+    def spread(x, y):
+        return dict(loss=float(np.max(np.abs(np.array(x[1]) - np.array(y[1])) / np.abs(np.array(x[1])))),
+                    far=float(((x[2] - y[2]).abs() > 1e-4 + 1e-4 * x[2].abs()).float().mean()),
+                    accum=float((x[3] - y[3]).abs().max() / x[3].abs().max()))
+
+    one, again, two = run(1), run(1), run(2)
+    (l1, g1, r1, d1), (l2, g2, r2, d2) = one[0], two[0]
+    assert abs(l1 - l2) <= 2e-6 * abs(l1), (l1, l2)
+    assert abs(r1 - r2) <= 2e-6 * abs(r1), (r1, r2)
     assert torch.equal(d1, d2)
-    torch.testing.assert_close(a2, a1, rtol=1e-3, atol=1e-3 * float(a1.abs().max()))
-    assert float((g2 - g1).abs().max()) <= 1e-3 * float(g1.abs().max())
-    # Adam's sign-like first steps amplify last-bit gradient differences of near-zero gradients: compare the bulk
-    close = ((p2 - p1).abs() <= 1e-4 + 1e-4 * p1.abs()).float().mean()
-    assert float(close) >= 0.999, float(close)
+    assert float((g2 - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
+    noise, diff = spread(one, again), spread(one, two)
+    assert torch.equal(one[4], two[4])
+    for k in noise:
+        assert diff[k] <= 4.0 * noise[k] + 1e-5, (k, diff, noise)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink / PCIe peer access")
