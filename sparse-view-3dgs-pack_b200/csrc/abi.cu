@@ -3,7 +3,9 @@
 // DGR/cuda_rasterizer/rasterizer_impl.cu:198-450) and error reporting.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <nvtx3/nvToolsExt.h>
 
 namespace lg {
 
@@ -90,7 +92,21 @@ static long long g_timing_calls = 0;
 static bool g_timing_active = false;
 static cudaEvent_t g_ev[LG_TIMING_SLOTS][ST_COUNT][2];
 static bool g_ev_used[LG_TIMING_SLOTS][ST_COUNT];
+// NVTX ranges around the launches of every stage (host-side ranges named like lgdwt_b200.STAGES), for timeline tools;
+// off unless LGDWT_NVTX=1 is set when the library is first used (nvtx3 is header-only and loads its injection library on
+// demand, so nothing is linked)
+static int nvtx_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("LGDWT_NVTX");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on;
+}
+static const char* const g_stage_names[ST_COUNT] = {"lg:preprocess", "lg:binning", "lg:blend_forward", "lg:blend_backward",
+                                                     "lg:preprocess_backward"};
 void stage_begin(int stage, cudaStream_t stream) {
+    if (nvtx_on()) nvtxRangePushA(g_stage_names[stage]);
     if (g_timing_slots <= 0) return;
     if (stage == ST_PREPROCESS) {
         g_timing_active = (g_timing_calls++ % g_timing_every) == 0;
@@ -102,6 +118,7 @@ void stage_begin(int stage, cudaStream_t stream) {
     if (g_timing_active && g_slot >= 0) cudaEventRecord(g_ev[g_slot][stage][0], stream);
 }
 void stage_end(int stage, cudaStream_t stream) {
+    if (nvtx_on()) nvtxRangePop();
     if (g_timing_slots <= 0 || g_slot < 0 || !g_timing_active) return;
     cudaEventRecord(g_ev[g_slot][stage][1], stream);
     g_ev_used[g_slot][stage] = true;
