@@ -86,10 +86,16 @@ struct BwdPixel {
     float x, y;            // pixel centre
 };
 
-template <int C, bool INVD, int NVT>
-__device__ __forceinline__ void bwd_hit_values(BwdPixel<C, INVD>& px, const char* ent, bool hit, float dx, float dy,
-                                               float G, float alpha, float invd, float (&v)[NVT]) {
-    constexpr int VC = 6 + (INVD ? 1 : 0);
+// One hit's per-lane scalars: everything its 6 + C (+1) partial sums are products of.
+struct BwdHit {
+    float w, dx, dy, aT;   // G * dL/dalpha, mean2D - pixel, alpha * T
+};
+
+// Advances the pixel state (T, B) over one list entry and returns the hit's scalars (all zero weights when the pixel is
+// not hit: alpha = G = 0 leaves B unchanged, T is kept by a select).
+template <int C, bool INVD>
+__device__ __forceinline__ BwdHit bwd_hit_scalars(BwdPixel<C, INVD>& px, const char* ent, bool hit, float dx, float dy,
+                                                  float G, float alpha, float invd) {
     const float alpha_e = hit ? alpha : 0.0f;
     const float G_e = hit ? G : 0.0f;
     float rinv;  // 1 - alpha lies in [0.01, 1]: the bare MUFU.RCP needs no range fix-up
@@ -106,17 +112,35 @@ __device__ __forceinline__ void bwd_hit_values(BwdPixel<C, INVD>& px, const char
     const float d = cg - px.B;
     const float dL_dalpha = fmaf(d, px.T, px.bg_term * rinv);
     px.B = fmaf(alpha_e, d, px.B);
-    const float w = G_e * dL_dalpha;
-    const float wx = w * dx, wy = w * dy;
+    BwdHit h;
+    h.w = G_e * dL_dalpha;
+    h.dx = dx;
+    h.dy = dy;
+    h.aT = aT;
+    return h;
+}
+
+// the 6 + (INVD) + C partial sums of one (pixel, Gaussian) hit (layout: see the record description above)
+template <int C, bool INVD, int NVT>
+__device__ __forceinline__ void bwd_hit_products(const BwdPixel<C, INVD>& px, const BwdHit& h, float (&v)[NVT]) {
+    constexpr int VC = 6 + (INVD ? 1 : 0);
+    const float wx = h.w * h.dx, wy = h.w * h.dy;
     v[0] = wx;
     v[1] = wy;
-    v[2] = wx * dx;
-    v[3] = wx * dy;
-    v[4] = wy * dy;
-    v[5] = w;
-    if (INVD) v[6] = aT * px.g_invd;
+    v[2] = wx * h.dx;
+    v[3] = wx * h.dy;
+    v[4] = wy * h.dy;
+    v[5] = h.w;
+    if (INVD) v[6] = h.aT * px.g_invd;
 #pragma unroll
-    for (int c = 0; c < C; c++) v[VC + c] = aT * px.g[c];
+    for (int c = 0; c < C; c++) v[VC + c] = h.aT * px.g[c];
+}
+
+template <int C, bool INVD, int NVT>
+__device__ __forceinline__ void bwd_hit_values(BwdPixel<C, INVD>& px, const char* ent, bool hit, float dx, float dy,
+                                               float G, float alpha, float invd, float (&v)[NVT]) {
+    const BwdHit h = bwd_hit_scalars<C, INVD>(px, ent, hit, dx, dy, G, alpha, invd);
+    bwd_hit_products<C, INVD, NVT>(px, h, v);
 }
 
 template <int C, bool INVD>
@@ -273,15 +297,27 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
             bool ok;
             float idf;
             if (any[0] != 0u && any[1] != 0u) {
-                float v0[NV], v1[NV], v[2 * NV];
-                bwd_hit_values<C, INVD, NV>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0], v0);
-                bwd_hit_values<C, INVD, NV>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1], v1);
+                // both entries hit somewhere in the patch: the first butterfly stage pairs entry 0's sum k with entry
+                // 1's sum k (upper half-warp keeps entry 1's).  Both are the same products of four per-lane scalars,
+                // so the keep / send choice is made on the scalars (8 selects) instead of on the 2 x NV products
+                const BwdHit h0 = bwd_hit_scalars<C, INVD>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0]);
+                const BwdHit h1 = bwd_hit_scalars<C, INVD>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1]);
+                const bool upper = (lane & 16u) != 0;
+                BwdHit keep, send;
+                keep.w = upper ? h1.w : h0.w;     send.w = upper ? h0.w : h1.w;
+                keep.dx = upper ? h1.dx : h0.dx;  send.dx = upper ? h0.dx : h1.dx;
+                keep.dy = upper ? h1.dy : h0.dy;  send.dy = upper ? h0.dy : h1.dy;
+                keep.aT = upper ? h1.aT : h0.aT;  send.aT = upper ? h0.aT : h1.aT;
+                float v[NV], vs[NV];
+                bwd_hit_products<C, INVD, NV>(px, keep, v);
+                bwd_hit_products<C, INVD, NV>(px, send, vs);
 #pragma unroll
-                for (int n = 0; n < NV; n++) {
-                    v[n] = v0[n];
-                    v[NV + n] = v1[n];
-                }
-                warp_multi_reduce<2 * NV>(v, lane, total, slot, ok);
+                for (int n = 0; n < NV; n++) v[n] += __shfl_xor_sync(0xffffffffu, vs[n], 16);
+                int cnt = NV, base = upper ? NV : 0;  // what the stage of 2 * NV values leaves behind
+                warp_multi_reduce_stage<NV, NV, 8>(v, lane, base, cnt);
+                total = v[0];
+                slot = base;
+                ok = cnt >= 1;
                 const bool second = slot >= NV;
                 idf = second ? ids[1] : ids[0];
                 slot -= second ? NV : 0;
