@@ -171,6 +171,30 @@ class Stepper:
             else:
                 self.peer_unavailable = "LGDWT_EXCHANGE=nccl"
         self.bucket = self.peer.grad if self.peer is not None else torch.zeros(59 * P, device=device)
+        # which all-reduce the timed step uses: measured here, on this box and this bucket (the NVLink paths of the
+        # leased GPUs differ from box to box: at N = 2 the peer kernel took 0.37 ms on one box and 0.74 ms on another, NCCL
+        # 0.47 / 0.65 ms); every rank takes the same decision from the max-over-ranks times
+        self.use_peer, self.exchange_pick = self.peer is not None, None
+        if self.peer is not None and os.environ.get("LGDWT_EXCHANGE_PICK", "auto") == "auto":
+            def t(fn):
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                torch.cuda.synchronize(device)
+                a.record()
+                for _ in range(5):
+                    fn()
+                b.record()
+                torch.cuda.synchronize(device)
+                ms = torch.tensor([a.elapsed_time(b) / 5], device=device)
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                return float(ms.item())
+            t_peer, t_nccl = t(lambda: self.peer.allreduce(1.0)), t(lambda: dist.all_reduce(self.bucket))
+            self.use_peer = t_peer <= t_nccl
+            self.exchange_pick = {"peer_ms": round(t_peer, 4), "nccl_ms": round(t_nccl, 4),
+                                  "picked": "peer" if self.use_peer else "nccl"}
+            self.bucket.zero_()
         self.fields = (("means3D", 3), ("shs", 48), ("opacities", 1), ("scales", 3), ("rotations", 4))
         views, off = {}, 0
         for k, w in self.fields:
@@ -220,7 +244,7 @@ class Stepper:
         if self.mode != "sinks":
             for k, _ in self.fields:
                 self.views[k].copy_(self.p[k].grad)
-        if self.peer is not None:
+        if self.use_peer:
             self.peer.allreduce(1.0)
         else:
             dist.all_reduce(self.bucket)
@@ -337,8 +361,9 @@ def exchange_section(stepper, device, world):
     alone: NCCL all-reduce vs the peer-memory all-reduce the timed step uses, and — with the optimizer — NCCL
     all-reduce + the fused Adam pass on every rank vs ONE fused reduce-scatter + Adam + all-gather kernel."""
     from lgdwt_b200 import dp
-    out = {"step_uses": ("peer all-reduce (csrc/peer.cu, %s)" % stepper.peer.backend) if stepper.peer is not None
+    out = {"step_uses": ("peer all-reduce (csrc/peer.cu, %s)" % stepper.peer.backend) if stepper.use_peer
            else "nccl all-reduce",
+           "picked_at_setup": stepper.exchange_pick,
            "bucket_bytes": int(stepper.bucket.numel() * 4)}
     if stepper.peer is None:
         out["peer_unavailable"] = stepper.peer_unavailable
@@ -856,7 +881,7 @@ def main():
         roofline["simt_peaks"] = {k: round(v, 1) for k, v in simt.items()}
 
     exchange = exchange_section(stepper, device, world) if world > 1 else None
-    exch_name = ("peer-memory kernel over NVLink" if stepper.peer is not None else "NCCL")
+    exch_name = ("peer-memory kernel over NVLink" if stepper.use_peer else "NCCL")
     del stepper
 
     h2d = V * (3 * HEIGHT * WIDTH * 4 + (16 + 16 + 3) * 4)
