@@ -470,3 +470,8 @@ def test_fused_image_loss_equals_the_reference_loss_assembly(shape):
     pred = gt.clone().mul_(0.9).requires_grad_(True)
     fused_image_loss(pred, gt, rm_dev, update_running_mean=False)[0].backward()
     assert float(rm_dev) == before
+    # an upstream gradient other than 1 reaches both gradient kernels (each scales its coefficients by it in-kernel)
+    g1 = pred.grad.clone()
+    pred.grad = None
+    (2.5 * fused_image_loss(pred, gt, rm_dev, update_running_mean=False)[0]).backward()
+    torch.testing.assert_close(pred.grad, 2.5 * g1, rtol=2e-6, atol=1e-12)
