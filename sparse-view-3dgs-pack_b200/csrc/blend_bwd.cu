@@ -1,11 +1,15 @@
 // blend_bwd.cu — per-tile back-to-front replay of the alpha blend (backward).  Replaces renderCUDA<C> in
 // DGR/cuda_rasterizer/backward.cu:452-638.
 //
-// The reference issues 9-10 global atomicAdds per (pixel, Gaussian) hit.  Here the 32 pixels of a warp (an 8x4
-// patch) reduce their 7+C partial gradients with a halving butterfly (12 shuffles for 10 values instead of 50),
-// after which 7+C *different lanes* each own one total and issue ONE coalesced red.global.add per warp into a
-// packed 12-float per-Gaussian record.  Warps in which no pixel hits the Gaussian skip everything after a ballot,
-// and list entries behind the last contributor of every pixel of the tile are never even staged.
+// The reference issues 9-10 global atomicAdds per (pixel, Gaussian) hit.  Here a half-warp owns a 4x4 pixel sub-patch
+// and walks its own compacted list of the entries that can reach it (the 16-bit sub-patch masks the forward left per
+// list entry); the two halves of a warp take a trip together, two entries each.  The 16 pixels of a half reduce the
+// 7+C partial gradients of both entries with a halving butterfly (19 shuffles per trip for 2 x 2 x 9 values), after
+// which every lane owns at most two totals and sends them with red.global.add into a packed 12-float per-Gaussian
+// record.  Trips in which no pixel hits skip everything after a ballot, and list entries behind the last contributor of
+// every pixel of the tile are never even staged.  (One list per warp over the 8x4 patch, round 2 until its last day:
+// 21 % more trips for the same hits — 336 -> 315 us.  The forward keeps the per-warp lists: with two addresses per
+// shared-memory load it becomes bound by the load pipe and loses 14 %.)
 #include "common.cuh"
 
 namespace lg {
@@ -22,11 +26,11 @@ namespace lg {
 #endif
 #define LG_REC 12  // floats per packed gradient record: mean2D.xy, conic.xyw, opacity, invdepth, colour[C], pad
 
-// Sum N per-lane values over the 32 lanes of a warp.  On return lane L holds in `out` the warp total of value
-// `idx` (idx < N valid); lanes whose slot is padding get valid=false.  Halving butterfly: at every stage the two
-// partner lanes split the n live values between them (the upper lane keeps the upper half), so stage sizes are
-// ceil(n/2): 9 -> 5, 3, 2, 1, 1 = 12 shuffles; 18 -> 9, 5, 3, 2, 1 = 20.  Sizes are template parameters so that every
-// array index is a compile-time constant (a run-time `n` put the 18-value form into local memory).
+// One stage (lane ^ OFF) and all later ones of a halving butterfly that sums N per-lane values over a group of 2 * OFF
+// lanes: the two partner lanes split the n live values between them (the upper lane keeps the upper half), so stage
+// sizes are ceil(n/2): from 9 values at OFF = 4: 5, 3, 2 shuffles, after which a lane holds at most two totals, values
+// base .. base + cnt - 1 of the N (cnt <= 0: none).  Sizes are template parameters so that every array index is a
+// compile-time constant (a run-time `n` put the values into local memory).
 template <int NA, int N, int OFF>
 __device__ __forceinline__ void warp_multi_reduce_stage(float (&v)[NA], unsigned lane, int& base, int& cnt) {
     if constexpr (OFF >= 1) {
@@ -49,16 +53,6 @@ __device__ __forceinline__ void warp_multi_reduce_stage(float (&v)[NA], unsigned
             warp_multi_reduce_stage<NA, 1, OFF / 2>(v, lane, base, cnt);
         }
     }
-}
-
-template <int N>
-__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], unsigned lane, float& out, int& idx, bool& valid) {
-    int cnt = N;  // true slot count of this lane's group
-    int base = 0;
-    warp_multi_reduce_stage<N, N, 16>(v, lane, base, cnt);
-    out = v[0];
-    idx = base;
-    valid = cnt >= 1;
 }
 
 // Per-Gaussian record accumulated here (LG_REC floats, consumed by preprocess_backward_kernel):
@@ -150,7 +144,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dinvdepth_pix, float* __restrict__ grad_rec,
-    const uint32_t* __restrict__ tile_order, const uint8_t* __restrict__ entry_masks) {
+    const uint32_t* __restrict__ tile_order, const uint16_t* __restrict__ entry_masks) {
     constexpr int NV = 6 + (INVD ? 1 : 0) + C;  // values reduced per (warp, Gaussian)
     constexpr int ENT = 48;                     // bytes per staged entry
     // one staged entry = three float4: (mean.x, mean.y, Gaussian id, 1/depth) (conic a, b, c, opacity) (colours, C <= 4),
@@ -159,15 +153,20 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     __shared__ float4 s_ent[(BWD_BATCH + 1) * 3];
     // per 32 staged entries and patch: which of them can touch the patch at all (ballots of the staging warps over the
     // mask bytes the forward pass left per list entry)
-    __shared__ uint32_t s_reach[BWD_BATCH / 32][LG_TILE_PIX / 32];
-    __shared__ __align__(4) lg_slot_t s_list[LG_TILE_PIX / 32][BWD_BATCH + 2];  // per warp: byte offsets into s_ent
+    __shared__ __align__(8) uint32_t s_reach[BWD_BATCH / 32][16];
+    // per half-warp (= 4x4 sub-patch, as in the forward): byte offsets into s_ent; the two lists of a warp are padded
+    // with the sentinel to a common even length
+    __shared__ __align__(4) lg_slot_t s_list[LG_TILE_PIX / 32][2][BWD_BATCH + 2];
     __shared__ uint32_t s_max;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = tile_order[blockIdx.x];  // deepest tiles first
     const uint32_t tile_x = tile % (uint32_t)grid_x, tile_y = tile / (uint32_t)grid_x;
-    const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + (lane >> 3);
+    const unsigned half = lane >> 4;  // lanes 0-15: the left 4x4 sub-patch of the warp's 8x4 patch, 16-31: the right one
+    const uint32_t pix_x = tile_x * LG_TILE_X + (warp & 1u) * 8u + half * 4u + (lane & 3u);
+    const uint32_t pix_y = tile_y * LG_TILE_Y + (warp >> 1) * 4u + ((lane >> 2) & 3u);
+    const unsigned sub0 = (warp >> 1) * 4u + (warp & 1u) * 2u;  // mask bit of the left sub-patch (right: + 1)
+    const unsigned half_mask = half ? 0xffff0000u : 0x0000ffffu;
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
     const uint2 range = ranges[tile];
@@ -183,6 +182,8 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
     }
     __syncthreads();
     const uint32_t warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
+    const uint32_t left_max = __reduce_max_sync(0xffffffffu, half ? 0u : last_contributor);
+    const uint32_t right_max = __reduce_max_sync(0xffffffffu, half ? last_contributor : 0u);
     if (lane == 0 && warp_max) atomicMax(&s_max, warp_max);
     __syncthreads();
     const uint32_t n_eff = s_max;  // entries [0, n_eff) of this tile's list can contribute to some pixel
@@ -229,11 +230,11 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
             }
             uint32_t word = 0;
 #pragma unroll
-            for (int b = 0; b < LG_TILE_PIX / 32; b++) {
+            for (int b = 0; b < 16; b++) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, (mask >> b) & 1u);
                 word = lane == (unsigned)b ? bal : word;
             }
-            if (lane < LG_TILE_PIX / 32) s_reach[slot >> 5][lane] = word;
+            if (lane < 16) s_reach[slot >> 5][lane] = word;
         }
         __syncthreads();
         const int batch = (int)min((uint32_t)BWD_BATCH, n_eff - batch_base);
@@ -241,24 +242,41 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
         // position rel = n_eff-1-(batch_base+j) < warp_max  <=>  j >= n_eff - warp_max - batch_base
         const int first = (int)max((long long)n_eff - (long long)warp_max - (long long)batch_base, 0ll);
         if (first >= batch) continue;
-        // compacted list of this warp's reachable entries as byte offsets into s_ent, padded to an even length
+        // compacted lists of the two sub-patches' reachable entries as byte offsets into s_ent (all 32 lanes build both:
+        // lane = entry within a chunk of 32), padded with the sentinel to a common even length.  A sub-patch also drops
+        // the slots behind its own last contributor.
         // (words of chunks past the end of the list are zero: the staging loop covers all BWD_BATCH slots)
         int cnt = 0;
         {
-            const uint32_t list_addr = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
+            const int first0 = (int)max((long long)n_eff - (long long)left_max - (long long)batch_base, 0ll);
+            const int first1 = (int)max((long long)n_eff - (long long)right_max - (long long)batch_base, 0ll);
+            const uint32_t list_addr0 = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0][0]);
+            const uint32_t list_addr1 = (uint32_t)__cvta_generic_to_shared(&s_list[warp][1][0]);
             const unsigned lt = (1u << lane) - 1u;
             const uint32_t my_off = lane * ENT;
+            int cnt0 = 0, cnt1 = 0;
 #pragma unroll
             for (int c = 0; c < BWD_BATCH / 32; c++) {
-                const int drop = min(max(first - c * 32, 0), 32);  // leading slots of this chunk behind `first`
-                const uint32_t bal = s_reach[c][warp] & (uint32_t)(0xffffffffull << drop);
-                if ((bal >> lane) & 1u)
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)(cnt + __popc(bal & lt))),
-                                 "h"((unsigned short)(my_off + c * 32 * ENT)) : "memory");
-                cnt += __popc(bal);
+                const uint2 reach = *reinterpret_cast<const uint2*>(&s_reach[c][sub0]);
+                const int drop0 = min(max(first0 - c * 32, 0), 32), drop1 = min(max(first1 - c * 32, 0), 32);
+                const uint32_t bal0 = reach.x & (uint32_t)(0xffffffffull << drop0);
+                const uint32_t bal1 = reach.y & (uint32_t)(0xffffffffull << drop1);
+                const unsigned short off = (unsigned short)(my_off + c * 32 * ENT);
+                if ((bal0 >> lane) & 1u)
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr0 + 2u * (uint32_t)(cnt0 + __popc(bal0 & lt))),
+                                 "h"(off) : "memory");
+                if ((bal1 >> lane) & 1u)
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr1 + 2u * (uint32_t)(cnt1 + __popc(bal1 & lt))),
+                                 "h"(off) : "memory");
+                cnt0 += __popc(bal0);
+                cnt1 += __popc(bal1);
             }
-            if (lane == 0)
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * (uint32_t)cnt),
+            cnt = (max(cnt0, cnt1) + 1) & ~1;
+            for (int j = cnt0 + (int)lane; j < cnt; j += 32)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr0 + 2u * (uint32_t)j),
+                             "h"((unsigned short)(BWD_BATCH * ENT)) : "memory");
+            for (int j = cnt1 + (int)lane; j < cnt; j += 32)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr1 + 2u * (uint32_t)j),
                              "h"((unsigned short)(BWD_BATCH * ENT)) : "memory");
             __syncwarp();
             cnt = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);  // same in every lane; tells the compiler so
@@ -267,11 +285,12 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
         //                                           <=>  j*ENT > ENT * (n_eff-1-batch_base-last_contributor)
         const long long thr = (long long)n_eff - 1ll - (long long)batch_base - (long long)last_contributor;
         const int thr_off = ENT * (int)max(min(thr, (long long)(2 * BWD_BATCH)), -1ll);
-        // two list entries per trip: their power / exp / alpha evaluations are independent of each other and of the
-        // pixel state, so they are issued together; the hit arithmetic then runs in list order and the partial sums of
-        // both entries go through ONE butterfly (20 shuffles for 2 x 9 values instead of 2 x 12)
+        // two list entries per trip and half-warp: their power / exp / alpha evaluations are independent of each other and
+        // of the pixel state, so they are issued together; the hit arithmetic then runs in list order and the partial
+        // sums of both entries go through ONE butterfly over the 16 lanes of the half (19 shuffles for the 2 x 2 x 9
+        // values of a trip)
         for (int k0 = 0; k0 < cnt; k0 += 2) {
-            const uint32_t offs = *reinterpret_cast<const uint32_t*>(&s_list[warp][k0]);
+            const uint32_t offs = *reinterpret_cast<const uint32_t*>(&s_list[warp][half][k0]);
             const char* ents[2] = {ent_base + (offs & 0xffffu), ent_base + (offs >> 16)};
             const int offv[2] = {(int)(offs & 0xffffu), (int)(offs >> 16)};
             float dxs[2], dys[2], Gs[2], alphas[2], ids[2], invds[2];
@@ -291,49 +310,37 @@ __global__ void __launch_bounds__(LG_TILE_PIX, BWD_MIN_BLOCKS) blend_backward_ke
                 hits[u] = hit;
                 any[u] = __ballot_sync(0xffffffffu, hit);
             }
-            if ((any[0] | any[1]) == 0u) continue;
-            float total;
-            int slot;
-            bool ok;
-            float idf;
-            if (any[0] != 0u && any[1] != 0u) {
-                // both entries hit somewhere in the patch: the first butterfly stage pairs entry 0's sum k with entry
-                // 1's sum k (upper half-warp keeps entry 1's).  Both are the same products of four per-lane scalars,
-                // so the keep / send choice is made on the scalars (8 selects) instead of on the 2 x NV products
-                const BwdHit h0 = bwd_hit_scalars<C, INVD>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0]);
-                const BwdHit h1 = bwd_hit_scalars<C, INVD>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1]);
-                const bool upper = (lane & 16u) != 0;
-                BwdHit keep, send;
-                keep.w = upper ? h1.w : h0.w;     send.w = upper ? h0.w : h1.w;
-                keep.dx = upper ? h1.dx : h0.dx;  send.dx = upper ? h0.dx : h1.dx;
-                keep.dy = upper ? h1.dy : h0.dy;  send.dy = upper ? h0.dy : h1.dy;
-                keep.aT = upper ? h1.aT : h0.aT;  send.aT = upper ? h0.aT : h1.aT;
-                float v[NV], vs[NV];
-                bwd_hit_products<C, INVD, NV>(px, keep, v);
-                bwd_hit_products<C, INVD, NV>(px, send, vs);
+            if ((any[0] | any[1]) == 0u) continue;  // neither half hits either entry
+            // The first butterfly stage (lane ^ 8) pairs entry 0's sum k with entry 1's sum k; both are the same products
+            // of four per-lane scalars, so the keep / send choice is made on the scalars (8 selects) instead of on the
+            // 2 x NV products.  Three more stages (lane ^ 4, 2, 1) leave every lane of the half with at most two totals.
+            const BwdHit h0 = bwd_hit_scalars<C, INVD>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0]);
+            const BwdHit h1 = bwd_hit_scalars<C, INVD>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1]);
+            const bool upper = (lane & 8u) != 0;
+            BwdHit keep, send;
+            keep.w = upper ? h1.w : h0.w;     send.w = upper ? h0.w : h1.w;
+            keep.dx = upper ? h1.dx : h0.dx;  send.dx = upper ? h0.dx : h1.dx;
+            keep.dy = upper ? h1.dy : h0.dy;  send.dy = upper ? h0.dy : h1.dy;
+            keep.aT = upper ? h1.aT : h0.aT;  send.aT = upper ? h0.aT : h1.aT;
+            float v[NV], vs[NV];
+            bwd_hit_products<C, INVD, NV>(px, keep, v);
+            bwd_hit_products<C, INVD, NV>(px, send, vs);
 #pragma unroll
-                for (int n = 0; n < NV; n++) v[n] += __shfl_xor_sync(0xffffffffu, vs[n], 16);
-                int cnt = NV, base = upper ? NV : 0;  // what the stage of 2 * NV values leaves behind
-                warp_multi_reduce_stage<NV, NV, 8>(v, lane, base, cnt);
-                total = v[0];
-                slot = base;
-                ok = cnt >= 1;
-                const bool second = slot >= NV;
-                idf = second ? ids[1] : ids[0];
-                slot -= second ? NV : 0;
-            } else if (any[0] != 0u) {
-                float v[NV];
-                bwd_hit_values<C, INVD, NV>(px, ents[0], hits[0], dxs[0], dys[0], Gs[0], alphas[0], invds[0], v);
-                warp_multi_reduce<NV>(v, lane, total, slot, ok);
-                idf = ids[0];
-            } else {
-                float v[NV];
-                bwd_hit_values<C, INVD, NV>(px, ents[1], hits[1], dxs[1], dys[1], Gs[1], alphas[1], invds[1], v);
-                warp_multi_reduce<NV>(v, lane, total, slot, ok);
-                idf = ids[1];
+            for (int n = 0; n < NV; n++) v[n] += __shfl_xor_sync(0xffffffffu, vs[n], 8);
+            int cnt_v = NV, base = upper ? NV : 0;  // what a stage over 2 * NV values leaves behind
+            warp_multi_reduce_stage<NV, NV, 4>(v, lane, base, cnt_v);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (j < cnt_v) {
+                    const int idx = base + j;
+                    const bool second = idx >= NV;
+                    int slot = idx - (second ? NV : 0);
+                    if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
+                    // totals of an entry no pixel of this half hit are exact zeros (sentinel padding included): not sent
+                    if ((second ? any[1] : any[0]) & half_mask)
+                        atomicAdd(grad_rec + (size_t)__float_as_uint(second ? ids[1] : ids[0]) * LG_REC + slot, v[j]);
+                }
             }
-            if (!INVD && slot >= 6) slot += 1;  // the record keeps its inverse-depth slot
-            if (ok) atomicAdd(grad_rec + (size_t)__float_as_uint(idf) * LG_REC + slot, total);
         }
     }
 }
@@ -349,7 +356,7 @@ int launch_blend_backward(int P, int C, int W, int H, const GeometryState& g, co
     blend_backward_kernel<CH, INVD><<<grid, block, 0, stream>>>(                                                     \
         img.ranges, b.point_list, W, H, gx, background, g.means2D, g.conic_opacity, features, g.depths,              \
         img.accum_alpha, img.n_contrib, dL_dpix, dL_dinvdepth_pix, grad_scratch, img.tile_order_bwd,                  \
-        reinterpret_cast<const uint8_t*>(b.pairs))
+        reinterpret_cast<const uint16_t*>(b.pairs))
     const bool invd = dL_dinvdepth_pix != nullptr;
     switch (C) {
         case 1: if (invd) LG_LAUNCH_BWD(1, true); else LG_LAUNCH_BWD(1, false); break;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
     const float* __restrict__ depths, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_invdepth,
     const uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_neff, uint32_t* __restrict__ counters,
-    uint32_t capacity, uint32_t* __restrict__ tile_order_bwd, uint8_t* __restrict__ entry_masks) {
+    uint32_t capacity, uint32_t* __restrict__ tile_order_bwd, uint16_t* __restrict__ entry_masks) {
     // The list was only built if it fits the binning buffer the caller sized speculatively (abi.cu); otherwise this
     // launch is void and the host queues the tail of the forward again.
     if (counters[1] > capacity) return;
@@ -84,12 +84,17 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
         for (int u = 0; u < BLEND_BATCH / LG_TILE_PIX; u++) {
             const unsigned slot = u * LG_TILE_PIX + tid;
             const uint32_t progress = (uint32_t)i * BLEND_BATCH + slot;
-            unsigned mask = 0;
+            unsigned mask = 0, mask16 = 0;
             if (range.x + progress < range.y) {
                 const uint32_t id = point_list[range.x + progress];
                 const float2 m = means2D[id];
                 const float4 co = conic_opacity[id];
-                mask = lg_patch_mask(m.x, m.y, co, tile_x0, tile_y0);
+                mask16 = lg_subpatch_mask16(m.x, m.y, co, tile_x0, tile_y0);
+                // this kernel walks one list per warp (8x4 patch = two sub-patches side by side: bits 2j, 2j + 1)
+                unsigned t = (mask16 | (mask16 >> 1)) & 0x5555u;
+                t = (t | (t >> 1)) & 0x3333u;
+                t = (t | (t >> 2)) & 0x0f0fu;
+                mask = (t | (t >> 4)) & 0x00ffu;
                 float fv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int c = 0; c < C; c++) fv[c] = features[(size_t)id * C + c];
@@ -97,9 +102,10 @@ __global__ void __launch_bounds__(LG_TILE_PIX, FWD_MIN_BLOCKS) blend_forward_ker
                 s_ent[slot * 3 + 1] = co;
                 s_ent[slot * 3 + 2] = make_float4(fv[0], fv[1], fv[2], fv[3]);
             }
-            // the staging warp votes once per patch; lane b keeps the word of patch b.  The mask byte also goes to
-            // global memory for the backward pass, which stages the same entries (it never goes past a batch staged here)
-            if (range.x + progress < range.y) entry_masks[range.x + progress] = (uint8_t)mask;
+            // the staging warp votes once per patch; lane b keeps the word of patch b.  The 16-bit sub-patch mask goes to
+            // global memory for the backward pass, which stages the same entries (it never goes past a batch staged
+            // here) and walks one list per half-warp
+            if (range.x + progress < range.y) entry_masks[range.x + progress] = (uint16_t)mask16;
             uint32_t word = 0;
 #pragma unroll
             for (int b = 0; b < LG_TILE_PIX / 32; b++) {
@@ -270,7 +276,7 @@ int launch_blend_forward(int C, int W, int H, int capacity, const GeometryState&
                                                          img.n_contrib, background, out_color, out_invdepth,         \
                                                          img.tile_order, img.tile_neff, img.counters,                \
                                                          (uint32_t)capacity, img.tile_order_bwd,                     \
-                                                         reinterpret_cast<uint8_t*>(b.pairs))
+                                                         reinterpret_cast<uint16_t*>(b.pairs))
     switch (C) {
         case 1: LG_LAUNCH_FWD(1); break;
         case 2: LG_LAUNCH_FWD(2); break;
