@@ -5,9 +5,11 @@
 // exact operation order of the reference's sm_100a build and the same libdevice expf (this file
 // must never be compiled with --use_fast_math).  Only the thread->pixel mapping and the data staging differ:
 //  - a warp covers an 8x4 pixel patch (better hit coherence than the reference's 16x2 rows);
-//  - while a batch is staged, every entry gets an 8-bit mask of the patches it can reach at all (conservative
-//    alpha >= 1/255 radius); each warp compacts its own order-preserving list with ballots and only evaluates those
-//    entries — a skipped entry would have failed the reference's alpha test on all 32 pixels, so results are unchanged;
+//  - while a batch is staged, every entry gets a 16-bit mask of the 4x4 sub-patches it can reach at all (exact minimum
+//    of the quadratic form over each box, common.cuh); neighbouring bits are ORed into the 8 patch bits and each warp
+//    compacts its own order-preserving list with ballots and only evaluates those entries — a skipped entry would have
+//    failed the reference's alpha test on all 32 pixels, so results are unchanged.  The 16-bit masks stay in global
+//    memory for the backward pass, which walks one list per half-warp;
 //  - colours and 1/depth are staged in shared memory with the geometry, so a hit never touches global memory
 //    (the reference gathers features[] / depths[] per hit, forward.cu:372,375).
 #include "common.cuh"

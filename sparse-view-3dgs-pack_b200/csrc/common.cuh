@@ -224,58 +224,18 @@ __device__ __forceinline__ void lg_get_rect(float px, float py, int radius, int 
              (uint32_t)max(0, __float2int_rz(F_MUL(F_ADD(F_ADD(F_ADD(py, r), 16.0f), -1.0f), 0.0625f))));
 }
 
-// Which 8x4 pixel patches (= warps) of a 16x16 tile can a list entry contribute to at all?
-// alpha = o * exp(power) >= 1/255 needs q := a dx^2 + 2 b dx dy + c dy^2 = -2 power <= 2 ln(255 o).  For every patch
-// the exact minimum of the convex quadratic q over the patch rectangle (pixel centres x0..x0+7, y0..y0+3, taken as
-// a continuous box, so a lower bound of q on the pixels) is compared with that threshold: if the mean lies in the
-// box the minimum is 0, otherwise it sits on the box edge(s) facing the mean, where q is a 1-D parabola whose
-// minimiser is clamped to the edge.  Bit (r*2 + k) of the result is clear only if every pixel of patch (row r,
-// column k) fails the reference's alpha test (forward.cu:358-361), with a margin (1 % in alpha, 0.1 % in q) that is
-// four orders of magnitude above the fp32 rounding of `power`; skipping such an entry for the whole warp therefore
-// never changes a decision the reference takes.  Degenerate inputs (non-positive or NaN a, c; NaN opacity) keep all
-// bits set.
-__device__ __forceinline__ unsigned lg_patch_mask(float mx, float my, float4 conic_opacity, float tx0, float ty0) {
-    const float a = conic_opacity.x, b = conic_opacity.y, c = conic_opacity.z, o = conic_opacity.w;
-    if (o <= 0.0f) return 0u;                                       // alpha <= 0 on every pixel
-    if (!(a > 0.0f) || !(c > 0.0f) || !(o > 0.0f)) return 0xffu;
-    const float qmax = 2.002f * (__logf(255.0f * o) + 0.01f);       // negative when o < 1/255: nothing survives
-    const float nb_over_c = -b * __fdividef(1.0f, c), nb_over_a = -b * __fdividef(1.0f, a);
-    float xlo[2], xhi[2], ex[2], ax2[2], bx2[2], ty[2];
-    bool in_x[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        xlo[k] = tx0 + 8.0f * k - mx;
-        xhi[k] = xlo[k] + 7.0f;
-        in_x[k] = xlo[k] <= 0.0f && xhi[k] >= 0.0f;
-        ex[k] = xlo[k] > 0.0f ? xlo[k] : xhi[k];  // offset of the box edge facing the mean
-        ax2[k] = a * ex[k] * ex[k];
-        bx2[k] = 2.0f * b * ex[k];
-        ty[k] = nb_over_c * ex[k];                // unconstrained minimiser of q along that edge
-    }
-    unsigned m = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const float ylo = ty0 + 4.0f * r - my, yhi = ylo + 3.0f;
-        const bool in_y = ylo <= 0.0f && yhi >= 0.0f;
-        const float ey = ylo > 0.0f ? ylo : yhi;
-        const float cy2 = c * ey * ey, by2 = 2.0f * b * ey, tx = nb_over_a * ey;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const float dy = fminf(fmaxf(ty[k], ylo), yhi);
-            const float q1 = in_x[k] ? 3.0e38f : fmaf(dy, fmaf(c, dy, bx2[k]), ax2[k]);
-            const float dx = fminf(fmaxf(tx, xlo[k]), xhi[k]);
-            const float q2 = in_y ? 3.0e38f : fmaf(dx, fmaf(a, dx, by2), cy2);
-            const float qmin = (in_x[k] && in_y) ? 0.0f : fminf(q1, q2);
-            m |= (qmin > qmax) ? 0u : (1u << (r * 2 + k));
-        }
-    }
-    return m;
-}
-
-// The same test for the sixteen 4x4 sub-patches of the tile (bit r*4 + col: pixel centres x0 + 4 col .. + 3,
-// y0 + 4 r .. + 3): a half-warp owns one sub-patch, so the two halves of a warp walk lists of their own.  Finer boxes cut
-// the (lane, entry) evaluations that cannot hit: on the benchmark scene the trips per warp — the longer of its two lists
-// — are 21 % fewer than the entries that reach the warp's 8x4 patch.
+// Which 4x4 pixel sub-patches of a 16x16 tile can a list entry contribute to at all?
+// alpha = o * exp(power) >= 1/255 needs q := a dx^2 + 2 b dx dy + c dy^2 = -2 power <= 2 ln(255 o).  For every
+// sub-patch the exact minimum of the convex quadratic q over its rectangle (pixel centres x0 + 4 col .. + 3,
+// y0 + 4 r .. + 3, taken as a continuous box, so a lower bound of q on the pixels) is compared with that threshold: if
+// the mean lies in the box the minimum is 0, otherwise it sits on the box edge(s) facing the mean, where q is a 1-D
+// parabola whose minimiser is clamped to the edge.  Bit (r*4 + col) of the result is clear only if every pixel of that
+// sub-patch fails the reference's alpha test (forward.cu:358-361), with a margin (1 % in alpha, 0.1 % in q) that is
+// four orders of magnitude above the fp32 rounding of `power`; skipping such an entry for those pixels therefore never
+// changes a decision the reference takes.  Degenerate inputs (non-positive or NaN a, c; NaN opacity) keep all bits set.
+// The blend forward ORs bits 2j and 2j + 1 into the bit of 8x4 patch j (one list per warp); the backward walks one list
+// per half-warp: on the benchmark scene the trips per warp — the longer of its two lists — are 21 % fewer than the
+// entries that reach the warp's 8x4 patch.
 __device__ __forceinline__ unsigned lg_subpatch_mask16(float mx, float my, float4 conic_opacity, float tx0, float ty0) {
     const float a = conic_opacity.x, b = conic_opacity.y, c = conic_opacity.z, o = conic_opacity.w;
     if (o <= 0.0f) return 0u;                                       // alpha <= 0 on every pixel
@@ -314,23 +274,7 @@ __device__ __forceinline__ unsigned lg_subpatch_mask16(float mx, float my, float
     return m;
 }
 
-// Warp `w` turns the per-entry patch masks of a staged batch into its own compacted, order-preserving list of the
-// entry slots in [lo, hi) that can reach its patch.  Returns the list length.  Only warp w reads list_w afterwards.
-typedef uint16_t lg_slot_t;  // index of a staged list entry inside its batch
-__device__ __forceinline__ int lg_compact_patch_list(const uint8_t* s_mask, lg_slot_t* list_w, unsigned w, unsigned lane,
-                                                     int lo, int hi) {
-    int cnt = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = lo & ~31; base < hi; base += 32) {
-        const int slot = base + (int)lane;
-        const bool bit = slot >= lo && slot < hi && ((s_mask[slot] >> w) & 1u);
-        const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        if (bit) list_w[cnt + __popc(bal & lt)] = (lg_slot_t)slot;
-        cnt += __popc(bal);
-    }
-    __syncwarp();
-    return cnt;
-}
+typedef uint16_t lg_slot_t;  // byte offset of a staged list entry inside its batch
 
 // A warp's 32 Gaussians own a contiguous block of 32 rows x M3 floats of a (P, M3) array.  Copy `count` floats of that
 // block between global memory and a shared-memory tile whose row stride is M3 | 1 (odd: bank-conflict-free row
