@@ -12,7 +12,9 @@
 
 namespace lg {
 
+#ifndef PRE_BLOCK
 #define PRE_BLOCK 256
+#endif
 #define PRE_MAX_ROW 48  // widest SH row (floats per Gaussian) staged through shared memory
 #define PRE_COOP 8      // tile rectangles above this many tiles are counted by the whole warp
 #ifndef PRE_SH_BULK

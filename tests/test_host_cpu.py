@@ -303,3 +303,30 @@ def test_binning_capacity_hint_bookkeeping():
     assert dgr._capacity_hint(*key) == int(1.25 * 50) + 1024          # the large value aged out
     assert dgr._capacity_hint("cuda:0", 2000, 64, 48) == 0            # another shape: no history
     dgr._CAPACITY_HISTORY.clear()
+
+
+def test_one_call_image_loss_entry_points_reject_bad_arguments_without_a_gpu():
+    """lg_image_loss_forward / _backward and the scaled gradient entry points validate before they launch anything"""
+    from lgdwt_b200 import _lib
+    w = (ctypes.c_float * 8)(*([1.0] * 8))
+    rc = _lib.lib.lg_image_loss_forward(None, None, 3, 8, 8, w, 0, 0.5, 1.0, 1.0, None, 0.2, 0.1, 1, None, None, 0, None, 0,
+                                        None, 0, 1, None)
+    assert rc == _lib.LG_ERR_INVALID_ARGUMENT and b"lg_image_loss_forward" in _lib.lib.lg_last_error()
+    rc = _lib.lib.lg_image_loss_backward(None, None, 3, 8, 8, w, 0, 1.0, 1.0, None, None, None, None, None, None)
+    assert rc == _lib.LG_ERR_INVALID_ARGUMENT and b"lg_image_loss_backward" in _lib.lib.lg_last_error()
+    assert _lib.lib.lg_photometric_loss_backward_scaled(None, None, 3, 8, 8, None, None, None, None, None,
+                                                        None) == _lib.LG_ERR_INVALID_ARGUMENT
+    assert _lib.lib.lg_dwt_loss_backward_scaled(None, None, 3, 8, 8, w, 0, 1.0, 1.0, None, None, None, None, None, None, 1,
+                                                None) == _lib.LG_ERR_INVALID_ARGUMENT
+
+
+def test_view_streams_argument_of_the_trainer():
+    """view_streams is validated, and a trainer without CUDA buffers (or with a custom render_fn) stays single-stream"""
+    import numpy as np
+    import torch
+    from lgdwt_b200 import dp, scenes
+    g = dp.FlatGaussians.from_scene(scenes.trained_like_scene(64, seed=3), torch.device("cpu"))
+    with pytest.raises(ValueError):
+        dp.ViewParallelTrainer(g, render_fn=lambda act, cam, bg: None, view_streams=3)
+    tr = dp.ViewParallelTrainer(g, render_fn=lambda act, cam, bg: None, view_streams=2)
+    assert tr.view_streams is None
