@@ -107,7 +107,9 @@ template <int WORLD>
 __global__ void __launch_bounds__(256, 2) peer_reduce_adam_kernel(PeerPtrs grads, PeerPtrs params, int rank,
                                                                float4* __restrict__ exp_avg,
                                                                float4* __restrict__ exp_avg_sq, long long lo4,
-                                                               long long hi4, PeerAdam a) {
+                                                               long long hi4, PeerAdam a,
+                                                               const unsigned* __restrict__ status) {
+    if (*status) return;  // a barrier in front of this kernel timed out
     constexpr int U = PeerUnroll<WORLD>::value;
     const float4* src[WORLD];
     float4* dst[WORLD];
@@ -149,7 +151,8 @@ __global__ void __launch_bounds__(256, 2) peer_reduce_adam_kernel(PeerPtrs grads
 // reduce-only variant (no optimizer): every rank ends up with the summed bucket, like an all-reduce
 template <int WORLD>
 __global__ void __launch_bounds__(256, 2) peer_allreduce_kernel(PeerPtrs grads, int rank, long long lo4, long long hi4,
-                                                             float grad_scale) {
+                                                             float grad_scale, const unsigned* __restrict__ status) {
+    if (*status) return;
     constexpr int U = PeerUnroll<WORLD>::value;
     const float4* src[WORLD];
     float4* dst[WORLD];
@@ -205,7 +208,9 @@ __global__ void __launch_bounds__(256, 2) peer_reduce_adam_mc_kernel(const float
                                                                      const float4* __restrict__ local_param,
                                                                      float4* __restrict__ exp_avg,
                                                                      float4* __restrict__ exp_avg_sq, long long lo4,
-                                                                     long long hi4, PeerAdam a) {
+                                                                     long long hi4, PeerAdam a,
+                                                                     const unsigned* __restrict__ status) {
+    if (*status) return;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q0 = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < hi4; q0 += MC_UNROLL * stride) {
         float4 s[MC_UNROLL], m[MC_UNROLL], v[MC_UNROLL], p[MC_UNROLL];
@@ -232,7 +237,9 @@ __global__ void __launch_bounds__(256, 2) peer_reduce_adam_mc_kernel(const float
 }
 
 __global__ void __launch_bounds__(256, 2) peer_allreduce_mc_kernel(float4* __restrict__ mc_grad, long long lo4,
-                                                                   long long hi4, float grad_scale) {
+                                                                   long long hi4, float grad_scale,
+                                                                   const unsigned* __restrict__ status) {
+    if (*status) return;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q0 = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < hi4; q0 += MC_UNROLL * stride) {
         float4 s[MC_UNROLL];
@@ -249,14 +256,23 @@ __global__ void __launch_bounds__(256, 2) peer_allreduce_mc_kernel(float4* __res
     }
 }
 
-static unsigned* g_peer_status = nullptr;  // device word set by a timed-out barrier
+// One word per device, set by a timed-out barrier.  The exchange kernels queued behind that barrier read it and do
+// nothing: sums over peers that never arrived must not reach the parameters (the error surfaces at lg_peer_check).
+#define PEER_MAX_DEVICES 32
+static unsigned* g_peer_status[PEER_MAX_DEVICES] = {};
 
 static int peer_status_word(unsigned** out) {
-    if (!g_peer_status) {
-        LG_CUDA(cudaMalloc(&g_peer_status, sizeof(unsigned)));
-        LG_CUDA(cudaMemset(g_peer_status, 0, sizeof(unsigned)));
+    int dev = 0;
+    LG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PEER_MAX_DEVICES) {
+        set_error("peer exchange: device ordinal %d out of range", dev);
+        return LG_ERR_UNSUPPORTED;
     }
-    *out = g_peer_status;
+    if (!g_peer_status[dev]) {
+        LG_CUDA(cudaMalloc(&g_peer_status[dev], sizeof(unsigned)));
+        LG_CUDA(cudaMemset(g_peer_status[dev], 0, sizeof(unsigned)));
+    }
+    *out = g_peer_status[dev];
     return LG_OK;
 }
 
@@ -335,12 +351,14 @@ extern "C" int lg_peer_barrier(int rank, int world, void* const* flag_ptrs, unsi
 
 extern "C" int lg_peer_check(void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
-    if (!g_peer_status) return LG_OK;
+    int dev = 0;
+    LG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PEER_MAX_DEVICES || !g_peer_status[dev]) return LG_OK;
     unsigned s = 0;
-    LG_CUDA(cudaMemcpyAsync(&s, g_peer_status, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    LG_CUDA(cudaMemcpyAsync(&s, g_peer_status[dev], sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     LG_CUDA(cudaStreamSynchronize(stream));
     if (s) {
-        LG_CUDA(cudaMemsetAsync(g_peer_status, 0, sizeof(unsigned), stream));  // reported once
+        LG_CUDA(cudaMemsetAsync(g_peer_status[dev], 0, sizeof(unsigned), stream));  // reported once
         set_error("lg_peer_barrier timed out: a peer rank did not reach the exchange step");
         return LG_ERR_CUDA;
     }
@@ -382,8 +400,11 @@ extern "C" int lg_peer_reduce_adam(int rank, int world, void* const* grad_ptrs, 
     long long lo4, hi4;
     shard_of(n / 4, rank, world, &lo4, &hi4);
     const int blocks = peer_grid(hi4 - lo4);
+    unsigned* status = nullptr;
+    const int rc_status = peer_status_word(&status);
+    if (rc_status != LG_OK) return rc_status;
 #define PEER_LAUNCH(W) case W: peer_reduce_adam_kernel<W><<<blocks, 256, 0, stream>>>(g, p, rank, (float4*)exp_avg, \
-                                                                                     (float4*)exp_avg_sq, lo4, hi4, a); break
+                                                                                     (float4*)exp_avg_sq, lo4, hi4, a, status); break
     switch (world) {
         PEER_LAUNCH(1); PEER_LAUNCH(2); PEER_LAUNCH(3); PEER_LAUNCH(4); PEER_LAUNCH(5); PEER_LAUNCH(6); PEER_LAUNCH(7);
         PEER_LAUNCH(8);
@@ -407,7 +428,10 @@ extern "C" int lg_peer_allreduce(int rank, int world, void* const* grad_ptrs, lo
     long long lo4, hi4;
     shard_of(n / 4, rank, world, &lo4, &hi4);
     const int blocks = peer_grid(hi4 - lo4);
-#define PEER_LAUNCH(W) case W: peer_allreduce_kernel<W><<<blocks, 256, 0, stream>>>(g, rank, lo4, hi4, grad_scale); break
+    unsigned* status = nullptr;
+    const int rc_status = peer_status_word(&status);
+    if (rc_status != LG_OK) return rc_status;
+#define PEER_LAUNCH(W) case W: peer_allreduce_kernel<W><<<blocks, 256, 0, stream>>>(g, rank, lo4, hi4, grad_scale, status); break
     switch (world) {
         PEER_LAUNCH(1); PEER_LAUNCH(2); PEER_LAUNCH(3); PEER_LAUNCH(4); PEER_LAUNCH(5); PEER_LAUNCH(6); PEER_LAUNCH(7);
         PEER_LAUNCH(8);
@@ -461,9 +485,12 @@ extern "C" int lg_peer_reduce_adam_mc(int rank, int world, const void* mc_grad, 
     if (rc != LG_OK) return rc;
     long long lo4, hi4;
     shard_of(n / 4, rank, world, &lo4, &hi4);
+    unsigned* status = nullptr;
+    rc = peer_status_word(&status);
+    if (rc != LG_OK) return rc;
     peer_reduce_adam_mc_kernel<<<peer_grid(hi4 - lo4), 256, 0, stream>>>((const float4*)mc_grad, (float4*)mc_param,
                                                                         (const float4*)local_param, (float4*)exp_avg,
-                                                                        (float4*)exp_avg_sq, lo4, hi4, a);
+                                                                        (float4*)exp_avg_sq, lo4, hi4, a, status);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
@@ -477,7 +504,10 @@ extern "C" int lg_peer_allreduce_mc(int rank, int world, void* mc_grad, long lon
     if (n == 0) return LG_OK;
     long long lo4, hi4;
     shard_of(n / 4, rank, world, &lo4, &hi4);
-    peer_allreduce_mc_kernel<<<peer_grid(hi4 - lo4), 256, 0, stream>>>((float4*)mc_grad, lo4, hi4, grad_scale);
+    unsigned* status = nullptr;
+    const int rc_status = peer_status_word(&status);
+    if (rc_status != LG_OK) return rc_status;
+    peer_allreduce_mc_kernel<<<peer_grid(hi4 - lo4), 256, 0, stream>>>((float4*)mc_grad, lo4, hi4, grad_scale, status);
     LG_LAUNCH_CHECK(false, stream);
     return LG_OK;
 }
