@@ -287,6 +287,15 @@ def test_fused_dwt_loss_matches_reference_golden_and_oracle(name):
     _, _, _, mask = dwt_oracle.lgdwt_losses(torch.from_numpy(pred), torch.from_numpy(gt), wts, ps, pct, w_lh, w_hl)
     if mask is not None:
         assert int(details[10]) == int(mask.sum())
+    # ELF map: the selection threshold the kernel found is the k-th smallest of the reference's own per-patch ELF means
+    # (compute_elf_map + unfold + mean, stored by make_dwt_golden.py), and the selected count follows from it
+    if name + "/patch_elf_means" in gold.files:
+        means = gold[name + "/patch_elf_means"].astype(np.float64)
+        k = min(max(1, int(means.size * (1.0 - pct))), means.size)
+        thr = np.sort(means)[k - 1]
+        assert abs(float(details[11]) - thr) <= 2e-5 * abs(thr), (float(details[11]), thr)
+        margin = np.abs(means - thr) > 1e-5 * abs(thr)      # patches not within rounding of the threshold
+        assert int((means[margin] >= thr).sum()) <= int(details[10]) <= int((means[margin] >= thr).sum() + (~margin).sum())
 
 
 @pytest.mark.parametrize("name", list(golden_inputs.PHOTOMETRIC_CASES))

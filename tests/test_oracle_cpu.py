@@ -126,6 +126,12 @@ def test_dwt_oracle_matches_reference_loss_utils(name):
     np.testing.assert_allclose(float(patch), gold[name + "/patch_loss"], rtol=1e-6, atol=1e-12)
     (g_dwt * dwt + g_patch * patch).backward()
     np.testing.assert_allclose(p.grad.numpy()[:, ::3, ::5], gold[name + "/grad_sub"], atol=1e-9, rtol=1e-5)
+    # the ELF map itself (compute_elf_map, LG/utils/loss_utils.py:336-366) and its per-patch means, not only what follows
+    elf = dwt_oracle.compute_elf_map(torch.from_numpy(gt).unsqueeze(0))
+    np.testing.assert_allclose(float(elf.mean()), gold[name + "/elf_mean"], rtol=1e-6)
+    if name + "/patch_elf_means" in gold.files:
+        means = dwt_oracle.patch_selection(elf, ps, float(pct))[2].view(-1).numpy()
+        np.testing.assert_allclose(means, gold[name + "/patch_elf_means"], rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", list(golden_inputs.PHOTOMETRIC_CASES))
