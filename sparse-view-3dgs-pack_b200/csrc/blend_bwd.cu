@@ -22,7 +22,7 @@ namespace lg {
 #endif
 
 #ifndef BWD_BATCH
-#define BWD_BATCH 512  // list entries staged per round (a multiple of the 256 threads)
+#define BWD_BATCH 256  // list entries staged per round (a multiple of the 256 threads; 512: 315 vs 307 us)
 #endif
 #define LG_REC 12  // floats per packed gradient record: mean2D.xy, conic.xyw, opacity, invdepth, colour[C], pad
 
